@@ -1,0 +1,44 @@
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+RES = os.path.join(ROOT, "rusty_sr_b200", "res")
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a real B200 (run with -m gpu under gpurun)")
+
+
+def load_png(name):
+    from PIL import Image
+    return np.asarray(Image.open(os.path.join(GOLDEN, name + ".png")))
+
+
+@pytest.fixture(scope="session")
+def weights():
+    """The three bundled parameter sets (reference src/res/*.rsr, main.rs:26-28)."""
+    from oracle import oracle as O
+    out = {}
+    for k in ("imagenet", "imagenetlinear", "anime"):
+        with open(os.path.join(RES, k + ".rsr"), "rb") as fh:
+            out[k] = O.decode_rsr(fh.read())
+    return out
+
+
+def synthetic_kat_image(H=16, W=20):
+    """x[h,w,c] = ((31h + 17w + 7c) mod 256) / 255."""
+    h, w, c = np.meshgrid(np.arange(H), np.arange(W), np.arange(3), indexing="ij")
+    return (((31 * h + 17 * w + 7 * c) % 256) / 255).astype(np.float32)
+
+
+def noise_image(H, W, seed):
+    """Uniform-random u8 RGB as f32 /255."""
+    rng = np.random.default_rng(seed)
+    return (rng.integers(0, 256, size=(H, W, 3), dtype=np.uint8).astype(np.float32) / 255.0)
