@@ -1,0 +1,117 @@
+/*
+ * rsr_b200.h — C ABI of the B200-native rusty_sr forward path (librsr_b200.so).
+ *
+ * Drop-in boundary: the single call `graph.forward(1, vec![input], &params).remove(0)` at
+ * reference src/main.rs:171, with the graph built by `sr_net(FACTOR, None)`
+ * (src/network.rs:16-109, src/main.rs:138,146,149,152).  Everything the reference does on
+ * either side of that call (clap CLI, .rsr decode, image decode/encode) stays host-side.
+ *
+ * Plain pointers and sizes only.  All functions return 0 on success and a negative RSR_E_*
+ * code on failure (the reference panics instead: main.rs:134-138,162,164,175); the message is
+ * available from rsr_last_error().  A context is bound to one GPU and is not thread-safe
+ * (the reference's Graph is `&mut self`, main.rs:133,171).  There is no CPU fallback.
+ */
+#ifndef RSR_B200_H
+#define RSR_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct rsr_ctx rsr_ctx;
+
+enum {
+    RSR_OK = 0,
+    RSR_E_PARAM_COUNT = -1, /* params.len() != graph.num_params()            (main.rs:162) */
+    RSR_E_BAD_ARG = -2,     /* null pointer, non-positive dims, bad channels/factor        */
+    RSR_E_CUDA = -3,        /* CUDA runtime / driver error, no device, kernel fault        */
+    RSR_E_OOM = -4,         /* device or host allocation failed                            */
+    RSR_E_UNSUPPORTED = -5  /* valid request this build does not implement                 */
+};
+
+/* Flags for rsr_create. */
+enum {
+    RSR_FLAG_NONE = 0
+};
+
+/* graph.num_params() of sr_net(factor, None): 130459 for factor 3 (main.rs:162; layout in
+ * network.rs:27-76 op-registration order).  Returns 0 for an unsupported factor. */
+size_t rsr_num_params(int factor);
+
+/* Builds the device-side network from the flat parameter vector the reference passes as
+ * `&params` (decoded .rsr, main.rs:138-152): copies, splits to bf16 hi/mid and repacks the
+ * weights once.  The caller keeps ownership of `params`.  `device` is a CUDA ordinal.
+ * Returns NULL on failure (see rsr_last_error / rsr_last_error_code). */
+rsr_ctx* rsr_create(const float* params, size_t n_params, int factor, int device, int flags);
+void rsr_destroy(rsr_ctx* ctx);
+
+/* upscale, f32 in / f32 out — the exact tensor contract of graph.forward (main.rs:168-171):
+ * in  : host [h][w][3] f32, sRGB-encoded 0..1 (what img_to_data produces, main.rs:170)
+ * out : host [factor*h][factor*w][3] f32, NOT clamped (clamping is data_to_img's job). */
+int rsr_upscale_f32(rsr_ctx* ctx, const float* in_hwc3, int w, int h, float* out_hwc3);
+
+/* upscale with the reference's image<->tensor mapping fused on the device
+ * (img_to_data main.rs:170: v = u8/255, alpha dropped; data_to_img(..).to_rgba() main.rs:175:
+ * round(clamp(v,0,1)*255), alpha = 255).
+ * in  : host [h][w][in_channels] u8, in_channels 3 (RGB) or 4 (RGBA)
+ * out : host [factor*h][factor*w][4] u8 RGBA. */
+int rsr_upscale_u8(rsr_ctx* ctx, const uint8_t* in, int w, int h, int in_channels, uint8_t* out_rgba);
+
+/* Batches of n equally sized images, contiguous [n][h][w][c] (image-batch sharding unit). */
+int rsr_upscale_batch_f32(rsr_ctx* ctx, const float* in, int n, int w, int h, float* out);
+int rsr_upscale_batch_u8(rsr_ctx* ctx, const uint8_t* in, int n, int w, int h, int in_channels,
+                         uint8_t* out_rgba);
+
+/* Device-resident variants: `d_in` / `d_out` are device pointers on the context's GPU; the work
+ * is enqueued on the context's stream and NOT synchronised (use rsr_synchronize).  Exactly one
+ * of d_out_f32 / d_out_rgba may be non-null per call; in_channels is 3 or 4 for u8 input. */
+int rsr_upscale_device_f32(rsr_ctx* ctx, const float* d_in, int n, int w, int h, float* d_out_f32,
+                           uint8_t* d_out_rgba);
+int rsr_upscale_device_u8(rsr_ctx* ctx, const uint8_t* d_in, int n, int w, int h, int in_channels,
+                          float* d_out_f32, uint8_t* d_out_rgba);
+int rsr_synchronize(rsr_ctx* ctx);
+
+/* Spatial-band entry point for sharding one large frame across GPUs (scheme
+ * "overlap-recompute"): `in` holds rows [band_y0 - top_halo, band_y1 + bottom_halo) of a frame,
+ * where the halos are min(7, rows available) — 7 = receptive field of the net.  Writes the
+ * factor*(band_y1-band_y0) output rows of the band to `out`.  Rows of `in` beyond the halo
+ * are not needed; image edges are zero padded exactly as in the unsharded frame. */
+int rsr_upscale_band_f32(rsr_ctx* ctx, const float* in_rows, int w, int rows_in, int top_halo,
+                         int bottom_halo, float* out_rows);
+
+/* Use an externally created CUDA stream (cudaStream_t passed as void*) instead of the
+ * context's own; NULL restores the internal stream. */
+int rsr_set_stream(rsr_ctx* ctx, void* cuda_stream);
+
+/* Per-kernel device times (ms, CUDA events on the launching stream) of the most recent call,
+ * in launch order: pack, conv0, conv1|2|3, conv5|6|7, conv8|9, conv10+expand.  Synchronises.
+ * Returns the number of entries written (<= cap) or a negative error. */
+int rsr_last_kernel_times(rsr_ctx* ctx, float* ms, int cap);
+/* Names matching rsr_last_kernel_times entries. */
+const char* rsr_kernel_name(int index);
+/* Number of kernel launches issued by the most recent call. */
+int rsr_last_launch_count(rsr_ctx* ctx);
+
+/* Test hooks (used by tests/ to localise a parity failure to one launch; not needed by a host
+ * integration).  rsr_debug_stop_after(k): subsequent calls stop after launch index k (see
+ * rsr_kernel_name; negative = run everything; outputs are then not written).  rsr_debug_read_node
+ * copies one workspace buffer of the most recent call to the host as f32 [n*h*w][32]:
+ * which = 0: activation buffer A (f, later l2), 1: activation buffer B (l1, later l3),
+ *         2: partial buffer A (conv2(f), later expand), 3: partial buffer B (l3_conv partial). */
+int rsr_debug_stop_after(rsr_ctx* ctx, int launch_index);
+int rsr_debug_read_node(rsr_ctx* ctx, int which, float* out, size_t n_pixels);
+
+/* Thread-local description of the last failure in this thread ("" if none). */
+const char* rsr_last_error(void);
+int rsr_last_error_code(void);
+
+/* Build identification, e.g. "rsr_b200 0.1 sm_100a". */
+const char* rsr_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RSR_B200_H */

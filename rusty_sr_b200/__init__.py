@@ -1,0 +1,178 @@
+"""rusty_sr_b200 — B200-native forward path of millardjn/rusty_sr's super-resolution net.
+
+Host-side mirror of the reference's `upscale()` (src/main.rs:130-178): pick parameters
+(`-p imagenet|imagenetlinear|anime`, `-c FILE.rsr`), decode the .rsr blob, map the image to
+the tensor `graph.forward` takes, run the forward pass, map back.  The forward pass itself is
+the C-ABI library `lib/librsr_b200.so` (hand-written sm_100a kernels; include/rsr_b200.h).
+There is no CPU fallback: importing works anywhere, running needs a B200.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from typing import Optional
+
+import numpy as np
+
+from . import _lib
+from ._lib import RsrError
+from .network import FACTOR, num_params, param_layout
+from .rsr_format import decode_rsr, encode_rsr
+
+__all__ = ["Upscaler", "upscale", "load_builtin_params", "decode_rsr", "encode_rsr", "RsrError",
+           "num_params", "param_layout", "FACTOR", "BUILTIN_PARAMETERS"]
+
+_RES = os.path.join(os.path.dirname(os.path.abspath(__file__)), "res")
+
+# main.rs:26-28 include_bytes!("res/*.rsr"); `-p` possible values main.rs:55
+BUILTIN_PARAMETERS = ("imagenet", "imagenetlinear", "anime")
+
+
+def load_builtin_params(name: str = "imagenet") -> np.ndarray:
+    """The parameter vectors the reference embeds (main.rs:143-152; default imagenet :144)."""
+    if name not in BUILTIN_PARAMETERS:
+        raise ValueError(f"unknown built-in parameters {name!r}; choose from {BUILTIN_PARAMETERS}")
+    with open(os.path.join(_RES, name + ".rsr"), "rb") as fh:
+        return decode_rsr(fh.read())
+
+
+def _as_ptr(a: np.ndarray) -> ctypes.c_void_p:
+    return ctypes.c_void_p(a.ctypes.data)
+
+
+class Upscaler:
+    """One network instance bound to one GPU (the reference's `(params, graph)` pair,
+    main.rs:133-158).  Not thread-safe, like the reference's `&mut Graph`."""
+
+    def __init__(self, params: Optional[np.ndarray] = None, parameters: str = "imagenet",
+                 factor: int = FACTOR, device: int = 0):
+        if params is None:
+            params = load_builtin_params(parameters)
+        params = np.ascontiguousarray(params, dtype=np.float32).ravel()
+        self._L = _lib.load()
+        self.factor = factor
+        self.device = device
+        self.n_params = int(params.size)
+        h = self._L.rsr_create(params.ctypes.data_as(ctypes.POINTER(ctypes.c_float)), params.size,
+                               factor, device, 0)
+        if not h:
+            code = self._L.rsr_last_error_code()
+            msg = self._L.rsr_last_error().decode("utf-8", "replace")
+            if code == _lib.RSR_E_PARAM_COUNT:
+                # the reference's assert_eq! message (main.rs:162)
+                raise ValueError(msg)
+            raise RsrError(code, msg)
+        self._h = ctypes.c_void_p(h)
+
+    # -- lifetime -------------------------------------------------------------------------
+    def close(self) -> None:
+        if getattr(self, "_h", None):
+            self._L.rsr_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    # -- graph.forward --------------------------------------------------------------------
+    def forward(self, x_hwc3: np.ndarray) -> np.ndarray:
+        """graph.forward(1, vec![input], &params).remove(0) (main.rs:171).
+        x: f32 [H][W][3] (or [N][H][W][3]) sRGB 0..1 -> f32 [fH][fW][3], not clamped."""
+        x = np.ascontiguousarray(x_hwc3, dtype=np.float32)
+        if x.ndim == 3:
+            if x.shape[2] != 3:
+                raise ValueError("expected [H][W][3]")
+            H, W = x.shape[:2]
+            out = np.empty((H * self.factor, W * self.factor, 3), np.float32)
+            _lib.check(self._L.rsr_upscale_f32(self._h, _as_ptr(x), W, H, _as_ptr(out)))
+            return out
+        if x.ndim == 4 and x.shape[3] == 3:
+            N, H, W = x.shape[:3]
+            out = np.empty((N, H * self.factor, W * self.factor, 3), np.float32)
+            _lib.check(self._L.rsr_upscale_batch_f32(self._h, _as_ptr(x), N, W, H, _as_ptr(out)))
+            return out
+        raise ValueError("expected [H][W][3] or [N][H][W][3]")
+
+    def forward_u8(self, img: np.ndarray) -> np.ndarray:
+        """img_to_data -> forward -> data_to_img(..).to_rgba() fused on the device
+        (main.rs:170-175).  img: u8 [H][W][3|4] or [N][H][W][3|4] -> u8 RGBA [.., fH, fW, 4]."""
+        a = np.ascontiguousarray(img, dtype=np.uint8)
+        if a.ndim == 3:
+            H, W, C = a.shape
+            out = np.empty((H * self.factor, W * self.factor, 4), np.uint8)
+            _lib.check(self._L.rsr_upscale_u8(self._h, _as_ptr(a), W, H, C, _as_ptr(out)))
+            return out
+        if a.ndim == 4:
+            N, H, W, C = a.shape
+            out = np.empty((N, H * self.factor, W * self.factor, 4), np.uint8)
+            _lib.check(self._L.rsr_upscale_batch_u8(self._h, _as_ptr(a), N, W, H, C, _as_ptr(out)))
+            return out
+        raise ValueError("expected [H][W][C] or [N][H][W][C]")
+
+    def forward_band(self, rows: np.ndarray, top_halo: int, bottom_halo: int) -> np.ndarray:
+        """One horizontal band of a larger frame (spatial sharding, overlap-recompute)."""
+        x = np.ascontiguousarray(rows, dtype=np.float32)
+        H, W = x.shape[:2]
+        out = np.empty(((H - top_halo - bottom_halo) * self.factor, W * self.factor, 3), np.float32)
+        _lib.check(self._L.rsr_upscale_band_f32(self._h, _as_ptr(x), W, H, top_halo, bottom_halo,
+                                                _as_ptr(out)))
+        return out
+
+    # -- device-resident entry points (raw device pointers as ints) ------------------------
+    def forward_device(self, d_in: int, n: int, w: int, h: int, d_out_f32: int = 0,
+                       d_out_rgba: int = 0, u8_channels: int = 0) -> None:
+        if u8_channels:
+            rc = self._L.rsr_upscale_device_u8(self._h, ctypes.c_void_p(d_in), n, w, h, u8_channels,
+                                               ctypes.c_void_p(d_out_f32 or None),
+                                               ctypes.c_void_p(d_out_rgba or None))
+        else:
+            rc = self._L.rsr_upscale_device_f32(self._h, ctypes.c_void_p(d_in), n, w, h,
+                                                ctypes.c_void_p(d_out_f32 or None),
+                                                ctypes.c_void_p(d_out_rgba or None))
+        _lib.check(rc)
+
+    def set_stream(self, cuda_stream: int) -> None:
+        _lib.check(self._L.rsr_set_stream(self._h, ctypes.c_void_p(cuda_stream or None)))
+
+    def synchronize(self) -> None:
+        _lib.check(self._L.rsr_synchronize(self._h))
+
+    def last_kernel_times_ms(self) -> dict:
+        buf = (ctypes.c_float * 16)()
+        n = self._L.rsr_last_kernel_times(self._h, buf, 16)
+        if n < 0:
+            _lib.check(n)
+        return {self._L.rsr_kernel_name(i).decode(): float(buf[i]) for i in range(n)}
+
+    # -- test hooks (tests/ only) ----------------------------------------------------------
+    def debug_stop_after(self, launch_index: int) -> None:
+        _lib.check(self._L.rsr_debug_stop_after(self._h, launch_index))
+
+    def debug_read_node(self, which: int, n_pixels: int) -> np.ndarray:
+        out = np.empty((n_pixels, 32), np.float32)
+        _lib.check(self._L.rsr_debug_read_node(self._h, which, _as_ptr(out), n_pixels))
+        return out
+
+    def last_launch_count(self) -> int:
+        return int(self._L.rsr_last_launch_count(self._h))
+
+
+def upscale(input_image: np.ndarray, parameters: str = "imagenet", custom: Optional[str] = None,
+            device: int = 0) -> np.ndarray:
+    """The reference's upscale(input_image) -> output_image (main.rs:130-178) for the neural
+    modes: u8 RGB/RGBA image in, u8 RGBA image out (3x).  `custom` is a .rsr path (`-c`)."""
+    if custom is not None:
+        with open(custom, "rb") as fh:  # "Error opening parameter file" main.rs:134
+            params = decode_rsr(fh.read())
+    else:
+        params = load_builtin_params(parameters)
+    with Upscaler(params, device=device) as up:
+        return up.forward_u8(input_image)

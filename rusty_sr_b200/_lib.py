@@ -1,0 +1,84 @@
+"""ctypes binding of librsr_b200.so (include/rsr_b200.h).  Fails loudly if the CUDA library is
+missing: there is no CPU or PyTorch fallback anywhere in this package."""
+from __future__ import annotations
+
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "librsr_b200.so")
+
+RSR_OK = 0
+RSR_E_PARAM_COUNT = -1
+RSR_E_BAD_ARG = -2
+RSR_E_CUDA = -3
+RSR_E_OOM = -4
+RSR_E_UNSUPPORTED = -5
+
+# every symbol include/rsr_b200.h declares (checked by tests/test_abi.py)
+EXPORTS = (
+    "rsr_num_params", "rsr_create", "rsr_destroy", "rsr_upscale_f32", "rsr_upscale_u8",
+    "rsr_upscale_batch_f32", "rsr_upscale_batch_u8", "rsr_upscale_device_f32",
+    "rsr_upscale_device_u8", "rsr_synchronize", "rsr_upscale_band_f32", "rsr_set_stream",
+    "rsr_last_kernel_times", "rsr_kernel_name", "rsr_last_launch_count", "rsr_last_error",
+    "rsr_last_error_code", "rsr_version", "rsr_debug_stop_after", "rsr_debug_read_node",
+)
+
+_lib = None
+
+
+class RsrError(RuntimeError):
+    def __init__(self, code: int, message: str):
+        super().__init__(f"rsr_b200 error {code}: {message}")
+        self.code = code
+
+
+def load() -> ctypes.CDLL:
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} not built. Run `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(or `make -C rusty_sr_b200/csrc`). rusty_sr_b200 has no CPU fallback.")
+    L = ctypes.CDLL(LIB_PATH)
+    vp, fp, u8p, ci = ctypes.c_void_p, ctypes.POINTER(ctypes.c_float), ctypes.c_void_p, ctypes.c_int
+    L.rsr_num_params.restype = ctypes.c_size_t
+    L.rsr_num_params.argtypes = [ci]
+    L.rsr_create.restype = vp
+    L.rsr_create.argtypes = [fp, ctypes.c_size_t, ci, ci, ci]
+    L.rsr_destroy.restype = None
+    L.rsr_destroy.argtypes = [vp]
+    L.rsr_upscale_f32.argtypes = [vp, vp, ci, ci, vp]
+    L.rsr_upscale_u8.argtypes = [vp, u8p, ci, ci, ci, u8p]
+    L.rsr_upscale_batch_f32.argtypes = [vp, vp, ci, ci, ci, vp]
+    L.rsr_upscale_batch_u8.argtypes = [vp, u8p, ci, ci, ci, ci, u8p]
+    L.rsr_upscale_device_f32.argtypes = [vp, vp, ci, ci, ci, vp, vp]
+    L.rsr_upscale_device_u8.argtypes = [vp, vp, ci, ci, ci, ci, vp, vp]
+    L.rsr_synchronize.argtypes = [vp]
+    L.rsr_upscale_band_f32.argtypes = [vp, vp, ci, ci, ci, ci, vp]
+    L.rsr_set_stream.argtypes = [vp, vp]
+    L.rsr_last_kernel_times.argtypes = [vp, fp, ci]
+    L.rsr_kernel_name.restype = ctypes.c_char_p
+    L.rsr_kernel_name.argtypes = [ci]
+    L.rsr_last_launch_count.argtypes = [vp]
+    L.rsr_last_error.restype = ctypes.c_char_p
+    L.rsr_last_error_code.restype = ci
+    L.rsr_version.restype = ctypes.c_char_p
+    L.rsr_debug_stop_after.argtypes = [vp, ci]
+    L.rsr_debug_stop_after.restype = ci
+    L.rsr_debug_read_node.argtypes = [vp, ci, vp, ctypes.c_size_t]
+    L.rsr_debug_read_node.restype = ci
+    for name in ("rsr_upscale_f32", "rsr_upscale_u8", "rsr_upscale_batch_f32", "rsr_upscale_batch_u8",
+                 "rsr_upscale_device_f32", "rsr_upscale_device_u8", "rsr_synchronize",
+                 "rsr_upscale_band_f32", "rsr_set_stream", "rsr_last_kernel_times",
+                 "rsr_last_launch_count"):
+        getattr(L, name).restype = ci
+    _lib = L
+    return L
+
+
+def check(rc: int) -> None:
+    if rc != 0:
+        L = load()
+        raise RsrError(rc, L.rsr_last_error().decode("utf-8", "replace"))

@@ -1,0 +1,620 @@
+// rsr_b200.cu — C-ABI library (include/rsr_b200.h) over the sm_100a kernels.
+//
+// Host side of the drop-in boundary `graph.forward(1, vec![input], &params)` (reference
+// src/main.rs:171): parameter-vector layout of sr_net (src/network.rs:27-76), weight split +
+// repack, workspace management, TMA tensor maps, the launch sequence and error mapping.
+// No CPU fallback: every entry point fails with RSR_E_CUDA if no sm_100 device is usable.
+#include <cudaTypedefs.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "../../include/rsr_b200.h"
+#include "conv_strip.cuh"
+
+using namespace rsr;
+
+// ------------------------------------------------------------------------------------ errors
+static thread_local std::string g_err;
+static thread_local int g_err_code = 0;
+
+static int fail(int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    g_err_code = code;
+    return code;
+}
+#define CUDA_TRY(expr)                                                                         \
+    do {                                                                                       \
+        cudaError_t e__ = (expr);                                                              \
+        if (e__ != cudaSuccess)                                                                \
+            return fail(e__ == cudaErrorMemoryAllocation ? RSR_E_OOM : RSR_E_CUDA, "%s: %s (%s:%d)", #expr, \
+                        cudaGetErrorString(e__), __FILE__, __LINE__);                          \
+    } while (0)
+
+// --------------------------------------------------------------- parameter layout (network.rs)
+// Order = order in which ops are added to the graph (network.rs:27-76): LinearInterp (no
+// params) then the `ops` vec.  Conv kernels are [Cout][Kh][Kw][Cin].
+struct Layout {
+    size_t conv0, f_bias, f_activ, expand_bias, l1_bias, l2_bias, l3_bias, l1_activ, l2_activ, l3_activ;
+    size_t conv1, conv2, conv3, conv5, conv6, conv7, conv8, conv9, conv10, total;
+    int ce;
+};
+static Layout make_layout(int factor) {
+    Layout L{};
+    size_t o = 0;
+    L.ce = 3 * factor * factor;                       // network.rs:37
+    L.conv0 = o;       o += 32 * 5 * 5 * 3;           // :33
+    L.f_bias = o;      o += 32;                       // :34
+    L.f_activ = o;     o += 32;                       // :35
+    L.expand_bias = o; o += L.ce;                     // :38
+    L.l1_bias = o;     o += 32;                       // :50
+    L.l2_bias = o;     o += 32;                       // :51
+    L.l3_bias = o;     o += 32;                       // :52
+    L.l1_activ = o;    o += 32;                       // :54
+    L.l2_activ = o;    o += 32;                       // :55
+    L.l3_activ = o;    o += 32;                       // :56
+    L.conv1 = o;       o += 32 * 25 * 32;             // :60
+    L.conv2 = o;       o += 32 * 25 * 32;             // :61
+    L.conv3 = o;       o += 32 * 25 * 32;             // :62
+    L.conv5 = o;       o += 32 * 9 * 32;              // :65
+    L.conv6 = o;       o += 32 * 9 * 32;              // :66
+    L.conv7 = o;       o += (size_t)L.ce * 9 * 32;    // :67
+    L.conv8 = o;       o += 32 * 9 * 32;              // :69
+    L.conv9 = o;       o += (size_t)L.ce * 9 * 32;    // :70
+    L.conv10 = o;      o += (size_t)L.ce * 9 * 32;    // :72
+    L.total = o;
+    return L;
+}
+
+// --------------------------------------------------------------------------- kernel configs
+using Cfg0 = ConvCfg<5, 1, 64, 1, 4>;    // conv0 on the x-im2col'd input (K = 5 taps x 16)
+using Cfg1 = ConvCfg<5, 5, 128, 3, 2>;   // f  -> conv1 | conv2 | conv3
+using Cfg2 = ConvCfg<3, 3, 128, 3, 2>;   // l1 -> conv5 | conv6 | conv7
+using Cfg3 = ConvCfg<3, 3, 128, 2, 4>;   // l2 -> conv8 | conv9
+using Cfg4 = ConvCfg<3, 3, 128, 1, 4>;   // l3 -> conv10 (+ expand + bilinear skip)
+
+enum { K_PACK = 0, K_CONV0, K_F, K_L1, K_L2, K_L3, K_COUNT };
+static const char* kKernelNames[K_COUNT] = {"pack_input", "conv0", "conv1|2|3", "conv5|6|7", "conv8|9",
+                                            "conv10+expand+skip"};
+
+// ------------------------------------------------------------------------------ pack kernel
+// img_to_data (main.rs:170) fused with the layout change conv0 needs: for every pixel the 5
+// horizontal neighbours x-2..x+2 (zero outside the image = Padding::Same) x 3 channels become
+// one 16-element K chunk (15 used), stored split as bf16 hi | mid = 64 B per pixel.  Also keeps
+// the pixel as a float4 for the bilinear skip of the last kernel.
+template <bool U8>
+__global__ void __launch_bounds__(256) pack_input_kernel(const void* __restrict__ in, int in_ch, int W, int H,
+                                                          int NIMG, __nv_bfloat16* __restrict__ xcol,
+                                                          float4* __restrict__ xf4) {
+    const size_t npx = (size_t)NIMG * H * W;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < npx; i += (size_t)gridDim.x * blockDim.x) {
+        const int x = (int)(i % W);
+        const size_t rowbase = i - x;  // (img*H + y) * W
+        float v[16];
+        #pragma unroll
+        for (int d = 0; d < 5; ++d) {
+            const int xx = x + d - 2;
+            const bool ok = xx >= 0 && xx < W;
+            #pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                float t = 0.f;
+                if (ok) {
+                    if (U8) t = (float)reinterpret_cast<const uint8_t*>(in)[(rowbase + xx) * in_ch + c] / 255.0f;
+                    else    t = reinterpret_cast<const float*>(in)[(rowbase + xx) * 3 + c];
+                }
+                v[d * 3 + c] = t;
+            }
+        }
+        v[15] = 0.f;
+        uint32_t hi[8], mid[8];
+        #pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const __nv_bfloat16 h0 = __float2bfloat16_rn(v[2 * k]), h1 = __float2bfloat16_rn(v[2 * k + 1]);
+            const __nv_bfloat16 m0 = __float2bfloat16_rn(v[2 * k] - __bfloat162float(h0));
+            const __nv_bfloat16 m1 = __float2bfloat16_rn(v[2 * k + 1] - __bfloat162float(h1));
+            hi[k] = pack_bf16x2(h0, h1);
+            mid[k] = pack_bf16x2(m0, m1);
+        }
+        uint4* dst = reinterpret_cast<uint4*>(xcol + i * 32);
+        dst[0] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+        dst[1] = make_uint4(hi[4], hi[5], hi[6], hi[7]);
+        dst[2] = make_uint4(mid[0], mid[1], mid[2], mid[3]);
+        dst[3] = make_uint4(mid[4], mid[5], mid[6], mid[7]);
+        xf4[i] = make_float4(v[6], v[7], v[8], 0.f);  // d = 2 is the pixel itself
+    }
+}
+
+// ---------------------------------------------------------------------------------- context
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+};
+
+struct rsr_ctx {
+    int device = 0, factor = 3, num_sms = 148;
+    Layout L{};
+    cudaStream_t own_stream = nullptr, stream = nullptr;
+    // packed weights (bf16 hi|mid), biases / slopes (32 floats each, zero padded)
+    __nv_bfloat16 *w0 = nullptr, *w1 = nullptr, *w2 = nullptr, *w3 = nullptr, *w4 = nullptr;
+    float* vecs = nullptr;  // 9 x 32 floats: f_bias f_activ l1_bias l1_activ l2_bias l2_activ l3_bias l3_activ expand_bias
+    // workspace
+    DevBuf xcol, xf4, actA, actB, partA, partB, out_f32, out_u8, in_stage;
+    int* fault = nullptr;
+    cudaEvent_t ev[K_COUNT + 1] = {};
+    bool timed = false;
+    int last_launches = 0;
+    int stop_after = -1;  // test hook
+    PFN_cuTensorMapEncodeTiled_v12000 encode = nullptr;
+};
+
+static int ensure(DevBuf& b, size_t bytes) {
+    if (bytes <= b.cap) return 0;
+    if (b.p) cudaFree(b.p);
+    b.p = nullptr;
+    b.cap = 0;
+    cudaError_t e = cudaMalloc(&b.p, bytes);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return fail(RSR_E_OOM, "cudaMalloc(%zu bytes) failed: %s", bytes, cudaGetErrorString(e));
+    }
+    b.cap = bytes;
+    return 0;
+}
+static void release(DevBuf& b) {
+    if (b.p) cudaFree(b.p);
+    b.p = nullptr;
+    b.cap = 0;
+}
+
+static inline void split_bf16(float w, __nv_bfloat16& hi, __nv_bfloat16& mid) {
+    hi = __float2bfloat16_rn(w);
+    mid = __float2bfloat16_rn(w - __bfloat162float(hi));
+}
+
+// Packs the convolutions that read one input node into the per-tap B tiles of the kernel:
+// out[t][n][0..31] = hi(w[n][t][ci]), out[t][n][32..63] = mid(...); n runs over the listed
+// convolutions, each padded to 32 output channels with zero rows.
+static void pack_group(const float* params, const size_t* offs, const int* couts, int nconv, int K,
+                       std::vector<__nv_bfloat16>& out) {
+    const int taps = K * K, ncol = 32 * nconv;
+    out.assign((size_t)taps * ncol * 64, __float2bfloat16_rn(0.f));
+    for (int g = 0; g < nconv; ++g)
+        for (int o = 0; o < couts[g]; ++o)
+            for (int t = 0; t < taps; ++t)
+                for (int ci = 0; ci < 32; ++ci) {
+                    const float w = params[offs[g] + ((size_t)o * taps + t) * 32 + ci];
+                    __nv_bfloat16 h, m;
+                    split_bf16(w, h, m);
+                    const size_t row = ((size_t)t * ncol + g * 32 + o) * 64;
+                    out[row + ci] = h;
+                    out[row + 32 + ci] = m;
+                }
+}
+
+extern "C" size_t rsr_num_params(int factor) {
+    if (factor < 1 || factor > 4) return 0;
+    return make_layout(factor).total;
+}
+
+extern "C" const char* rsr_last_error(void) { return g_err.c_str(); }
+extern "C" int rsr_last_error_code(void) { return g_err_code; }
+extern "C" const char* rsr_version(void) { return "rsr_b200 0.1 sm_100a (tcgen05 bf16x3 implicit-GEMM)"; }
+extern "C" const char* rsr_kernel_name(int i) { return (i >= 0 && i < K_COUNT) ? kKernelNames[i] : ""; }
+
+extern "C" void rsr_destroy(rsr_ctx* c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    cudaFree(c->w0); cudaFree(c->w1); cudaFree(c->w2); cudaFree(c->w3); cudaFree(c->w4);
+    cudaFree(c->vecs); cudaFree(c->fault);
+    release(c->xcol); release(c->xf4); release(c->actA); release(c->actB); release(c->partA);
+    release(c->partB); release(c->out_f32); release(c->out_u8); release(c->in_stage);
+    for (auto& e : c->ev) if (e) cudaEventDestroy(e);
+    if (c->own_stream) cudaStreamDestroy(c->own_stream);
+    delete c;
+}
+
+template <class T>
+static int upload(T** dst, const void* src, size_t bytes) {
+    CUDA_TRY(cudaMalloc((void**)dst, bytes));
+    CUDA_TRY(cudaMemcpy(*dst, src, bytes, cudaMemcpyHostToDevice));
+    return 0;
+}
+
+static int create_impl(rsr_ctx* c, const float* params) {
+    const Layout& L = c->L;
+    CUDA_TRY(cudaSetDevice(c->device));
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, c->device));
+    if (prop.major != 10)
+        return fail(RSR_E_CUDA, "device %d is sm_%d%d; this library contains sm_100a code only (no fallback)",
+                    c->device, prop.major, prop.minor);
+    c->num_sms = prop.multiProcessorCount;
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    CUDA_TRY(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+    if (qres != cudaDriverEntryPointSuccess || !fn) return fail(RSR_E_CUDA, "driver lacks cuTensorMapEncodeTiled");
+    c->encode = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(fn);
+    CUDA_TRY(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
+    c->stream = c->own_stream;
+    for (auto& e : c->ev) CUDA_TRY(cudaEventCreate(&e));
+    CUDA_TRY(cudaMalloc((void**)&c->fault, sizeof(int)));
+    CUDA_TRY(cudaMemset(c->fault, 0, sizeof(int)));
+
+    // conv0: [32][5][5][3] -> w0[a][n][k = dxi*3 + c | 16 + k]  (x-im2col form, 64 B rows)
+    {
+        std::vector<__nv_bfloat16> w((size_t)5 * 32 * 32, __float2bfloat16_rn(0.f));
+        for (int n = 0; n < 32; ++n)
+            for (int a = 0; a < 5; ++a)
+                for (int b = 0; b < 5; ++b)
+                    for (int ch = 0; ch < 3; ++ch) {
+                        __nv_bfloat16 h, m;
+                        split_bf16(params[L.conv0 + (((size_t)n * 5 + a) * 5 + b) * 3 + ch], h, m);
+                        const size_t row = ((size_t)a * 32 + n) * 32;
+                        w[row + b * 3 + ch] = h;
+                        w[row + 16 + b * 3 + ch] = m;
+                    }
+        if (int rc = upload(&c->w0, w.data(), w.size() * 2)) return rc;
+    }
+    std::vector<__nv_bfloat16> w;
+    {
+        const size_t offs[3] = {L.conv1, L.conv2, L.conv3};
+        const int co[3] = {32, 32, 32};
+        pack_group(params, offs, co, 3, 5, w);
+        if (int rc = upload(&c->w1, w.data(), w.size() * 2)) return rc;
+    }
+    {
+        const size_t offs[3] = {L.conv5, L.conv6, L.conv7};
+        const int co[3] = {32, 32, L.ce};
+        pack_group(params, offs, co, 3, 3, w);
+        if (int rc = upload(&c->w2, w.data(), w.size() * 2)) return rc;
+    }
+    {
+        const size_t offs[2] = {L.conv8, L.conv9};
+        const int co[2] = {32, L.ce};
+        pack_group(params, offs, co, 2, 3, w);
+        if (int rc = upload(&c->w3, w.data(), w.size() * 2)) return rc;
+    }
+    {
+        const size_t offs[1] = {L.conv10};
+        const int co[1] = {L.ce};
+        pack_group(params, offs, co, 1, 3, w);
+        if (int rc = upload(&c->w4, w.data(), w.size() * 2)) return rc;
+    }
+    {
+        std::vector<float> v(9 * 32, 0.f);
+        const size_t src[9] = {L.f_bias, L.f_activ, L.l1_bias, L.l1_activ, L.l2_bias, L.l2_activ,
+                               L.l3_bias, L.l3_activ, L.expand_bias};
+        for (int i = 0; i < 9; ++i) memcpy(&v[i * 32], params + src[i], sizeof(float) * (i == 8 ? L.ce : 32));
+        if (int rc = upload(&c->vecs, v.data(), v.size() * 4)) return rc;
+    }
+    CUDA_TRY(cudaFuncSetAttribute(conv_strip_kernel<Cfg0>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg0::SMEM_BYTES));
+    CUDA_TRY(cudaFuncSetAttribute(conv_strip_kernel<Cfg1>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg1::SMEM_BYTES));
+    CUDA_TRY(cudaFuncSetAttribute(conv_strip_kernel<Cfg2>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg2::SMEM_BYTES));
+    CUDA_TRY(cudaFuncSetAttribute(conv_strip_kernel<Cfg3>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg3::SMEM_BYTES));
+    CUDA_TRY(cudaFuncSetAttribute(conv_strip_kernel<Cfg4>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg4::SMEM_BYTES));
+    return 0;
+}
+
+extern "C" rsr_ctx* rsr_create(const float* params, size_t n_params, int factor, int device, int flags) {
+    (void)flags;
+    g_err.clear();
+    g_err_code = 0;
+    if (!params) { fail(RSR_E_BAD_ARG, "params is null"); return nullptr; }
+    if (factor != 3) {
+        // the reference is compiled with FACTOR = 3 (main.rs:31) and ships factor-3 weights only
+        fail(factor >= 1 && factor <= 4 ? RSR_E_UNSUPPORTED : RSR_E_BAD_ARG,
+             "factor %d not supported by the GPU path (reference FACTOR is 3, main.rs:31)", factor);
+        return nullptr;
+    }
+    const Layout L = make_layout(factor);
+    if (n_params != L.total) {
+        fail(RSR_E_PARAM_COUNT,
+             "Parameters selected do not have the size required by the neural net (%zu given, %zu required)",
+             n_params, L.total);
+        return nullptr;
+    }
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        fail(RSR_E_CUDA, "no CUDA device available (this library has no CPU fallback)");
+        return nullptr;
+    }
+    if (device < 0 || device >= ndev) { fail(RSR_E_BAD_ARG, "device %d out of range (0..%d)", device, ndev - 1); return nullptr; }
+    rsr_ctx* c = new (std::nothrow) rsr_ctx();
+    if (!c) { fail(RSR_E_OOM, "host allocation failed"); return nullptr; }
+    c->device = device;
+    c->factor = factor;
+    c->L = L;
+    if (create_impl(c, params) != 0) {
+        const std::string keep = g_err;
+        const int code = g_err_code;
+        rsr_destroy(c);
+        g_err = keep;
+        g_err_code = code;
+        return nullptr;
+    }
+    return c;
+}
+
+extern "C" int rsr_set_stream(rsr_ctx* c, void* s) {
+    if (!c) return fail(RSR_E_BAD_ARG, "ctx is null");
+    c->stream = s ? reinterpret_cast<cudaStream_t>(s) : c->own_stream;
+    return 0;
+}
+
+extern "C" int rsr_synchronize(rsr_ctx* c) {
+    if (!c) return fail(RSR_E_BAD_ARG, "ctx is null");
+    CUDA_TRY(cudaSetDevice(c->device));
+    cudaError_t e = cudaStreamSynchronize(c->stream);
+    if (e != cudaSuccess) {
+        int f = 0;
+        cudaMemcpy(&f, c->fault, sizeof f, cudaMemcpyDeviceToHost);
+        return fail(RSR_E_CUDA, "kernel failed: %s (fault word 0x%x)", cudaGetErrorString(e), f);
+    }
+    return 0;
+}
+
+// ------------------------------------------------------------------------------ tensor maps
+static int make_map_act(rsr_ctx* c, CUtensorMap* m, const void* base, int elems, int W, int H, int N, int boxw) {
+    const cuuint64_t rb = (cuuint64_t)elems * 2;
+    cuuint64_t dims[4] = {(cuuint64_t)elems, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+    cuuint64_t strides[3] = {rb, rb * W, rb * W * H};
+    cuuint32_t box[4] = {(cuuint32_t)elems, (cuuint32_t)boxw, 1, 1};
+    cuuint32_t es[4] = {1, 1, 1, 1};
+    CUresult r = c->encode(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, es,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE,
+                           elems == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                           CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(RSR_E_CUDA, "cuTensorMapEncodeTiled(activation %dx%dx%d) failed: %d", W, H, N, (int)r);
+    return 0;
+}
+static int make_map_w(rsr_ctx* c, CUtensorMap* m, const void* base, int elems, int rows, int boxrows) {
+    const cuuint64_t rb = (cuuint64_t)elems * 2;
+    cuuint64_t dims[2] = {(cuuint64_t)elems, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {rb};
+    cuuint32_t box[2] = {(cuuint32_t)elems, (cuuint32_t)boxrows};
+    cuuint32_t es[2] = {1, 1};
+    CUresult r = c->encode(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, es,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE,
+                           elems == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                           CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(RSR_E_CUDA, "cuTensorMapEncodeTiled(weights) failed: %d", (int)r);
+    return 0;
+}
+
+// Chooses the rows-per-work-item so that the persistent grid is balanced: minimises
+// ceil(items / SMs) * (rows per item + pipeline-fill overhead).
+static void plan_items(ConvParams& p, int R, int PH, int num_sms) {
+    const int rows = p.row_end - p.row_begin;
+    p.n_strips = (p.W + 127) / 128;
+    const int per_row_items = p.NIMG * p.n_strips;
+    double best = 1e300;
+    int best_seg = ((rows + R - 1) / R) * R;
+    for (int seg = R; seg <= ((rows + R - 1) / R) * R; seg += R) {
+        const int nseg = (rows + seg - 1) / seg;
+        const long items = (long)per_row_items * nseg;
+        const long waves = (items + num_sms - 1) / num_sms;
+        const double cost = (double)waves * (seg + 0.75 * (2 * PH) + 1.0);
+        if (cost < best - 1e-9) { best = cost; best_seg = seg; }
+    }
+    p.seg_rows = best_seg;
+    p.n_segs = (rows + best_seg - 1) / best_seg;
+    p.total_items = per_row_items * p.n_segs;
+}
+
+template <class C>
+static int launch_conv(rsr_ctx* c, ConvParams& p) {
+    plan_items(p, C::R, C::PH, c->num_sms);
+    const int grid = p.total_items < c->num_sms ? p.total_items : c->num_sms;
+    conv_strip_kernel<C><<<grid, 256, C::SMEM_BYTES, c->stream>>>(p);
+    CUDA_TRY(cudaGetLastError());
+    c->last_launches++;
+    return 0;
+}
+
+// The whole forward pass on device-resident input.  in: f32 [n][h][w][3] or u8 [n][h][w][ch].
+static int forward_device(rsr_ctx* c, const void* d_in, bool u8, int in_ch, int n, int w, int h, float* d_out_f32,
+                          uint8_t* d_out_u8) {
+    if (!c) return fail(RSR_E_BAD_ARG, "ctx is null");
+    if (!d_in || (!d_out_f32 && !d_out_u8)) return fail(RSR_E_BAD_ARG, "null buffer");
+    if (n < 1 || w < 1 || h < 1) return fail(RSR_E_BAD_ARG, "bad dimensions n=%d w=%d h=%d", n, w, h);
+    if (u8 && in_ch != 3 && in_ch != 4) return fail(RSR_E_BAD_ARG, "in_channels must be 3 or 4 (got %d)", in_ch);
+    CUDA_TRY(cudaSetDevice(c->device));
+    const size_t npx = (size_t)n * w * h;
+    if (int rc = ensure(c->xcol, npx * 64)) return rc;
+    if (int rc = ensure(c->xf4, npx * 16)) return rc;
+    if (int rc = ensure(c->actA, npx * 128)) return rc;
+    if (int rc = ensure(c->actB, npx * 128)) return rc;
+    if (int rc = ensure(c->partA, npx * 128)) return rc;
+    if (int rc = ensure(c->partB, npx * 128)) return rc;
+
+    __nv_bfloat16* xcol = (__nv_bfloat16*)c->xcol.p;
+    __nv_bfloat16* f_act = (__nv_bfloat16*)c->actA.p;   // f, later l2
+    __nv_bfloat16* l1_act = (__nv_bfloat16*)c->actB.p;  // l1, later l3
+    __nv_bfloat16* l2_act = f_act;
+    __nv_bfloat16* l3_act = l1_act;
+    float* P2 = (float*)c->partA.p;  // conv2(f) partial of l2_conv; later E (expand partial)
+    float* P3 = (float*)c->partB.p;  // conv3(f) (+conv6(l1)) partial of l3_conv
+    float* E = P2;
+    const float* V = c->vecs;
+    const float *f_bias = V, *f_slope = V + 32, *l1_bias = V + 64, *l1_slope = V + 96, *l2_bias = V + 128,
+                *l2_slope = V + 160, *l3_bias = V + 192, *l3_slope = V + 224, *e_bias = V + 256;
+
+    c->last_launches = 0;
+    CUDA_TRY(cudaEventRecord(c->ev[0], c->stream));
+    {
+        const int blocks = (int)std::min<size_t>((npx + 255) / 256, (size_t)c->num_sms * 16);
+        if (u8) pack_input_kernel<true><<<blocks, 256, 0, c->stream>>>(d_in, in_ch, w, h, n, xcol, (float4*)c->xf4.p);
+        else    pack_input_kernel<false><<<blocks, 256, 0, c->stream>>>(d_in, 3, w, h, n, xcol, (float4*)c->xf4.p);
+        CUDA_TRY(cudaGetLastError());
+        c->last_launches++;
+    }
+    CUDA_TRY(cudaEventRecord(c->ev[1], c->stream));
+    if (c->stop_after == 0) return 0;
+
+    ConvParams p{};
+    p.W = w; p.H = h; p.NIMG = n; p.row_begin = 0; p.row_end = h; p.factor = c->factor; p.fault = c->fault;
+    p.xf4 = (const float4*)c->xf4.p;
+
+    // conv0: xcol -> f = BeLU(conv0(x) + f_bias)                       network.rs:33-35
+    if (int rc = make_map_act(c, &p.tmA, xcol, 32, w, h, n, Cfg0::BOXW)) return rc;
+    if (int rc = make_map_w(c, &p.tmB, c->w0, 32, 5 * 32, 32)) return rc;
+    p.grp[0] = EpiGroup{EPI_ACT, 0, nullptr, nullptr, f_act, f_bias, f_slope};
+    p.grp[1] = EpiGroup{}; p.grp[2] = EpiGroup{};
+    if (int rc = launch_conv<Cfg0>(c, p)) return rc;
+    CUDA_TRY(cudaEventRecord(c->ev[2], c->stream));
+    if (c->stop_after == 1) return 0;
+
+    // f -> l1 = BeLU(conv1(f) + l1_bias); P2 = conv2(f); P3 = conv3(f)  network.rs:60-62,50,54
+    if (int rc = make_map_act(c, &p.tmA, f_act, 64, w, h, n, Cfg1::BOXW)) return rc;
+    if (int rc = make_map_w(c, &p.tmB, c->w1, 64, 25 * 96, 96)) return rc;
+    p.grp[0] = EpiGroup{EPI_ACT, 0, nullptr, nullptr, l1_act, l1_bias, l1_slope};
+    p.grp[1] = EpiGroup{EPI_PARTIAL, 0, nullptr, P2, nullptr, nullptr, nullptr};
+    p.grp[2] = EpiGroup{EPI_PARTIAL, 0, nullptr, P3, nullptr, nullptr, nullptr};
+    if (int rc = launch_conv<Cfg1>(c, p)) return rc;
+    CUDA_TRY(cudaEventRecord(c->ev[3], c->stream));
+    if (c->stop_after == 2) return 0;
+
+    // l1 -> l2 = BeLU(P2 + conv5(l1) + l2_bias); P3 += conv6(l1); E = conv7(l1)   :65-67,51,55
+    if (int rc = make_map_act(c, &p.tmA, l1_act, 64, w, h, n, Cfg2::BOXW)) return rc;
+    if (int rc = make_map_w(c, &p.tmB, c->w2, 64, 9 * 96, 96)) return rc;
+    p.grp[0] = EpiGroup{EPI_ACT, 0, P2, nullptr, l2_act, l2_bias, l2_slope};
+    p.grp[1] = EpiGroup{EPI_PARTIAL, 0, P3, P3, nullptr, nullptr, nullptr};
+    p.grp[2] = EpiGroup{EPI_PARTIAL, 0, nullptr, E, nullptr, nullptr, nullptr};
+    if (int rc = launch_conv<Cfg2>(c, p)) return rc;
+    CUDA_TRY(cudaEventRecord(c->ev[4], c->stream));
+    if (c->stop_after == 3) return 0;
+
+    // l2 -> l3 = BeLU(P3 + conv8(l2) + l3_bias); E += conv9(l2)                   :69-70,52,56
+    if (int rc = make_map_act(c, &p.tmA, l2_act, 64, w, h, n, Cfg3::BOXW)) return rc;
+    if (int rc = make_map_w(c, &p.tmB, c->w3, 64, 9 * 64, 64)) return rc;
+    p.grp[0] = EpiGroup{EPI_ACT, 0, P3, nullptr, l3_act, l3_bias, l3_slope};
+    p.grp[1] = EpiGroup{EPI_PARTIAL, 0, E, E, nullptr, nullptr, nullptr};
+    p.grp[2] = EpiGroup{};
+    if (int rc = launch_conv<Cfg3>(c, p)) return rc;
+    CUDA_TRY(cudaEventRecord(c->ev[5], c->stream));
+    if (c->stop_after == 4) return 0;
+
+    // l3 -> output = Expand(E + conv10(l3) + expand_bias) + LinearInterp(x)       :72,38-39,27
+    if (int rc = make_map_act(c, &p.tmA, l3_act, 64, w, h, n, Cfg4::BOXW)) return rc;
+    if (int rc = make_map_w(c, &p.tmB, c->w4, 64, 9 * 32, 32)) return rc;
+    p.grp[0] = EpiGroup{EPI_SHUFFLE, 0, E, nullptr, nullptr, e_bias, nullptr};
+    p.grp[1] = EpiGroup{}; p.grp[2] = EpiGroup{};
+    p.out_f32 = d_out_f32;
+    p.out_u8 = d_out_u8;
+    if (int rc = launch_conv<Cfg4>(c, p)) return rc;
+    CUDA_TRY(cudaEventRecord(c->ev[6], c->stream));
+    if (c->stop_after == 5) return 0;
+    c->timed = true;
+    return 0;
+}
+
+extern "C" int rsr_upscale_device_f32(rsr_ctx* c, const float* d_in, int n, int w, int h, float* d_out_f32,
+                                      uint8_t* d_out_rgba) {
+    return forward_device(c, d_in, false, 3, n, w, h, d_out_f32, d_out_rgba);
+}
+extern "C" int rsr_upscale_device_u8(rsr_ctx* c, const uint8_t* d_in, int n, int w, int h, int in_channels,
+                                     float* d_out_f32, uint8_t* d_out_rgba) {
+    return forward_device(c, d_in, true, in_channels, n, w, h, d_out_f32, d_out_rgba);
+}
+
+// Host-buffer entry points: H2D, forward, D2H on the context's stream, then synchronise.
+static int upscale_host(rsr_ctx* c, const void* in, bool u8, int in_ch, int n, int w, int h, float* out_f32,
+                        uint8_t* out_u8, int out_row_begin, int out_rows) {
+    if (!c) return fail(RSR_E_BAD_ARG, "ctx is null");
+    if (!in || (!out_f32 && !out_u8)) return fail(RSR_E_BAD_ARG, "null buffer");
+    if (n < 1 || w < 1 || h < 1) return fail(RSR_E_BAD_ARG, "bad dimensions n=%d w=%d h=%d", n, w, h);
+    if (u8 && in_ch != 3 && in_ch != 4) return fail(RSR_E_BAD_ARG, "in_channels must be 3 or 4 (got %d)", in_ch);
+    CUDA_TRY(cudaSetDevice(c->device));
+    const int F = c->factor;
+    const size_t npx = (size_t)n * w * h;
+    const size_t in_bytes = u8 ? npx * in_ch : npx * 3 * sizeof(float);
+    if (int rc = ensure(c->in_stage, in_bytes)) return rc;
+    CUDA_TRY(cudaMemcpyAsync(c->in_stage.p, in, in_bytes, cudaMemcpyHostToDevice, c->stream));
+    const size_t opx = npx * F * F;
+    float* d_f32 = nullptr;
+    uint8_t* d_u8 = nullptr;
+    if (out_f32) { if (int rc = ensure(c->out_f32, opx * 3 * sizeof(float))) return rc; d_f32 = (float*)c->out_f32.p; }
+    if (out_u8) { if (int rc = ensure(c->out_u8, opx * 4)) return rc; d_u8 = (uint8_t*)c->out_u8.p; }
+    if (int rc = forward_device(c, c->in_stage.p, u8, in_ch, n, w, h, d_f32, d_u8)) return rc;
+    // band mode copies a row window of a single image; otherwise everything
+    const size_t orow_px = (size_t)w * F;
+    if (out_f32)
+        CUDA_TRY(cudaMemcpyAsync(out_f32, d_f32 + (size_t)out_row_begin * orow_px * 3,
+                                 (out_rows < 0 ? opx : (size_t)out_rows * orow_px) * 3 * sizeof(float),
+                                 cudaMemcpyDeviceToHost, c->stream));
+    if (out_u8)
+        CUDA_TRY(cudaMemcpyAsync(out_u8, d_u8 + (size_t)out_row_begin * orow_px * 4,
+                                 (out_rows < 0 ? opx : (size_t)out_rows * orow_px) * 4, cudaMemcpyDeviceToHost,
+                                 c->stream));
+    return rsr_synchronize(c);
+}
+
+extern "C" int rsr_upscale_f32(rsr_ctx* c, const float* in, int w, int h, float* out) {
+    return upscale_host(c, in, false, 3, 1, w, h, out, nullptr, 0, -1);
+}
+extern "C" int rsr_upscale_u8(rsr_ctx* c, const uint8_t* in, int w, int h, int in_channels, uint8_t* out_rgba) {
+    return upscale_host(c, in, true, in_channels, 1, w, h, nullptr, out_rgba, 0, -1);
+}
+extern "C" int rsr_upscale_batch_f32(rsr_ctx* c, const float* in, int n, int w, int h, float* out) {
+    return upscale_host(c, in, false, 3, n, w, h, out, nullptr, 0, -1);
+}
+extern "C" int rsr_upscale_batch_u8(rsr_ctx* c, const uint8_t* in, int n, int w, int h, int in_channels,
+                                    uint8_t* out_rgba) {
+    return upscale_host(c, in, true, in_channels, n, w, h, nullptr, out_rgba, 0, -1);
+}
+extern "C" int rsr_upscale_band_f32(rsr_ctx* c, const float* in_rows, int w, int rows_in, int top_halo,
+                                    int bottom_halo, float* out_rows) {
+    if (top_halo < 0 || bottom_halo < 0 || rows_in - top_halo - bottom_halo < 1)
+        return fail(RSR_E_BAD_ARG, "bad band: rows_in=%d top_halo=%d bottom_halo=%d", rows_in, top_halo, bottom_halo);
+    const int F = c ? c->factor : 3;
+    return upscale_host(c, in_rows, false, 3, 1, w, rows_in, out_rows, nullptr, top_halo * F,
+                        (rows_in - top_halo - bottom_halo) * F);
+}
+
+extern "C" int rsr_last_kernel_times(rsr_ctx* c, float* ms, int cap) {
+    if (!c || !ms) return fail(RSR_E_BAD_ARG, "null argument");
+    if (!c->timed) return 0;
+    if (int rc = rsr_synchronize(c)) return rc;
+    int nout = 0;
+    for (int i = 0; i < K_COUNT && i < cap; ++i, ++nout) CUDA_TRY(cudaEventElapsedTime(&ms[i], c->ev[i], c->ev[i + 1]));
+    return nout;
+}
+extern "C" int rsr_last_launch_count(rsr_ctx* c) { return c ? c->last_launches : 0; }
+
+// ------------------------------------------------------------------------------- test hooks
+extern "C" int rsr_debug_stop_after(rsr_ctx* c, int k) {
+    if (!c) return fail(RSR_E_BAD_ARG, "ctx is null");
+    c->stop_after = k;
+    return 0;
+}
+extern "C" int rsr_debug_read_node(rsr_ctx* c, int which, float* out, size_t npx) {
+    if (!c || !out) return fail(RSR_E_BAD_ARG, "null argument");
+    if (int rc = rsr_synchronize(c)) return rc;
+    DevBuf* b = which == 0 ? &c->actA : which == 1 ? &c->actB : which == 2 ? &c->partA : which == 3 ? &c->partB : nullptr;
+    if (!b || !b->p || b->cap < npx * 128) return fail(RSR_E_BAD_ARG, "node %d not available for %zu pixels", which, npx);
+    if (which >= 2) {
+        CUDA_TRY(cudaMemcpy(out, b->p, npx * 128, cudaMemcpyDeviceToHost));
+        return 0;
+    }
+    std::vector<__nv_bfloat16> tmp(npx * 64);
+    CUDA_TRY(cudaMemcpy(tmp.data(), b->p, npx * 128, cudaMemcpyDeviceToHost));
+    for (size_t i = 0; i < npx; ++i)
+        for (int ch = 0; ch < 32; ++ch)
+            out[i * 32 + ch] = __bfloat162float(tmp[i * 64 + ch]) + __bfloat162float(tmp[i * 64 + 32 + ch]);
+    return 0;
+}

@@ -1,0 +1,188 @@
+"""Parity of the sm_100a path against the CPU oracle, through the C ABI (ctypes).
+
+Tolerance (BASELINE.json north_star): max-abs < 1e-3 in linear light vs the reference's fp32
+CPU path.  The BF16x3 split keeps us ~10x inside that, so the tests assert 2e-4 (linear light
+and raw sRGB domain) against the fp64 oracle; the fp32 oracle is itself within 5e-5 of fp64."""
+import numpy as np
+import pytest
+
+from conftest import load_png, noise_image, synthetic_kat_image
+from oracle import oracle as O
+
+pytestmark = pytest.mark.gpu
+
+TOL = 2e-4          # asserted; the contract is 1e-3
+CONTRACT = 1e-3
+
+
+@pytest.fixture(scope="module")
+def R():
+    import rusty_sr_b200 as R
+    return R
+
+
+@pytest.fixture(scope="module")
+def ups(R, weights):
+    d = {k: R.Upscaler(weights[k]) for k in weights}
+    yield d
+    for u in d.values():
+        u.close()
+
+
+def errs(out, ref):
+    srgb = float(np.abs(out.astype(np.float64) - ref).max())
+    lin = float(np.abs(O.srgb_to_linear(out) - O.srgb_to_linear(ref)).max())
+    return srgb, lin
+
+
+def test_golden_cartoon_u8_bit_level(ups):
+    """docs/cartoon_lr.png + anime.rsr -> docs/cartoon_rsa.png through the fused u8 entry point."""
+    lr, hr = load_png("cartoon_lr"), load_png("cartoon_rsa")
+    img = ups["anime"].forward_u8(lr)
+    assert img.shape == hr.shape and img.dtype == np.uint8
+    d = np.abs(img.astype(int) - hr.astype(int))
+    assert d.max() <= 1
+    assert (d == 0).mean() >= 0.9999
+    assert (img[..., 3] == 255).all()
+
+
+def test_golden_butterfly(ups):
+    lr, hr = load_png("butterfly_lr"), load_png("butterfly_rs")
+    img = ups["imagenet"].forward_u8(lr[..., :3].copy())  # RGB input path
+    d = np.abs(img.astype(int) - hr.astype(int))
+    mse = np.mean((img[..., :3].astype(float) - hr[..., :3]) ** 2)
+    assert 10 * np.log10(255 ** 2 / mse) >= 55.0 and d.max() <= 5
+    # identical to what the oracle's u8 mapping gives, up to rounding ties
+    ref = O.data_to_img(O.forward(ups["imagenet"] and O_params(ups, "imagenet"), O.img_to_data(lr), 3, np.float32))
+    assert (np.abs(img.astype(int) - ref.astype(int)) <= 1).all()
+    assert (img == ref).mean() > 0.999
+
+
+def O_params(ups, name):
+    import rusty_sr_b200 as R
+    return R.load_builtin_params(name)
+
+
+@pytest.mark.parametrize("wname", ["imagenet", "imagenetlinear", "anime"])
+@pytest.mark.parametrize("case", ["cartoon", "butterfly", "kat", "noise256"])
+def test_f32_parity_all_weight_sets(ups, weights, wname, case):
+    x = {"cartoon": lambda: O.img_to_data(load_png("cartoon_lr")),
+         "butterfly": lambda: O.img_to_data(load_png("butterfly_lr")),
+         "kat": lambda: synthetic_kat_image(),
+         "noise256": lambda: noise_image(256, 256, 1234)}[case]()
+    ref = O.forward(weights[wname], x, 3, np.float64)
+    out = ups[wname].forward(x)
+    assert out.shape == ref.shape and out.dtype == np.float32
+    srgb, lin = errs(out, ref)
+    assert lin < TOL and srgb < TOL, (srgb, lin)
+
+
+def test_known_answers(ups):
+    """SURVEY.md App. B.4 values, straight from the GPU."""
+    out = ups["imagenet"].forward(synthetic_kat_image())
+    np.testing.assert_allclose(out[0, 0], [-0.0265731391, -0.0054821758, 0.0289644812], atol=TOL)
+    np.testing.assert_allclose(out[24, 31], [0.5922541513, 0.6175470251, 0.6417088860], atol=TOL)
+    assert abs(float(out.sum(dtype=np.float64)) - 3992.76461685) < 0.05
+
+
+@pytest.mark.parametrize("shape", [(1, 1), (1, 9), (9, 1), (7, 5), (2, 130), (3, 128), (5, 129),
+                                   (131, 4), (17, 257), (45, 300)])
+def test_odd_sizes(ups, weights, shape):
+    """Edge cases: sizes below / across the 128-pixel strip and the rows-per-pass granularity."""
+    H, W = shape
+    x = noise_image(H, W, 100 + H * 1000 + W)
+    ref = O.forward(weights["anime"], x, 3, np.float64)
+    out = ups["anime"].forward(x)
+    srgb, lin = errs(out, ref)
+    assert lin < TOL and srgb < TOL, (shape, srgb, lin)
+
+
+def test_constant_and_zero_images(ups, weights):
+    for val in (0.0, 1.0, 0.5):
+        x = np.full((20, 33, 3), val, np.float32)
+        ref = O.forward(weights["imagenet"], x, 3, np.float64)
+        out = ups["imagenet"].forward(x)
+        assert errs(out, ref)[0] < TOL
+    z = ups["imagenet"].forward(np.zeros((24, 24, 3), np.float32))
+    assert np.abs(z[24:48, 24:48]).max() < 1e-3  # SURVEY.md B.3 null test
+
+
+def test_out_of_range_input_is_not_clamped(ups, weights):
+    """graph.forward does not clamp (main.rs:171); only data_to_img does (main.rs:175)."""
+    rng = np.random.default_rng(3)
+    x = (rng.random((16, 40, 3), dtype=np.float32) * 3.0 - 1.0)
+    ref = O.forward(weights["anime"], x, 3, np.float64)
+    out = ups["anime"].forward(x)
+    assert np.abs(out - ref).max() < 5e-4
+    assert out.min() < 0 and out.max() > 1
+
+
+def test_batch_equals_singles(ups):
+    xs = np.stack([noise_image(64, 80, 1234 + i) for i in range(5)])
+    outs = ups["imagenet"].forward(xs)
+    for i in range(5):
+        single = ups["imagenet"].forward(xs[i])
+        assert np.array_equal(outs[i], single)  # same kernels, same order: bit-identical
+
+
+def test_u8_path_matches_f32_path(ups):
+    rng = np.random.default_rng(11)
+    img = rng.integers(0, 256, size=(50, 70, 4), dtype=np.uint8)
+    a = ups["anime"].forward_u8(img)
+    b = O.data_to_img(ups["anime"].forward(O.img_to_data(img)))
+    assert np.array_equal(a, b)
+    batch = np.stack([img[..., :3], img[::-1, :, :3]])
+    ab = ups["anime"].forward_u8(batch)
+    assert np.array_equal(ab[0], a)
+
+
+def test_band_mode_equals_full_frame(ups, weights):
+    """Spatial sharding (overlap-recompute): bands with 7-row halos reproduce the
+    unsharded frame exactly (same accumulation order => bit-identical)."""
+    x = noise_image(96, 150, 4321)
+    full = ups["imagenet"].forward(x)
+    H = x.shape[0]
+    parts = []
+    nb = 4
+    for b in range(nb):
+        y0, y1 = b * H // nb, (b + 1) * H // nb
+        top, bot = min(7, y0), min(7, H - y1)
+        parts.append(ups["imagenet"].forward_band(x[y0 - top:y1 + bot], top, bot))
+    tiled = np.concatenate(parts, axis=0)
+    assert tiled.shape == full.shape
+    assert np.array_equal(tiled, full)
+
+
+def test_1080p_properties(ups, weights):
+    """BASELINE config 2 at full size: too big to oracle in a unit test in full, so check
+    (a) a 64-row horizontal slab against the oracle (the slab + 7-row halo is self-contained),
+    (b) translation consistency with a separately computed crop."""
+    x = noise_image(1080, 1920, 1234)
+    out = ups["imagenet"].forward(x)
+    assert out.shape == (3240, 5760, 3) and np.isfinite(out).all()
+    y0, y1 = 500, 564
+    slab = x[y0 - 7:y1 + 7]
+    ref = O.forward(weights["imagenet"], slab, 3, np.float64)[21:-21]
+    srgb, lin = errs(out[3 * y0:3 * y1], ref)
+    assert lin < TOL and srgb < TOL, (srgb, lin)
+    crop = ups["imagenet"].forward(x[:40, :300])
+    assert np.abs(crop[:99, :879] - out[:99, :879]).max() < 1e-5
+
+
+def test_error_paths(R, ups):
+    u = ups["anime"]
+    with pytest.raises(R.RsrError):
+        u.forward_u8(np.zeros((4, 4, 2), np.uint8))
+    with pytest.raises(ValueError):
+        u.forward(np.zeros((4, 4, 4), np.float32))
+    with pytest.raises(R.RsrError):
+        u.forward_band(np.zeros((4, 4, 3), np.float32), 3, 3)
+
+
+def test_native_launches_are_counted(ups):
+    u = ups["imagenet"]
+    u.forward(noise_image(32, 32, 1))
+    assert u.last_launch_count() == 6
+    t = u.last_kernel_times_ms()
+    assert list(t) == ["pack_input", "conv0", "conv1|2|3", "conv5|6|7", "conv8|9", "conv10+expand+skip"]
+    assert all(v > 0 for v in t.values())
