@@ -24,6 +24,7 @@
  * Two precisions: sr_oracle_forward_f32 (what the reference computes in: fp32) and
  * sr_oracle_forward_f64 (ground truth for tolerances).  OpenMP over image rows.
  */
+#define _POSIX_C_SOURCE 200112L
 #include <math.h>
 #include <stdint.h>
 #include <stdlib.h>
@@ -115,6 +116,9 @@ long sr_oracle_decode_rsr(const uint8_t *bytes, size_t len, float *out, size_t o
 
 /* The generic body is instantiated twice (float / double) through the preprocessor. */
 #define REAL float
+#define SR_LANES 16
+typedef float sr_v16f __attribute__((vector_size(64), aligned(64)));
+#define SR_VEC sr_v16f
 #define SUF(x) x##_f32
 #define SQRT sqrtf
 #define FLOOR floorf
@@ -123,8 +127,13 @@ long sr_oracle_decode_rsr(const uint8_t *bytes, size_t len, float *out, size_t o
 #undef SUF
 #undef SQRT
 #undef FLOOR
+#undef SR_LANES
+#undef SR_VEC
 
 #define REAL double
+#define SR_LANES 8
+typedef double sr_v8d __attribute__((vector_size(64), aligned(64)));
+#define SR_VEC sr_v8d
 #define SUF(x) x##_f64
 #define SQRT sqrt
 #define FLOOR floor
