@@ -103,6 +103,10 @@ int rsr_last_launch_count(rsr_ctx* ctx);
  *         2: partial buffer A (conv2(f), later expand), 3: partial buffer B (l3_conv partial). */
 int rsr_debug_stop_after(rsr_ctx* ctx, int launch_index);
 int rsr_debug_read_node(rsr_ctx* ctx, int which, float* out, size_t n_pixels);
+/* Per-CTA wait-cycle counters of the conv launches (which mbarrier each warp role waited on, in SM
+ * cycles): enable, run a call, then read [grid][16] rows for launch index 1..5; returns the grid. */
+int rsr_debug_profile(rsr_ctx* ctx, int enable);
+int rsr_debug_read_profile(rsr_ctx* ctx, int launch_index, long long* out, int cap_rows);
 
 /* Thread-local description of the last failure in this thread ("" if none). */
 const char* rsr_last_error(void);

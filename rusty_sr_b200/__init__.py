@@ -121,6 +121,8 @@ class Upscaler:
         """One horizontal band of a larger frame (spatial sharding, overlap-recompute)."""
         x = np.ascontiguousarray(rows, dtype=np.float32)
         H, W = x.shape[:2]
+        if top_halo < 0 or bottom_halo < 0 or H - top_halo - bottom_halo < 1:
+            raise ValueError(f"bad band: rows_in={H} top_halo={top_halo} bottom_halo={bottom_halo}")
         out = np.empty(((H - top_halo - bottom_halo) * self.factor, W * self.factor, 3), np.float32)
         _lib.check(self._L.rsr_upscale_band_f32(self._h, _as_ptr(x), W, H, top_halo, bottom_halo,
                                                 _as_ptr(out)))
@@ -160,6 +162,16 @@ class Upscaler:
         out = np.empty((n_pixels, 32), np.float32)
         _lib.check(self._L.rsr_debug_read_node(self._h, which, _as_ptr(out), n_pixels))
         return out
+
+    def debug_profile(self, enable: bool = True) -> None:
+        _lib.check(self._L.rsr_debug_profile(self._h, int(enable)))
+
+    def debug_read_profile(self, launch_index: int) -> np.ndarray:
+        out = np.zeros((256, 16), np.int64)
+        n = self._L.rsr_debug_read_profile(self._h, launch_index, _as_ptr(out), 256)
+        if n < 0:
+            _lib.check(n)
+        return out[:n]
 
     def last_launch_count(self) -> int:
         return int(self._L.rsr_last_launch_count(self._h))

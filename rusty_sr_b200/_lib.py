@@ -6,7 +6,7 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "librsr_b200.so")
+LIB_PATH = os.environ.get("RSR_B200_LIB") or os.path.join(_HERE, "lib", "librsr_b200.so")  # env override: tools/ablate.sh
 
 RSR_OK = 0
 RSR_E_PARAM_COUNT = -1
@@ -22,6 +22,7 @@ EXPORTS = (
     "rsr_upscale_device_u8", "rsr_synchronize", "rsr_upscale_band_f32", "rsr_set_stream",
     "rsr_last_kernel_times", "rsr_kernel_name", "rsr_last_launch_count", "rsr_last_error",
     "rsr_last_error_code", "rsr_version", "rsr_debug_stop_after", "rsr_debug_read_node",
+    "rsr_debug_profile", "rsr_debug_read_profile",
 )
 
 _lib = None
@@ -69,6 +70,10 @@ def load() -> ctypes.CDLL:
     L.rsr_debug_stop_after.restype = ci
     L.rsr_debug_read_node.argtypes = [vp, ci, vp, ctypes.c_size_t]
     L.rsr_debug_read_node.restype = ci
+    L.rsr_debug_profile.argtypes = [vp, ci]
+    L.rsr_debug_profile.restype = ci
+    L.rsr_debug_read_profile.argtypes = [vp, ci, vp, ci]
+    L.rsr_debug_read_profile.restype = ci
     for name in ("rsr_upscale_f32", "rsr_upscale_u8", "rsr_upscale_batch_f32", "rsr_upscale_batch_u8",
                  "rsr_upscale_device_f32", "rsr_upscale_device_u8", "rsr_synchronize",
                  "rsr_upscale_band_f32", "rsr_set_stream", "rsr_last_kernel_times",

@@ -16,77 +16,121 @@
 // each into a ring of row slots in shared memory (box = 128 + KW - 1 pixels, SWIZZLE_128B,
 // out-of-bounds = zero fill = `Padding::Same`); the KH*KW taps are NOT re-loaded: the tap
 // (a, b) operand is the same shared-memory row slot (row + a) read through a UMMA descriptor whose
-// start address is shifted by b pixels.  Weights stream per tap through a small ring.  R output
-// rows are accumulated per pass in TMEM (double buffered) so that the epilogue of pass j overlaps
-// the MMAs of pass j + 1.
+// start address is shifted by b pixels.  Weights stream per tap through a small TMA ring.
 //
-// Warp roles (256 threads): warp 0 = input-row TMA producer, warp 3 = weight TMA producer,
-// warp 1 = MMA issuer (one lane), warp 2 = TMEM allocator, warps 4..7 = epilogue (TMEM -> regs ->
-// bias / BeLU / split / partial sums / depth-to-space + bilinear skip -> global).
+// Partial pre-activation sums that an earlier launch produced for the same node (alumina nodes
+// sum all their writers: network.rs:61+65, :62+66+69, :67+70+72) are NOT added in the epilogue:
+// they are stored in the same split-bf16 pixel format, TMA-loaded as one more A tile and folded
+// into the accumulator by the tensor core with an identity B tile (4 tiny MMAs per row).
+// The epilogue therefore never waits on global memory: TMEM -> registers -> bias / BeLU / split
+// -> swizzled shared staging -> TMA store.  R output rows are accumulated per pass in TMEM, double
+// buffered, so the epilogue of pass j overlaps the MMAs of pass j + 1.
+//
+// Warp roles (256 threads): warp 0 = input-row producer, warp 3 = weight producer, warp 2 = TMEM
+// allocator + partial-sum producer, warp 1 = MMA issuer (one lane), warps 4..7 = epilogue.
 #pragma once
 #include <cuda_bf16.h>
 #include "ptx.cuh"
+
+// Timing-ablation switches (tools/ablate.sh builds variants; results are then WRONG on purpose).
+#ifndef RSR_ABL
+#define RSR_ABL 0
+#endif
+#define ABL_NO_A_LOAD (RSR_ABL & 1)     // input rows: barrier protocol only, no TMA
+#define ABL_NO_B_LOAD (RSR_ABL & 2)     // weights: barrier protocol only, no TMA
+#define ABL_NO_PIN (RSR_ABL & 4)        // partial-sum tiles: no TMA (MMAs still issued)
+#define ABL_NO_MMA (RSR_ABL & 8)        // no tcgen05.mma at all
+#define ABL_NO_EPI_OUT (RSR_ABL & 16)   // epilogue: TMEM load only, no math / staging / store
+#define ABL_NO_PIN_MMA (RSR_ABL & 32)   // partial-sum fold MMAs skipped
 
 namespace rsr {
 
 // What happens to one 32-column group of the accumulator.
 enum EpiKind : int {
     EPI_NONE = 0,
-    EPI_ACT = 1,      // v = acc + bias (+ partial_in); y = BeLU(v; slope); store split-bf16 activation
-    EPI_PARTIAL = 2,  // v = acc (+ partial_in); store fp32 partial pre-activation sum
-    EPI_SHUFFLE = 3,  // v = acc + bias (+ partial_in); depth-to-space + bilinear skip; store image
+    EPI_ACT = 1,      // y = BeLU(acc + bias; slope); store split-bf16 activation
+    EPI_RAW = 2,      // store acc as split-bf16 (partial pre-activation sum for a later launch)
+    EPI_SHUFFLE = 3,  // acc + bias; depth-to-space + bilinear skip; store image
 };
 
 struct EpiGroup {
     int kind;
-    int pad_;
-    const float* partial_in;   // [N][H][W][32] fp32 or null
-    float* partial_out;        // EPI_PARTIAL
-    __nv_bfloat16* act_out;    // EPI_ACT: [N][H][W][64] (hi 32 | mid 32)
-    const float* bias;         // 32 floats (zero padded)
-    const float* slope;        // 32 floats: BeLU p
+    int has_pin;          // a partial sum from an earlier launch is folded into this group
+    const float* bias;    // 32 floats (zero padded) or null
+    const float* slope;   // 32 floats: BeLU p (EPI_ACT)
 };
 
 struct ConvParams {
-    CUtensorMap tmA;  // input node, rank 4: (RB/2 elems, W, H, NIMG)
-    CUtensorMap tmB;  // packed weights, rank 2: (RB/2 elems, taps * NCOL)
+    CUtensorMap tmA;       // input node, rank 4: (RB/2 elems, W, H, NIMG), box (RB/2, BOXW, 1, 1)
+    CUtensorMap tmB;       // packed weights, rank 2: (RB/2 elems, taps * NCOL), box (RB/2, NCOL)
+    CUtensorMap tmI;       // identity tile [32][64] bf16 (partial-sum fold)
+    CUtensorMap tmPin[3];  // per group: partial-sum input, rank 4 (64, W, H, NIMG), box (64, 128, 1, 1)
+    CUtensorMap tmOut[3];  // per group: split-bf16 output, rank 4 (64, W, H, NIMG), box (64, 32, 1, 1)
     int W, H, NIMG;
-    int row_begin, row_end;  // output rows computed (band mode); [0, H) normally
-    int n_strips, n_segs, seg_rows, total_items;
+    int row_begin, row_end;  // output rows computed; [0, H) normally
+    int n_strips;
+    long long total_rowtiles;  // NIMG * n_strips * (row_end - row_begin)
     int factor;
     EpiGroup grp[3];
-    const float4* xf4;   // EPI_SHUFFLE: input image as float4 [N][H][W] (bilinear skip)
-    float* out_f32;      // EPI_SHUFFLE: [N][fH][fW][3] (or null)
-    uint8_t* out_u8;     // EPI_SHUFFLE: [N][fH][fW][4] RGBA (or null)
+    const float4* xf4;  // EPI_SHUFFLE: input image as float4 [N][H][W] (bilinear skip)
+    float* out_f32;     // EPI_SHUFFLE: [N][fH][fW][3] (or null)
+    uint8_t* out_u8;    // EPI_SHUFFLE: [N][fH][fW][4] RGBA (or null)
+    int out_vec_ok;     // f32 output rows are 16-byte aligned (W % 4 == 0 and aligned base)
     int* fault;
+    long long* prof;    // test hook: per-CTA wait-cycle counters [gridDim.x][16] (null = off)
 };
 
-#ifndef RSR_UMMA_BASE_OFFSET_POLICY
-#define RSR_UMMA_BASE_OFFSET_POLICY 0   // set from the hardware probe (tests/cuda/umma_probe.cu)
+// Wait on an mbarrier and, when profiling, charge the cycles to counter `slot`.
+#ifndef RSR_PROFILE
+#define RSR_PROFILE 0   // tools/ablate.sh builds the profiling variant with -DRSR_PROFILE=1
 #endif
+#define RSR_PROF_ON (RSR_PROFILE && p.prof)
+#define RSR_WAIT(bar, par, tag, slot)                                   \
+    do {                                                                 \
+        if (RSR_PROF_ON) {                                               \
+            const long long t0__ = clock64();                            \
+            mbar_wait(bar, par, p.fault, tag);                           \
+            prof_acc[slot] += clock64() - t0__;                          \
+        } else {                                                         \
+            mbar_wait(bar, par, p.fault, tag);                           \
+        }                                                                \
+    } while (0)
 
-template <int KH_, int KW_, int RB_, int NG_, int R_>
+template <int KH_, int KW_, int RB_, int NG_, int R_, int NR_, int TPS_, int NBS_, int NPIN_, int NOUT_, bool SHUF_>
 struct ConvCfg {
     static constexpr int KH = KH_, KW = KW_, RB = RB_, NG = NG_, R = R_;
+    static constexpr int NBS = NBS_, NPIN = NPIN_, NOUT = NOUT_;
+    static constexpr bool SHUF = SHUF_;
     static constexpr int NCOL = 32 * NG;
     static constexpr int PH = KH / 2, PW = KW / 2;
     static constexpr int TAPS = KH * KW;
     static constexpr int BOXW = 128 + KW - 1;                          // pixels per loaded row
     static constexpr int ROW_BYTES = BOXW * RB;                        // TMA bytes per row
     static constexpr int SLOT = (ROW_BYTES + 1023) / 1024 * 1024;      // ring slot pitch
-    static constexpr int NR = 2 * R + 2 * PH;                          // ring slots (one pass lookahead)
-    static constexpr int BST = NCOL * RB;                              // bytes per weight stage (one tap)
-    static constexpr int NBS = 4;                                      // weight stages
+    static constexpr int NR = NR_;                                     // input-row ring slots (>= R + 2*PH)
+    static constexpr int TPS = TPS_;                                   // taps per weight stage
+    static constexpr int NSTG = (TAPS + TPS - 1) / TPS;                // weight stages per pass
+    static constexpr int TAP_BYTES = NCOL * RB;                        // weight bytes of one tap
+    static constexpr int BST = TPS * TAP_BYTES;                        // bytes per weight stage
     static constexpr int KC = RB / 64;                                 // 16-channel chunks per plane
+    static constexpr int PIN_BYTES = 128 * 128;                        // one partial-sum tile
+    static constexpr int IDENT_BYTES = NPIN > 0 ? 32 * 128 : 0;
     static constexpr int ACC_COLS = 2 * R * NCOL;                      // double-buffered accumulators
     static constexpr int TMEM_COLS = ACC_COLS <= 32 ? 32 : ACC_COLS <= 64 ? 64 : ACC_COLS <= 128 ? 128
                                    : ACC_COLS <= 256 ? 256 : 512;
-    static constexpr int NBAR = 2 * NR + 2 * NBS + 4;
-    static constexpr int SMEM_BYTES = 1024 + NR * SLOT + NBS * BST + NBAR * 8 + 16;
+    static constexpr int OFF_B = NR * SLOT;
+    static constexpr int OFF_P = OFF_B + NBS * BST;
+    static constexpr int OFF_I = OFF_P + NPIN * PIN_BYTES;
+    static constexpr int OFF_O = OFF_I + IDENT_BYTES;
+    static constexpr int OFF_BAR = OFF_O + 4 * NOUT * 4096;
+    static constexpr int NBAR = 2 * NR + 2 * NBS + 2 * (NPIN > 0 ? NPIN : 1) + 4 + 1;
+    static constexpr int SMEM_BYTES = 1024 + OFF_BAR + NBAR * 8 + 16;
     static constexpr uint32_t SWZ = RB == 128 ? UMMA_SW_128B : UMMA_SW_64B;
     static_assert(ACC_COLS <= 512, "accumulators exceed TMEM");
     static_assert(RB == 128 || RB == 64, "pixel row must be 128 or 64 bytes");
-    static_assert(BST % 1024 == 0, "weight stage must keep 1024-byte alignment");
+    static_assert(TAP_BYTES % 1024 == 0, "weight tap tile must keep 1024-byte alignment");
+    static_assert(TPS * NCOL <= 256, "weight stage exceeds the TMA box limit");
+    static_assert(NR >= R + 2 * PH, "row ring smaller than one pass window");
     static_assert(SMEM_BYTES <= 232448, "shared memory budget");
 };
 
@@ -94,138 +138,134 @@ struct WorkItem {
     int img, x0, y_b, y_e, npass;
 };
 
+// Static range partition: the NIMG * n_strips * rows row-tiles are linearised strip-major and cut
+// into gridDim.x equal ranges; a range that crosses a strip boundary becomes two work items.
+struct ItemIter {
+    long long cur, end;
+    int rows;
+};
+__device__ __forceinline__ ItemIter item_begin(const ConvParams& p) {
+    ItemIter it;
+    it.rows = p.row_end - p.row_begin;
+    it.cur = p.total_rowtiles * (long long)blockIdx.x / gridDim.x;
+    it.end = p.total_rowtiles * (long long)(blockIdx.x + 1) / gridDim.x;
+    return it;
+}
 template <class C>
-__device__ __forceinline__ WorkItem decode_item(const ConvParams& p, int item) {
-    WorkItem w;
-    const int seg = item % p.n_segs;
-    const int t = item / p.n_segs;
-    const int strip = t % p.n_strips;
-    w.img = t / p.n_strips;
-    w.x0 = strip * 128;
-    w.y_b = p.row_begin + seg * p.seg_rows;
-    w.y_e = min(w.y_b + p.seg_rows, p.row_end);
-    w.npass = (w.y_e - w.y_b + C::R - 1) / C::R;
-    return w;
+__device__ __forceinline__ bool item_next(const ConvParams& p, ItemIter& it, WorkItem& w) {
+    if (it.cur >= it.end) return false;
+    const int col = (int)(it.cur / it.rows);
+    const int y0 = (int)(it.cur % it.rows);
+    const int n = (int)min((long long)(it.rows - y0), it.end - it.cur);
+    w.img = col / p.n_strips;
+    w.x0 = (col % p.n_strips) * 128;
+    w.y_b = p.row_begin + y0;
+    w.y_e = w.y_b + n;
+    w.npass = (n + C::R - 1) / C::R;
+    it.cur += n;
+    return true;
 }
 
+__device__ __forceinline__ float sqrt_approx(float x) {
+    float r;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));   // one MUFU op, rel. error ~2^-23
+    return r;
+}
 __device__ __forceinline__ float belu(float x, float p) {
     // alumina BeLU (network.rs:35,54-56): y = p*x + sqrt(x^2 + 1) - 1   
-    return fmaf(p, x, sqrtf(fmaf(x, x, 1.0f)) - 1.0f);
+    return fmaf(p, x, sqrt_approx(fmaf(x, x, 1.0f)) - 1.0f);
 }
 
 __device__ __forceinline__ uint32_t pack_bf16x2(__nv_bfloat16 a, __nv_bfloat16 b) {
     return (uint32_t)__bfloat16_as_ushort(a) | ((uint32_t)__bfloat16_as_ushort(b) << 16);
 }
-
-// ---- epilogue pieces (one thread = one pixel, v[] = its 32 accumulator columns) -------------
-__device__ __forceinline__ void epi_add_vec(float (&v)[32], const float* __restrict__ src) {
-    const float4* s4 = reinterpret_cast<const float4*>(src);
-    #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        const float4 t = __ldg(s4 + i);
-        v[4 * i + 0] += t.x; v[4 * i + 1] += t.y; v[4 * i + 2] += t.z; v[4 * i + 3] += t.w;
-    }
+// (lo, hi) floats -> packed bf16x2 with round-to-nearest-even, one instruction
+__device__ __forceinline__ uint32_t cvt_bf16x2(float lo, float hi) {
+    uint32_t r;
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+    return r;
 }
-// Partial sums may be updated in place (and the buffers are re-used between nodes), so they are
-// read with ordinary coherent loads, never through the read-only path.
-__device__ __forceinline__ void epi_add_partial(float (&v)[32], const float* src) {
-    const float4* s4 = reinterpret_cast<const float4*>(src);
-    #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        const float4 t = s4[i];
-        v[4 * i + 0] += t.x; v[4 * i + 1] += t.y; v[4 * i + 2] += t.z; v[4 * i + 3] += t.w;
-    }
+// split two floats into bf16 hi parts (packed) and bf16 mid parts (packed): v = hi + mid + O(2^-17 v)
+__device__ __forceinline__ void split_pair(float v0, float v1, uint32_t& hi, uint32_t& mid) {
+    hi = cvt_bf16x2(v0, v1);
+    const float h0 = __uint_as_float(hi << 16), h1 = __uint_as_float(hi & 0xffff0000u);
+    mid = cvt_bf16x2(v0 - h0, v1 - h1);
 }
 
-__device__ __forceinline__ void epi_act(const EpiGroup& g, float (&v)[32], size_t px) {
-    epi_add_vec(v, g.bias);
-    if (g.partial_in) epi_add_partial(v, g.partial_in + px * 32);
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+
+// One thread = one pixel; v[] = its 32 accumulator columns.  Applies bias / BeLU, splits every
+// value into bf16 hi + mid and writes the pixel's 128-byte row (hi 0..31 | mid 0..31) into the
+// warp's staging tile with the 128-byte TMA swizzle (16-byte chunk j of row r sits at j ^ (r & 7)).
+__device__ __forceinline__ void epi_split_to_stage(const EpiGroup& g, float (&v)[32], uint32_t stage_addr, int lane) {
+    if (g.bias) {
+        const float4* b4 = reinterpret_cast<const float4*>(g.bias);
+        #pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const float4 t = __ldg(b4 + i);
+            v[4 * i + 0] += t.x; v[4 * i + 1] += t.y; v[4 * i + 2] += t.z; v[4 * i + 3] += t.w;
+        }
+    }
+    if (g.kind == EPI_ACT) {
+        const float4* s4 = reinterpret_cast<const float4*>(g.slope);
+        #pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const float4 t = __ldg(s4 + i);
+            v[4 * i + 0] = belu(v[4 * i + 0], t.x); v[4 * i + 1] = belu(v[4 * i + 1], t.y);
+            v[4 * i + 2] = belu(v[4 * i + 2], t.z); v[4 * i + 3] = belu(v[4 * i + 3], t.w);
+        }
+    }
     uint32_t hi[16], mid[16];
     #pragma unroll
-    for (int i = 0; i < 16; ++i) {
-        const float y0 = belu(v[2 * i], __ldg(g.slope + 2 * i));
-        const float y1 = belu(v[2 * i + 1], __ldg(g.slope + 2 * i + 1));
-        const __nv_bfloat16 h0 = __float2bfloat16_rn(y0), h1 = __float2bfloat16_rn(y1);
-        const __nv_bfloat16 m0 = __float2bfloat16_rn(y0 - __bfloat162float(h0));
-        const __nv_bfloat16 m1 = __float2bfloat16_rn(y1 - __bfloat162float(h1));
-        hi[i] = pack_bf16x2(h0, h1);
-        mid[i] = pack_bf16x2(m0, m1);
+    for (int i = 0; i < 16; ++i) split_pair(v[2 * i], v[2 * i + 1], hi[i], mid[i]);
+    const uint32_t row = stage_addr + lane * 128;
+    const uint32_t sw = lane & 7;
+    #pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        st_shared_v4(row + ((j ^ sw) << 4), hi[4 * j], hi[4 * j + 1], hi[4 * j + 2], hi[4 * j + 3]);
+        st_shared_v4(row + (((4 + j) ^ sw) << 4), mid[4 * j], mid[4 * j + 1], mid[4 * j + 2], mid[4 * j + 3]);
     }
-    uint4* dst = reinterpret_cast<uint4*>(g.act_out + px * 64);
-    #pragma unroll
-    for (int i = 0; i < 4; ++i) dst[i] = make_uint4(hi[4 * i], hi[4 * i + 1], hi[4 * i + 2], hi[4 * i + 3]);
-    #pragma unroll
-    for (int i = 0; i < 4; ++i) dst[4 + i] = make_uint4(mid[4 * i], mid[4 * i + 1], mid[4 * i + 2], mid[4 * i + 3]);
 }
 
-__device__ __forceinline__ void epi_partial(const EpiGroup& g, float (&v)[32], size_t px) {
-    if (g.partial_in) epi_add_partial(v, g.partial_in + px * 32);
-    float4* dst = reinterpret_cast<float4*>(g.partial_out + px * 32);
-    #pragma unroll
-    for (int i = 0; i < 8; ++i) dst[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
-}
-
-// Expand (depth-to-space, network.rs:39) + LinearInterp skip (network.rs:27) + image store.
-__device__ __forceinline__ void epi_shuffle(const ConvParams& p, const EpiGroup& g, float (&v)[32], int img,
-                                            int y, int x) {
-    const int F = p.factor, W = p.W, H = p.H;
-    const size_t px = ((size_t)img * H + y) * W + x;
-    epi_add_vec(v, g.bias);
-    if (g.partial_in) epi_add_partial(v, g.partial_in + px * 32);
-    // 3x3 neighbourhood of the input, edge clamped (half-pixel-centre bilinear)
-    const int ym = max(y - 1, 0), yp = min(y + 1, H - 1), xm = max(x - 1, 0), xp = min(x + 1, W - 1);
+// 3x3 neighbourhood of the input pixel, edge clamped, for the LinearInterp skip (network.rs:27).
+struct SkipNb {
+    float v[3][3][3];
+};
+__device__ __forceinline__ void load_skip_nb(const ConvParams& p, int img, int y, int x, SkipNb& nb) {
+    const int W = p.W, H = p.H;
+    const int ys[3] = {max(y - 1, 0), y, min(y + 1, H - 1)};
+    const int xs[3] = {max(x - 1, 0), x, min(x + 1, W - 1)};
     const float4* xi = p.xf4 + (size_t)img * H * W;
-    float nb[3][3][3];
-    {
-        const int ys[3] = {ym, y, yp}, xs[3] = {xm, x, xp};
+    #pragma unroll
+    for (int a = 0; a < 3; ++a)
         #pragma unroll
-        for (int a = 0; a < 3; ++a)
-            #pragma unroll
-            for (int b = 0; b < 3; ++b) {
-                const float4 t = __ldg(xi + (size_t)ys[a] * W + xs[b]);
-                nb[a][b][0] = t.x; nb[a][b][1] = t.y; nb[a][b][2] = t.z;
-            }
-    }
-    const float invF = 1.0f / (float)F;
-    for (int dy = 0; dy < F; ++dy) {
-        const float sy = ((float)dy + 0.5f) * invF - 0.5f;     // in (-0.5, 0.5)
-        const int ya = sy < 0.f ? 0 : 1;                       // rows (ya, ya+1) of the 3x3 block
-        const float ty = sy < 0.f ? sy + 1.0f : sy;
-        const size_t orow = ((size_t)img * H * F + (size_t)y * F + dy) * ((size_t)W * F) + (size_t)x * F;
-        for (int dx = 0; dx < F; ++dx) {
-            const float sx = ((float)dx + 0.5f) * invF - 0.5f;
-            const int xa = sx < 0.f ? 0 : 1;
-            const float tx = sx < 0.f ? sx + 1.0f : sx;
-            float o[3];
+        for (int b = 0; b < 3; ++b) {
+            const float4 t = __ldg(xi + (size_t)ys[a] * W + xs[b]);
+            nb.v[a][b][0] = t.x; nb.v[a][b][1] = t.y; nb.v[a][b][2] = t.z;
+        }
+}
+
+// Expand (depth-to-space, network.rs:39: out[F*h+dy, F*w+dx, c] = e[h, w, (dy*F+dx)*3 + c]) plus the
+// half-pixel-centre bilinear skip; factor 3.  o[dy][dx*3 + c].
+__device__ __forceinline__ void shuffle_pixel(const float (&v)[32], const SkipNb& nb, float (&o)[3][9]) {
+    #pragma unroll
+    for (int dy = 0; dy < 3; ++dy) {
+        // sy = (dy + 0.5)/3 - 0.5 = -1/3, 0, +1/3  ->  rows (ya, ya+1) of the 3x3 block, weight ty
+        const int ya = dy == 0 ? 0 : 1;
+        const float ty = dy == 0 ? (2.0f / 3.0f) : (dy == 1 ? 0.0f : (1.0f / 3.0f));
+        #pragma unroll
+        for (int dx = 0; dx < 3; ++dx) {
+            const int xa = dx == 0 ? 0 : 1;
+            const float tx = dx == 0 ? (2.0f / 3.0f) : (dx == 1 ? 0.0f : (1.0f / 3.0f));
             #pragma unroll
             for (int c = 0; c < 3; ++c) {
-                float v00, v01, v10, v11;
-                // select without dynamic register indexing
-                v00 = ya == 0 ? (xa == 0 ? nb[0][0][c] : nb[0][1][c]) : (xa == 0 ? nb[1][0][c] : nb[1][1][c]);
-                v01 = ya == 0 ? (xa == 0 ? nb[0][1][c] : nb[0][2][c]) : (xa == 0 ? nb[1][1][c] : nb[1][2][c]);
-                v10 = ya == 0 ? (xa == 0 ? nb[1][0][c] : nb[1][1][c]) : (xa == 0 ? nb[2][0][c] : nb[2][1][c]);
-                v11 = ya == 0 ? (xa == 0 ? nb[1][1][c] : nb[1][2][c]) : (xa == 0 ? nb[2][1][c] : nb[2][2][c]);
+                const float v00 = nb.v[ya][xa][c], v01 = nb.v[ya][xa + 1][c];
+                const float v10 = nb.v[ya + 1][xa][c], v11 = nb.v[ya + 1][xa + 1][c];
                 const float top = v00 + (v01 - v00) * tx;
                 const float bot = v10 + (v11 - v10) * tx;
-                // Expand channel order: e[(dy*F + dx)*3 + c]
-                float e = 0.f;
-                const int ch = (dy * F + dx) * 3 + c;
-                #pragma unroll
-                for (int k = 0; k < 32; ++k) e = (k == ch) ? v[k] : e;
-                o[c] = e + top + (bot - top) * ty;
-            }
-            if (p.out_f32) {
-                float* d = p.out_f32 + (orow + dx) * 3;
-                d[0] = o[0]; d[1] = o[1]; d[2] = o[2];
-            }
-            if (p.out_u8) {
-                // alumina data_to_img + to_rgba (main.rs:175): round(clamp(v,0,1)*255), alpha 255
-                uchar4 q;
-                q.x = (unsigned char)(fminf(fmaxf(o[0], 0.f), 1.f) * 255.0f + 0.5f);
-                q.y = (unsigned char)(fminf(fmaxf(o[1], 0.f), 1.f) * 255.0f + 0.5f);
-                q.z = (unsigned char)(fminf(fmaxf(o[2], 0.f), 1.f) * 255.0f + 0.5f);
-                q.w = 255;
-                reinterpret_cast<uchar4*>(p.out_u8)[orow + dx] = q;
+                o[dy][dx * 3 + c] = v[(dy * 3 + dx) * 3 + c] + top + (bot - top) * ty;
             }
         }
     }
@@ -237,131 +277,279 @@ __global__ void __launch_bounds__(256, 1) conv_strip_kernel(const __grid_constan
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* sA = smem;
-    uint8_t* sB = sA + C::NR * C::SLOT;
-    uint64_t* a_full = reinterpret_cast<uint64_t*>(sB + C::NBS * C::BST);
+    uint8_t* sB = smem + C::OFF_B;
+    uint8_t* sP = smem + C::OFF_P;
+    uint8_t* sI = smem + C::OFF_I;
+    uint8_t* sO = smem + C::OFF_O;
+    uint64_t* a_full = reinterpret_cast<uint64_t*>(smem + C::OFF_BAR);
     uint64_t* a_empty = a_full + C::NR;
     uint64_t* b_full = a_empty + C::NR;
     uint64_t* b_empty = b_full + C::NBS;
-    uint64_t* t_full = b_empty + C::NBS;
+    constexpr int NPB = C::NPIN > 0 ? C::NPIN : 1;
+    uint64_t* p_full = b_empty + C::NBS;
+    uint64_t* p_empty = p_full + NPB;
+    uint64_t* t_full = p_empty + NPB;
     uint64_t* t_empty = t_full + 2;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(t_empty + 2);
+    uint64_t* i_full = t_empty + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(i_full + 1);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
+    long long prof_acc[6] = {0, 0, 0, 0, 0, 0};
+    const long long prof_t0 = RSR_PROF_ON ? clock64() : 0;
+
+    // which groups fold a partial sum (uniform per launch)
+    int pin_g[3], npg = 0;
+    #pragma unroll
+    for (int g = 0; g < C::NG; ++g)
+        if (C::NPIN > 0 && p.grp[g].has_pin) pin_g[npg++] = g;
+    const int n_pin = npg * C::R;  // partial tiles per pass
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < C::NR; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
         for (int i = 0; i < C::NBS; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
+        for (int i = 0; i < NPB; ++i) { mbar_init(&p_full[i], 1); mbar_init(&p_empty[i], 1); }
         for (int i = 0; i < 2; ++i) { mbar_init(&t_full[i], 1); mbar_init(&t_empty[i], 4); }
+        mbar_init(i_full, 1);
         fence_mbar_init();
         tma_prefetch_desc(&p.tmA);
         tma_prefetch_desc(&p.tmB);
+        if (C::NPIN > 0 && npg > 0) {
+            mbar_arrive_expect_tx(i_full, C::IDENT_BYTES);
+            tma_load_2d(sI, &p.tmI, i_full, 0, 0);
+        }
     }
     if (warp == 2) { tmem_alloc(tmem_slot, C::TMEM_COLS); tmem_relinquish(); }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);  // warp-uniform for the compiler
 
+    // All role loops below are executed by the whole warp with warp-uniform control flow; only the
+    // TMA / MMA / commit instructions themselves are issued by one lane, chosen with elect.sync —
+    // the pattern ptxas recognises.  (Issuing from inside a divergent `if (lane == 0)` region makes
+    // it wrap every tcgen05.mma in an ELECT / R2UR "waterfall" loop: ~100 issue cycles per MMA.)
     if (warp == 0) {
         // ===== input-row producer =====
-        if (lane == 0) {
-            uint32_t s = 0;
-            for (int item = blockIdx.x; item < p.total_items; item += gridDim.x) {
-                const WorkItem w = decode_item<C>(p, item);
-                const int nrows = w.npass * C::R + 2 * C::PH;
-                for (int i = 0; i < nrows; ++i, ++s) {
-                    const uint32_t slot = s % C::NR, par = (s / C::NR) & 1;
-                    mbar_wait(&a_empty[slot], par ^ 1, p.fault, 1);
-                    mbar_arrive_expect_tx(&a_full[slot], C::ROW_BYTES);
-                    tma_load_4d(sA + slot * C::SLOT, &p.tmA, &a_full[slot], 0, w.x0 - C::PW, w.y_b - C::PH + i, w.img);
+        uint32_t slot = 0, par = 1;   // waiting on parity 1 of a fresh barrier returns immediately
+        ItemIter it = item_begin(p);
+        WorkItem w;
+        while (item_next<C>(p, it, w)) {
+            const int nrows = w.npass * C::R + 2 * C::PH;
+            for (int i = 0; i < nrows; ++i) {
+                RSR_WAIT(&a_empty[slot], par, 1, 0);
+                if (elect_one()) {
+                    if (ABL_NO_A_LOAD) { mbar_arrive(&a_full[slot]); }
+                    else {
+                        mbar_arrive_expect_tx(&a_full[slot], C::ROW_BYTES);
+                        tma_load_4d(sA + slot * C::SLOT, &p.tmA, &a_full[slot], 0, w.x0 - C::PW, w.y_b - C::PH + i, w.img);
+                    }
                 }
+                __syncwarp();
+                if (++slot == C::NR) { slot = 0; par ^= 1; }
             }
         }
     } else if (warp == 3) {
-        // ===== weight producer =====
-        if (lane == 0) {
-            uint32_t q = 0;
-            for (int item = blockIdx.x; item < p.total_items; item += gridDim.x) {
-                const WorkItem w = decode_item<C>(p, item);
-                for (int j = 0; j < w.npass; ++j)
-                    for (int t = 0; t < C::TAPS; ++t, ++q) {
-                        const uint32_t st = q % C::NBS, par = (q / C::NBS) & 1;
-                        mbar_wait(&b_empty[st], par ^ 1, p.fault, 2);
-                        mbar_arrive_expect_tx(&b_full[st], C::BST);
-                        tma_load_2d(sB + st * C::BST, &p.tmB, &b_full[st], 0, t * C::NCOL);
+        // ===== weight producer: one stage = TPS consecutive taps =====
+        uint32_t st = 0, par = 1;
+        ItemIter it = item_begin(p);
+        WorkItem w;
+        while (item_next<C>(p, it, w)) {
+            for (int j = 0; j < w.npass; ++j)
+                for (int sp = 0; sp < C::NSTG; ++sp) {
+                    RSR_WAIT(&b_empty[st], par, 2, 0);
+                    if (elect_one()) {
+                        if (ABL_NO_B_LOAD) { mbar_arrive(&b_full[st]); }
+                        else {
+                            mbar_arrive_expect_tx(&b_full[st], C::BST);   // rows past the last tap are zero-filled
+                            tma_load_2d(sB + st * C::BST, &p.tmB, &b_full[st], 0, sp * C::TPS * C::NCOL);
+                        }
                     }
+                    __syncwarp();
+                    if (++st == C::NBS) { st = 0; par ^= 1; }
+                }
+        }
+    } else if (warp == 2) {
+        // ===== partial-sum tile producer =====
+        // Tile order: per pass, group-major then row (the MMA issuer folds them in the same order).
+        if (C::NPIN > 0 && n_pin > 0) {
+            uint32_t st = 0, par = 1;
+            ItemIter it = item_begin(p);
+            WorkItem w;
+            while (item_next<C>(p, it, w)) {
+                for (int j = 0; j < w.npass; ++j)
+                    for (int k = 0; k < npg; ++k)
+                        for (int r = 0; r < C::R; ++r) {
+                            RSR_WAIT(&p_empty[st], par, 7, 0);
+                            if (elect_one()) {
+                                if (ABL_NO_PIN) { mbar_arrive(&p_full[st]); }
+                                else {
+                                    mbar_arrive_expect_tx(&p_full[st], C::PIN_BYTES);
+                                    tma_load_4d(sP + st * C::PIN_BYTES, &p.tmPin[pin_g[k]], &p_full[st], 0, w.x0,
+                                                w.y_b + j * C::R + r, w.img);
+                                }
+                            }
+                            __syncwarp();
+                            if (++st == NPB) { st = 0; par ^= 1; }
+                        }
             }
         }
     } else if (warp == 1) {
         // ===== MMA issuer =====
-        if (lane == 0) {
-            constexpr uint32_t HI = (uint32_t)make_sdesc_hi(8 * C::RB, C::SWZ);
-            constexpr uint32_t IDESC = make_idesc_bf16(128, C::NCOL);
-            const uint32_t sA_u = smem_u32(sA), sB_u = smem_u32(sB);
-            uint32_t s_base = 0, waited = 0, q = 0, pq = 0;
-            for (int item = blockIdx.x; item < p.total_items; item += gridDim.x) {
-                const WorkItem w = decode_item<C>(p, item);
-                for (int j = 0; j < w.npass; ++j, ++pq) {
-                    const uint32_t buf = pq & 1, tpar = (pq >> 1) & 1;
-                    mbar_wait(&t_empty[buf], tpar ^ 1, p.fault, 3);
-                    const uint32_t need = s_base + j * C::R + C::R + 2 * C::PH;
-                    while (waited < need) {
-                        mbar_wait(&a_full[waited % C::NR], (waited / C::NR) & 1, p.fault, 4);
-                        ++waited;
+        // Descriptors: the upper 32 bits are constant, the lower 32 are (address >> 4) | LBO << 16, so
+        // a descriptor for a neighbouring chunk / plane / pixel shift is one 32-bit add.  All ring
+        // positions advance incrementally (no division); the tap loop is fully unrolled so that tap
+        // offsets are immediates.  The issue thread must stay ahead of an 8-deep MMA queue
+        // (tests/cuda/umma_queue.cu), so every instruction here counts.
+        constexpr uint32_t HI = (uint32_t)make_sdesc_hi(8 * C::RB, C::SWZ);
+        constexpr uint32_t HI128 = (uint32_t)make_sdesc_hi(1024, UMMA_SW_128B);
+        constexpr uint32_t IDESC = make_idesc_bf16(128, C::NCOL);
+        constexpr uint32_t IDESC32 = make_idesc_bf16(128, 32);
+        constexpr uint32_t LBO = 1u << 16;
+        constexpr uint32_t MID = (C::RB / 2) >> 4;   // encoded offset of the mid plane
+        constexpr int WIN = C::R + 2 * C::PH;        // input rows one pass reads
+        constexpr int NEARLY = C::R < C::KH ? C::R : C::KH;   // rows retired during the pass
+        const uint32_t sA_e = (smem_u32(sA) >> 4) | LBO, sB_e = (smem_u32(sB) >> 4) | LBO;
+        const uint32_t sP_e = (smem_u32(sP) >> 4) | LBO, sI_e = (smem_u32(sI) >> 4) | LBO;
+        auto desc = [](uint32_t hi, uint32_t lo) { return ((uint64_t)hi << 32) | lo; };
+        uint32_t slot0 = 0;              // ring slot of the first window row of the current pass
+        uint32_t wslot = 0, wpar = 0;    // next row slot to wait for, and its parity
+        uint32_t bst = 0, bpar = 0;      // weight stage ring
+        uint32_t pst = 0, ppar = 0;      // partial-sum tile ring
+        uint32_t buf = 0, tpar = 1;      // accumulator buffer, parity of its t_empty barrier
+        if (n_pin > 0) mbar_wait(i_full, 0, p.fault, 8);
+        ItemIter it = item_begin(p);
+        WorkItem w;
+        while (item_next<C>(p, it, w)) {
+            for (int j = 0; j < w.npass; ++j) {
+                RSR_WAIT(&t_empty[buf], tpar, 3, 0);
+                // rows this pass adds to the window: all of it for the first pass of an item, else R
+                const int nnew = j == 0 ? WIN : C::R;
+                for (int i = 0; i < nnew; ++i) {
+                    RSR_WAIT(&a_full[wslot], wpar, 4, 1);
+                    if (++wslot == C::NR) { wslot = 0; wpar ^= 1; }
+                }
+                tc_fence_after();
+                // encoded smem addresses of the window rows
+                uint32_t arow[WIN];
+                {
+                    uint32_t sl = slot0;
+                    #pragma unroll
+                    for (int i = 0; i < WIN; ++i) {
+                        arow[i] = sA_e + sl * (C::SLOT >> 4);
+                        if (++sl == C::NR) sl = 0;
                     }
+                }
+                const uint32_t d_pass = tmem_base + buf * (C::R * C::NCOL);
+                int pin_k = 0;
+                #pragma unroll
+                for (int sp = 0; sp < C::NSTG; ++sp) {
+                    RSR_WAIT(&b_full[bst], bpar, 5, 2);
                     tc_fence_after();
-                    for (int t = 0; t < C::TAPS; ++t, ++q) {
-                        const int ta = t / C::KW, tb = t % C::KW;
-                        const uint32_t st = q % C::NBS;
-                        mbar_wait(&b_full[st], (q / C::NBS) & 1, p.fault, 5);
-                        tc_fence_after();
-                        const uint32_t b_addr = sB_u + st * C::BST;
+                    const uint32_t b_st = sB_e + bst * (C::BST >> 4);
+                    const long long ti0 = RSR_PROF_ON ? clock64() : 0;
+                    if (elect_one()) {
                         #pragma unroll
-                        for (int r = 0; r < C::R; ++r) {
-                            const uint32_t slot = (s_base + j * C::R + r + ta) % C::NR;
-                            const uint32_t a_addr = sA_u + slot * C::SLOT + tb * C::RB;
-                            const uint32_t d = tmem_base + buf * (C::R * C::NCOL) + r * C::NCOL;
-                            #pragma unroll
-                            for (int c = 0; c < C::KC; ++c) {
-                                const uint32_t a_hi = a_addr + c * 32, a_mid = a_addr + C::RB / 2 + c * 32;
-                                const uint32_t b_hi = b_addr + c * 32, b_mid = b_addr + C::RB / 2 + c * 32;
-                                const uint32_t bo_a = RSR_UMMA_BASE_OFFSET_POLICY ? ((a_addr >> 7) & 7) : 0;
-                                const uint64_t dA_hi = make_sdesc(a_hi, 16, HI, bo_a);
-                                const uint64_t dA_mid = make_sdesc(a_mid, 16, HI, bo_a);
-                                const uint64_t dB_hi = make_sdesc(b_hi, 16, HI, 0);
-                                const uint64_t dB_mid = make_sdesc(b_mid, 16, HI, 0);
-                                umma_f16(d, dA_hi, dB_hi, IDESC, (t | c) != 0);
-                                umma_f16(d, dA_mid, dB_hi, IDESC, 1);
-                                umma_f16(d, dA_hi, dB_mid, IDESC, 1);
+                        for (int tt = 0; tt < C::TPS; ++tt) {
+                            const int t = sp * C::TPS + tt;
+                            if (t < C::TAPS) {
+                                const int ta = t / C::KW, tb = t % C::KW;
+                                const uint32_t b_e = b_st + tt * (C::TAP_BYTES >> 4);
+                                #pragma unroll
+                                for (int r = 0; r < C::R; ++r) {
+                                    const uint32_t a_e = arow[r + ta] + tb * (C::RB >> 4);
+                                    const uint32_t d = d_pass + r * C::NCOL;
+                                    #pragma unroll
+                                    for (int c = 0; c < C::KC; ++c) {
+                                        if (ABL_NO_MMA) continue;
+                                        umma_f16(d, desc(HI, a_e + 2 * c), desc(HI, b_e + 2 * c), IDESC, (t | c) != 0);
+                                        umma_f16(d, desc(HI, a_e + MID + 2 * c), desc(HI, b_e + 2 * c), IDESC, 1);
+                                        umma_f16(d, desc(HI, a_e + 2 * c), desc(HI, b_e + MID + 2 * c), IDESC, 1);
+                                    }
+                                }
+                                // the top window rows are dead once their tap row is done: free them early
+                                if (tb == C::KW - 1 && ta < NEARLY) {
+                                    uint32_t sl = slot0 + ta;
+                                    if (sl >= C::NR) sl -= C::NR;
+                                    umma_commit(&a_empty[sl]);
+                                }
                             }
                         }
-                        umma_commit(&b_empty[st]);
+                        umma_commit(&b_empty[bst]);
                     }
-                    umma_commit(&t_full[buf]);
-                    const int n_retire = (j == w.npass - 1) ? C::R + 2 * C::PH : C::R;
-                    for (int i = 0; i < n_retire; ++i) umma_commit(&a_empty[(s_base + j * C::R + i) % C::NR]);
+                    __syncwarp();
+                    if (RSR_PROF_ON) prof_acc[4] += clock64() - ti0;
+                    if (++bst == C::NBS) { bst = 0; bpar ^= 1; }
+                    // fold the partial-sum tiles of group k (all R rows) after a fixed stage, so that
+                    // the accumulation order of a pixel never depends on how rows pair up into passes
+                    if (C::NPIN > 0) {
+                        while (pin_k < npg && sp == ((2 * pin_k + 1) * C::NSTG) / (2 * npg)) {
+                            const int g = pin_g[pin_k];
+                            for (int r = 0; r < C::R; ++r) {
+                                RSR_WAIT(&p_full[pst], ppar, 9, 3);
+                                tc_fence_after();
+                                const uint32_t pa = sP_e + pst * (C::PIN_BYTES >> 4);
+                                const uint32_t d = d_pass + r * C::NCOL + g * 32;
+                                if (elect_one()) {
+                                    #pragma unroll
+                                    for (int pl = 0; pl < 2; ++pl)
+                                        #pragma unroll
+                                        for (int c = 0; c < 2; ++c)
+                                            if (!ABL_NO_MMA && !ABL_NO_PIN_MMA)
+                                                umma_f16(d, desc(HI128, pa + pl * 4 + c * 2), desc(HI128, sI_e + c * 2), IDESC32, 1);
+                                    umma_commit(&p_empty[pst]);
+                                }
+                                __syncwarp();
+                                if (++pst == NPB) { pst = 0; ppar ^= 1; }
+                            }
+                            ++pin_k;
+                        }
+                    }
                 }
-                s_base += w.npass * C::R + 2 * C::PH;
+                const bool last = j == w.npass - 1;
+                const int n_retire = last ? WIN : C::R;
+                if (elect_one()) {
+                    umma_commit(&t_full[buf]);
+                    uint32_t sl = slot0 + NEARLY;
+                    if (sl >= C::NR) sl -= C::NR;
+                    for (int i = NEARLY; i < n_retire; ++i) {
+                        umma_commit(&a_empty[sl]);
+                        if (++sl == C::NR) sl = 0;
+                    }
+                }
+                __syncwarp();
+                slot0 += n_retire;
+                if (slot0 >= C::NR) slot0 -= C::NR;
+                if (slot0 >= C::NR) slot0 -= C::NR;
+                buf ^= 1;
+                if (buf == 0) tpar ^= 1;
             }
         }
     } else if (warp >= 4) {
         // ===== epilogue =====
         const int ew = warp - 4;  // == warp % 4: TMEM lane quarter this warp may read
-        uint32_t pq = 0;
-        for (int item = blockIdx.x; item < p.total_items; item += gridDim.x) {
-            const WorkItem w = decode_item<C>(p, item);
-            const int x = w.x0 + ew * 32 + lane;
-            for (int j = 0; j < w.npass; ++j, ++pq) {
-                const uint32_t buf = pq & 1, tpar = (pq >> 1) & 1;
-                mbar_wait(&t_full[buf], tpar, p.fault, 6);
+        const uint32_t stage0 = smem_u32(sO) + ew * (C::NOUT * 4096);
+        uint32_t buf = 0, tpar = 0, oc = 0;
+        ItemIter it = item_begin(p);
+        WorkItem w;
+        while (item_next<C>(p, it, w)) {
+            const int xw = w.x0 + ew * 32;  // first pixel of this warp's 32-pixel slice
+            const int x = xw + lane;
+            for (int j = 0; j < w.npass; ++j, buf ^= 1, tpar ^= (buf == 0)) {
+                SkipNb nb;
+                if (C::SHUF) {
+                    // the skip input does not depend on the MMAs: fetch the first row's before waiting
+                    const int y = w.y_b + j * C::R;
+                    if (y < w.y_e && x < p.W) load_skip_nb(p, w.img, y, x, nb);
+                }
+                RSR_WAIT(&t_full[buf], tpar, 6, 0);
                 tc_fence_after();
+                const long long te0 = RSR_PROF_ON ? clock64() : 0;
                 #pragma unroll 1
                 for (int r = 0; r < C::R; ++r) {
                     const int y = w.y_b + j * C::R + r;
-                    if (y >= w.y_e) break;  // warp-uniform
-                    const bool valid = x < p.W;
-                    const size_t px = ((size_t)w.img * p.H + y) * p.W + (valid ? x : 0);
+                    if (y >= w.y_e) break;   // warp-uniform
+                    if (xw >= p.W) break;    // warp-uniform: slice entirely right of the image
                     #pragma unroll 1
                     for (int g = 0; g < C::NG; ++g) {
                         const EpiGroup& eg = p.grp[g];
@@ -369,21 +557,116 @@ __global__ void __launch_bounds__(256, 1) conv_strip_kernel(const __grid_constan
                         uint32_t raw[32];
                         tmem_ld_32x32(tmem_base + ((uint32_t)(ew * 32) << 16) + buf * (C::R * C::NCOL) + r * C::NCOL + g * 32, raw);
                         tmem_ld_wait();
-                        if (valid) {
-                            float v[32];
-                            #pragma unroll
-                            for (int k = 0; k < 32; ++k) v[k] = __uint_as_float(raw[k]);
-                            if (eg.kind == EPI_ACT) epi_act(eg, v, px);
-                            else if (eg.kind == EPI_PARTIAL) epi_partial(eg, v, px);
-                            else epi_shuffle(p, eg, v, w.img, y, x);
+                        float v[32];
+                        #pragma unroll
+                        for (int k = 0; k < 32; ++k) v[k] = __uint_as_float(raw[k]);
+                        if (ABL_NO_EPI_OUT) { if (v[0] == 123.456f && p.out_f32) p.out_f32[0] = v[1]; ++oc; continue; }
+                        const uint32_t stage = stage0 + (oc % C::NOUT) * 4096;
+                        // the staging tile used NOUT stores ago must have been read out by the TMA engine
+                        {
+                            const long long t0s = RSR_PROF_ON ? clock64() : 0;
+                            if (elect_one())
+                                asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(C::NOUT - 1) : "memory");
+                            __syncwarp();
+                            if (RSR_PROF_ON) prof_acc[1] += clock64() - t0s;
                         }
+                        if (!C::SHUF) {
+                            epi_split_to_stage(eg, v, stage, lane);
+                            fence_proxy_async_smem();
+                            __syncwarp();
+                            if (elect_one()) {
+                                asm volatile(
+                                    "cp.async.bulk.tensor.4d.global.shared::cta.tile.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+                                    ::"l"(reinterpret_cast<uint64_t>(&p.tmOut[g])), "r"(stage), "r"(0), "r"(xw), "r"(y),
+                                      "r"(w.img)
+                                    : "memory");
+                                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                            }
+                        } else {
+                            // bias, depth-to-space, bilinear skip -> staging [3 dy][32 px * 9] -> coalesced stores
+                            if (r > 0 && x < p.W) load_skip_nb(p, w.img, y, x, nb);
+                            {
+                                const float4* b4 = reinterpret_cast<const float4*>(eg.bias);
+                                #pragma unroll
+                                for (int i = 0; i < 8; ++i) {
+                                    const float4 t = __ldg(b4 + i);
+                                    v[4 * i + 0] += t.x; v[4 * i + 1] += t.y; v[4 * i + 2] += t.z; v[4 * i + 3] += t.w;
+                                }
+                            }
+                            float o[3][9];
+                            if (x >= p.W) {
+                                #pragma unroll
+                                for (int a = 0; a < 3; ++a)
+                                    #pragma unroll
+                                    for (int b = 0; b < 3; ++b) { nb.v[a][b][0] = 0.f; nb.v[a][b][1] = 0.f; nb.v[a][b][2] = 0.f; }
+                            }
+                            shuffle_pixel(v, nb, o);
+                            const int npx_valid = min(32, p.W - xw);
+                            const size_t W3 = (size_t)p.W * 3;
+                            const size_t orow0 = ((size_t)w.img * p.H * 3 + (size_t)y * 3) * W3 + (size_t)xw * 3;  // in output pixels
+                            if (p.out_f32) {
+                                float* sf = reinterpret_cast<float*>(smem + C::OFF_O) + (ew * C::NOUT + (oc % C::NOUT)) * 1024;
+                                #pragma unroll
+                                for (int dy = 0; dy < 3; ++dy)
+                                    #pragma unroll
+                                    for (int k = 0; k < 9; ++k) sf[dy * 288 + lane * 9 + k] = o[dy][k];
+                                __syncwarp();
+                                const int nfl = npx_valid * 9;
+                                #pragma unroll
+                                for (int dy = 0; dy < 3; ++dy) {
+                                    float* dst = p.out_f32 + (orow0 + (size_t)dy * W3) * 3;
+                                    if (npx_valid == 32 && p.out_vec_ok) {
+                                        for (int i = lane; i < 72; i += 32)
+                                            reinterpret_cast<float4*>(dst)[i] = reinterpret_cast<const float4*>(sf + dy * 288)[i];
+                                    } else {
+                                        for (int i = lane; i < nfl; i += 32) dst[i] = sf[dy * 288 + i];
+                                    }
+                                }
+                            }
+                            if (p.out_u8) {
+                                // alumina data_to_img + to_rgba (main.rs:175): round(clamp(v,0,1)*255), alpha 255
+                                // (the host guarantees exactly one of out_f32 / out_u8, so the tile is shared)
+                                uint32_t* sq = reinterpret_cast<uint32_t*>(smem + C::OFF_O) + (ew * C::NOUT + (oc % C::NOUT)) * 1024;
+                                #pragma unroll
+                                for (int dy = 0; dy < 3; ++dy)
+                                    #pragma unroll
+                                    for (int dx = 0; dx < 3; ++dx) {
+                                        const uint32_t r8 = (uint32_t)(fminf(fmaxf(o[dy][dx * 3 + 0], 0.f), 1.f) * 255.0f + 0.5f);
+                                        const uint32_t g8 = (uint32_t)(fminf(fmaxf(o[dy][dx * 3 + 1], 0.f), 1.f) * 255.0f + 0.5f);
+                                        const uint32_t b8 = (uint32_t)(fminf(fmaxf(o[dy][dx * 3 + 2], 0.f), 1.f) * 255.0f + 0.5f);
+                                        sq[dy * 96 + lane * 3 + dx] = r8 | (g8 << 8) | (b8 << 16) | 0xFF000000u;
+                                    }
+                                __syncwarp();
+                                const int nu = npx_valid * 3;
+                                #pragma unroll
+                                for (int dy = 0; dy < 3; ++dy) {
+                                    uint32_t* dst = reinterpret_cast<uint32_t*>(p.out_u8) + orow0 + (size_t)dy * W3;
+                                    for (int i = lane; i < nu; i += 32) dst[i] = sq[dy * 96 + i];
+                                }
+                            }
+                            __syncwarp();
+                        }
+                        ++oc;
                     }
                 }
                 tc_fence_before();
                 __syncwarp();
+                if (RSR_PROF_ON) prof_acc[2] += clock64() - te0;
                 if (lane == 0) mbar_arrive(&t_empty[buf]);
             }
         }
+        // all TMA stores of this warp must have completed before the CTA exits
+        if (elect_one()) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    }
+    if (RSR_PROF_ON && lane == 0 && (warp < 5)) {
+        // row per CTA: [warp0: a_empty] [warp1: t_empty a_full b_full p_full] [warp2: p_empty] [warp3: b_empty]
+        //              [warp4: t_full store_read] [15: total cycles]
+        long long* dst = p.prof + (size_t)blockIdx.x * 16;
+        const int base = warp == 0 ? 0 : warp == 1 ? 1 : warp == 2 ? 5 : warp == 3 ? 6 : 7;
+        const int n = warp == 1 ? 4 : warp == 4 ? 2 : 1;
+        for (int i = 0; i < n; ++i) dst[base + i] = prof_acc[i];
+        if (warp == 1) { dst[9] = prof_acc[4]; dst[15] = clock64() - prof_t0; }
+        if (warp == 4) dst[10] = prof_acc[2];
     }
     tc_fence_before();
     __syncthreads();

@@ -80,11 +80,12 @@ static Layout make_layout(int factor) {
 }
 
 // --------------------------------------------------------------------------- kernel configs
-using Cfg0 = ConvCfg<5, 1, 64, 1, 4>;    // conv0 on the x-im2col'd input (K = 5 taps x 16)
-using Cfg1 = ConvCfg<5, 5, 128, 3, 2>;   // f  -> conv1 | conv2 | conv3
-using Cfg2 = ConvCfg<3, 3, 128, 3, 2>;   // l1 -> conv5 | conv6 | conv7
-using Cfg3 = ConvCfg<3, 3, 128, 2, 4>;   // l2 -> conv8 | conv9
-using Cfg4 = ConvCfg<3, 3, 128, 1, 4>;   // l3 -> conv10 (+ expand + bilinear skip)
+//                      KH KW  RB NG R NR TPS NBS NPIN NOUT SHUF
+using Cfg0 = ConvCfg<5, 1,  64, 1, 4, 12, 5, 2, 0, 2, false>;  // conv0 on the x-im2col'd input (K = 5 taps x 16)
+using Cfg1 = ConvCfg<5, 5, 128, 3, 2,  7, 2, 3, 0, 2, false>;  // f  -> conv1 | conv2 | conv3
+using Cfg2 = ConvCfg<3, 3, 128, 3, 2,  5, 2, 3, 2, 2, false>;  // l1 -> conv5 | conv6 | conv7   (+ P2, P3)
+using Cfg3 = ConvCfg<3, 3, 128, 2, 2,  6, 2, 3, 2, 2, false>;  // l2 -> conv8 | conv9           (+ P3, E)
+using Cfg4 = ConvCfg<3, 3, 128, 1, 2,  6, 3, 3, 3, 2, true>;   // l3 -> conv10 (+ E) + expand + bilinear skip
 
 enum { K_PACK = 0, K_CONV0, K_F, K_L1, K_L2, K_L3, K_COUNT };
 static const char* kKernelNames[K_COUNT] = {"pack_input", "conv0", "conv1|2|3", "conv5|6|7", "conv8|9",
@@ -149,6 +150,7 @@ struct rsr_ctx {
     cudaStream_t own_stream = nullptr, stream = nullptr;
     // packed weights (bf16 hi|mid), biases / slopes (32 floats each, zero padded)
     __nv_bfloat16 *w0 = nullptr, *w1 = nullptr, *w2 = nullptr, *w3 = nullptr, *w4 = nullptr;
+    __nv_bfloat16* ident = nullptr;  // [32][64] identity tile (partial-sum fold)
     float* vecs = nullptr;  // 9 x 32 floats: f_bias f_activ l1_bias l1_activ l2_bias l2_activ l3_bias l3_activ expand_bias
     // workspace
     DevBuf xcol, xf4, actA, actB, partA, partB, out_f32, out_u8, in_stage;
@@ -157,6 +159,8 @@ struct rsr_ctx {
     bool timed = false;
     int last_launches = 0;
     int stop_after = -1;  // test hook
+    long long* prof = nullptr;  // test hook: [K_COUNT][256][16] wait-cycle counters
+    int prof_grid[K_COUNT] = {};
     PFN_cuTensorMapEncodeTiled_v12000 encode = nullptr;
 };
 
@@ -219,7 +223,7 @@ extern "C" void rsr_destroy(rsr_ctx* c) {
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
     cudaFree(c->w0); cudaFree(c->w1); cudaFree(c->w2); cudaFree(c->w3); cudaFree(c->w4);
-    cudaFree(c->vecs); cudaFree(c->fault);
+    cudaFree(c->vecs); cudaFree(c->fault); cudaFree(c->ident); cudaFree(c->prof);
     release(c->xcol); release(c->xf4); release(c->actA); release(c->actB); release(c->partA);
     release(c->partB); release(c->out_f32); release(c->out_u8); release(c->in_stage);
     for (auto& e : c->ev) if (e) cudaEventDestroy(e);
@@ -300,6 +304,11 @@ static int create_impl(rsr_ctx* c, const float* params) {
                                L.l3_bias, L.l3_activ, L.expand_bias};
         for (int i = 0; i < 9; ++i) memcpy(&v[i * 32], params + src[i], sizeof(float) * (i == 8 ? L.ce : 32));
         if (int rc = upload(&c->vecs, v.data(), v.size() * 4)) return rc;
+    }
+    {
+        std::vector<__nv_bfloat16> id((size_t)32 * 64, __float2bfloat16_rn(0.f));
+        for (int n = 0; n < 32; ++n) id[(size_t)n * 64 + n] = __float2bfloat16_rn(1.0f);
+        if (int rc = upload(&c->ident, id.data(), id.size() * 2)) return rc;
     }
     CUDA_TRY(cudaFuncSetAttribute(conv_strip_kernel<Cfg0>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg0::SMEM_BYTES));
     CUDA_TRY(cudaFuncSetAttribute(conv_strip_kernel<Cfg1>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg1::SMEM_BYTES));
@@ -396,30 +405,13 @@ static int make_map_w(rsr_ctx* c, CUtensorMap* m, const void* base, int elems, i
     return 0;
 }
 
-// Chooses the rows-per-work-item so that the persistent grid is balanced: minimises
-// ceil(items / SMs) * (rows per item + pipeline-fill overhead).
-static void plan_items(ConvParams& p, int R, int PH, int num_sms) {
-    const int rows = p.row_end - p.row_begin;
-    p.n_strips = (p.W + 127) / 128;
-    const int per_row_items = p.NIMG * p.n_strips;
-    double best = 1e300;
-    int best_seg = ((rows + R - 1) / R) * R;
-    for (int seg = R; seg <= ((rows + R - 1) / R) * R; seg += R) {
-        const int nseg = (rows + seg - 1) / seg;
-        const long items = (long)per_row_items * nseg;
-        const long waves = (items + num_sms - 1) / num_sms;
-        const double cost = (double)waves * (seg + 0.75 * (2 * PH) + 1.0);
-        if (cost < best - 1e-9) { best = cost; best_seg = seg; }
-    }
-    p.seg_rows = best_seg;
-    p.n_segs = (rows + best_seg - 1) / best_seg;
-    p.total_items = per_row_items * p.n_segs;
-}
-
 template <class C>
-static int launch_conv(rsr_ctx* c, ConvParams& p) {
-    plan_items(p, C::R, C::PH, c->num_sms);
-    const int grid = p.total_items < c->num_sms ? p.total_items : c->num_sms;
+static int launch_conv(rsr_ctx* c, ConvParams& p, int kindex) {
+    p.n_strips = (p.W + 127) / 128;
+    p.total_rowtiles = (long long)p.NIMG * p.n_strips * (p.row_end - p.row_begin);
+    const int grid = (int)std::min<long long>(p.total_rowtiles, c->num_sms);
+    p.prof = (c->prof && grid <= 256) ? c->prof + (size_t)kindex * 256 * 16 : nullptr;
+    c->prof_grid[kindex] = grid;
     conv_strip_kernel<C><<<grid, 256, C::SMEM_BYTES, c->stream>>>(p);
     CUDA_TRY(cudaGetLastError());
     c->last_launches++;
@@ -431,6 +423,7 @@ static int forward_device(rsr_ctx* c, const void* d_in, bool u8, int in_ch, int 
                           uint8_t* d_out_u8) {
     if (!c) return fail(RSR_E_BAD_ARG, "ctx is null");
     if (!d_in || (!d_out_f32 && !d_out_u8)) return fail(RSR_E_BAD_ARG, "null buffer");
+    if (d_out_f32 && d_out_u8) return fail(RSR_E_BAD_ARG, "exactly one of the f32 / RGBA outputs may be requested");
     if (n < 1 || w < 1 || h < 1) return fail(RSR_E_BAD_ARG, "bad dimensions n=%d w=%d h=%d", n, w, h);
     if (u8 && in_ch != 3 && in_ch != 4) return fail(RSR_E_BAD_ARG, "in_channels must be 3 or 4 (got %d)", in_ch);
     CUDA_TRY(cudaSetDevice(c->device));
@@ -447,9 +440,11 @@ static int forward_device(rsr_ctx* c, const void* d_in, bool u8, int in_ch, int 
     __nv_bfloat16* l1_act = (__nv_bfloat16*)c->actB.p;  // l1, later l3
     __nv_bfloat16* l2_act = f_act;
     __nv_bfloat16* l3_act = l1_act;
-    float* P2 = (float*)c->partA.p;  // conv2(f) partial of l2_conv; later E (expand partial)
-    float* P3 = (float*)c->partB.p;  // conv3(f) (+conv6(l1)) partial of l3_conv
-    float* E = P2;
+    __nv_bfloat16* P2 = (__nv_bfloat16*)c->partA.p;  // conv2(f): partial of l2_conv; later E (expand partial)
+    __nv_bfloat16* P3 = (__nv_bfloat16*)c->partB.p;  // conv3(f) (+conv6(l1)): partial of l3_conv
+    __nv_bfloat16* P3b = P3;                          // P3 + conv6(l1), updated in place (aliasing)
+    __nv_bfloat16* E = P2;                            // conv7(l1)
+    __nv_bfloat16* Eb = E;                            // E + conv9(l2), updated in place
     const float* V = c->vecs;
     const float *f_bias = V, *f_slope = V + 32, *l1_bias = V + 64, *l1_slope = V + 96, *l2_bias = V + 128,
                 *l2_slope = V + 160, *l3_bias = V + 192, *l3_slope = V + 224, *e_bias = V + 256;
@@ -469,56 +464,75 @@ static int forward_device(rsr_ctx* c, const void* d_in, bool u8, int in_ch, int 
     ConvParams p{};
     p.W = w; p.H = h; p.NIMG = n; p.row_begin = 0; p.row_end = h; p.factor = c->factor; p.fault = c->fault;
     p.xf4 = (const float4*)c->xf4.p;
+    if (int rc = make_map_w(c, &p.tmI, c->ident, 64, 32, 32)) return rc;
+    const EpiGroup none{EPI_NONE, 0, nullptr, nullptr};
+    auto in_map = [&](CUtensorMap* m, const void* base, int boxw) { return make_map_act(c, m, base, 64, w, h, n, boxw); };
 
     // conv0: xcol -> f = BeLU(conv0(x) + f_bias)                       network.rs:33-35
     if (int rc = make_map_act(c, &p.tmA, xcol, 32, w, h, n, Cfg0::BOXW)) return rc;
-    if (int rc = make_map_w(c, &p.tmB, c->w0, 32, 5 * 32, 32)) return rc;
-    p.grp[0] = EpiGroup{EPI_ACT, 0, nullptr, nullptr, f_act, f_bias, f_slope};
-    p.grp[1] = EpiGroup{}; p.grp[2] = EpiGroup{};
-    if (int rc = launch_conv<Cfg0>(c, p)) return rc;
+    if (int rc = make_map_w(c, &p.tmB, c->w0, 32, 5 * 32, Cfg0::TPS * 32)) return rc;
+    if (int rc = in_map(&p.tmOut[0], f_act, 32)) return rc;
+    p.grp[0] = EpiGroup{EPI_ACT, 0, f_bias, f_slope};
+    p.grp[1] = none; p.grp[2] = none;
+    if (int rc = launch_conv<Cfg0>(c, p, 1)) return rc;
     CUDA_TRY(cudaEventRecord(c->ev[2], c->stream));
     if (c->stop_after == 1) return 0;
 
     // f -> l1 = BeLU(conv1(f) + l1_bias); P2 = conv2(f); P3 = conv3(f)  network.rs:60-62,50,54
-    if (int rc = make_map_act(c, &p.tmA, f_act, 64, w, h, n, Cfg1::BOXW)) return rc;
-    if (int rc = make_map_w(c, &p.tmB, c->w1, 64, 25 * 96, 96)) return rc;
-    p.grp[0] = EpiGroup{EPI_ACT, 0, nullptr, nullptr, l1_act, l1_bias, l1_slope};
-    p.grp[1] = EpiGroup{EPI_PARTIAL, 0, nullptr, P2, nullptr, nullptr, nullptr};
-    p.grp[2] = EpiGroup{EPI_PARTIAL, 0, nullptr, P3, nullptr, nullptr, nullptr};
-    if (int rc = launch_conv<Cfg1>(c, p)) return rc;
+    if (int rc = in_map(&p.tmA, f_act, Cfg1::BOXW)) return rc;
+    if (int rc = make_map_w(c, &p.tmB, c->w1, 64, 25 * 96, Cfg1::TPS * 96)) return rc;
+    if (int rc = in_map(&p.tmOut[0], l1_act, 32)) return rc;
+    if (int rc = in_map(&p.tmOut[1], P2, 32)) return rc;
+    if (int rc = in_map(&p.tmOut[2], P3, 32)) return rc;
+    p.grp[0] = EpiGroup{EPI_ACT, 0, l1_bias, l1_slope};
+    p.grp[1] = EpiGroup{EPI_RAW, 0, nullptr, nullptr};
+    p.grp[2] = EpiGroup{EPI_RAW, 0, nullptr, nullptr};
+    if (int rc = launch_conv<Cfg1>(c, p, 2)) return rc;
     CUDA_TRY(cudaEventRecord(c->ev[3], c->stream));
     if (c->stop_after == 2) return 0;
 
-    // l1 -> l2 = BeLU(P2 + conv5(l1) + l2_bias); P3 += conv6(l1); E = conv7(l1)   :65-67,51,55
-    if (int rc = make_map_act(c, &p.tmA, l1_act, 64, w, h, n, Cfg2::BOXW)) return rc;
-    if (int rc = make_map_w(c, &p.tmB, c->w2, 64, 9 * 96, 96)) return rc;
-    p.grp[0] = EpiGroup{EPI_ACT, 0, P2, nullptr, l2_act, l2_bias, l2_slope};
-    p.grp[1] = EpiGroup{EPI_PARTIAL, 0, P3, P3, nullptr, nullptr, nullptr};
-    p.grp[2] = EpiGroup{EPI_PARTIAL, 0, nullptr, E, nullptr, nullptr, nullptr};
-    if (int rc = launch_conv<Cfg2>(c, p)) return rc;
+    // l1 -> l2 = BeLU(P2 + conv5(l1) + l2_bias); P3b = P3 + conv6(l1); E = conv7(l1)   :65-67,51,55
+    // (l2 overwrites f, E overwrites P2: both are dead; a thread block only overwrites pixels whose
+    //  partial tile it has already consumed — see DESIGN.md "aliasing")
+    if (int rc = in_map(&p.tmA, l1_act, Cfg2::BOXW)) return rc;
+    if (int rc = make_map_w(c, &p.tmB, c->w2, 64, 9 * 96, Cfg2::TPS * 96)) return rc;
+    if (int rc = in_map(&p.tmPin[0], P2, 128)) return rc;
+    if (int rc = in_map(&p.tmPin[1], P3, 128)) return rc;
+    if (int rc = in_map(&p.tmOut[0], l2_act, 32)) return rc;
+    if (int rc = in_map(&p.tmOut[1], P3b, 32)) return rc;
+    if (int rc = in_map(&p.tmOut[2], E, 32)) return rc;
+    p.grp[0] = EpiGroup{EPI_ACT, 1, l2_bias, l2_slope};
+    p.grp[1] = EpiGroup{EPI_RAW, 1, nullptr, nullptr};
+    p.grp[2] = EpiGroup{EPI_RAW, 0, nullptr, nullptr};
+    if (int rc = launch_conv<Cfg2>(c, p, 3)) return rc;
     CUDA_TRY(cudaEventRecord(c->ev[4], c->stream));
     if (c->stop_after == 3) return 0;
 
-    // l2 -> l3 = BeLU(P3 + conv8(l2) + l3_bias); E += conv9(l2)                   :69-70,52,56
-    if (int rc = make_map_act(c, &p.tmA, l2_act, 64, w, h, n, Cfg3::BOXW)) return rc;
-    if (int rc = make_map_w(c, &p.tmB, c->w3, 64, 9 * 64, 64)) return rc;
-    p.grp[0] = EpiGroup{EPI_ACT, 0, P3, nullptr, l3_act, l3_bias, l3_slope};
-    p.grp[1] = EpiGroup{EPI_PARTIAL, 0, E, E, nullptr, nullptr, nullptr};
-    p.grp[2] = EpiGroup{};
-    if (int rc = launch_conv<Cfg3>(c, p)) return rc;
+    // l2 -> l3 = BeLU(P3b + conv8(l2) + l3_bias); Eb = E + conv9(l2)                  :69-70,52,56
+    if (int rc = in_map(&p.tmA, l2_act, Cfg3::BOXW)) return rc;
+    if (int rc = make_map_w(c, &p.tmB, c->w3, 64, 9 * 64, Cfg3::TPS * 64)) return rc;
+    if (int rc = in_map(&p.tmPin[0], P3b, 128)) return rc;
+    if (int rc = in_map(&p.tmPin[1], E, 128)) return rc;
+    if (int rc = in_map(&p.tmOut[0], l3_act, 32)) return rc;
+    if (int rc = in_map(&p.tmOut[1], Eb, 32)) return rc;
+    p.grp[0] = EpiGroup{EPI_ACT, 1, l3_bias, l3_slope};
+    p.grp[1] = EpiGroup{EPI_RAW, 1, nullptr, nullptr};
+    p.grp[2] = none;
+    if (int rc = launch_conv<Cfg3>(c, p, 4)) return rc;
     CUDA_TRY(cudaEventRecord(c->ev[5], c->stream));
     if (c->stop_after == 4) return 0;
 
-    // l3 -> output = Expand(E + conv10(l3) + expand_bias) + LinearInterp(x)       :72,38-39,27
-    if (int rc = make_map_act(c, &p.tmA, l3_act, 64, w, h, n, Cfg4::BOXW)) return rc;
-    if (int rc = make_map_w(c, &p.tmB, c->w4, 64, 9 * 32, 32)) return rc;
-    p.grp[0] = EpiGroup{EPI_SHUFFLE, 0, E, nullptr, nullptr, e_bias, nullptr};
-    p.grp[1] = EpiGroup{}; p.grp[2] = EpiGroup{};
+    // l3 -> output = Expand(Eb + conv10(l3) + expand_bias) + LinearInterp(x)          :72,38-39,27
+    if (int rc = in_map(&p.tmA, l3_act, Cfg4::BOXW)) return rc;
+    if (int rc = make_map_w(c, &p.tmB, c->w4, 64, 9 * 32, Cfg4::TPS * 32)) return rc;
+    if (int rc = in_map(&p.tmPin[0], Eb, 128)) return rc;
+    p.grp[0] = EpiGroup{EPI_SHUFFLE, 1, e_bias, nullptr};
+    p.grp[1] = none; p.grp[2] = none;
     p.out_f32 = d_out_f32;
     p.out_u8 = d_out_u8;
-    if (int rc = launch_conv<Cfg4>(c, p)) return rc;
+    p.out_vec_ok = (w % 4 == 0) && ((reinterpret_cast<uintptr_t>(d_out_f32) & 15) == 0);
+    if (int rc = launch_conv<Cfg4>(c, p, 5)) return rc;
     CUDA_TRY(cudaEventRecord(c->ev[6], c->stream));
-    if (c->stop_after == 5) return 0;
     c->timed = true;
     return 0;
 }
@@ -607,14 +621,32 @@ extern "C" int rsr_debug_read_node(rsr_ctx* c, int which, float* out, size_t npx
     if (int rc = rsr_synchronize(c)) return rc;
     DevBuf* b = which == 0 ? &c->actA : which == 1 ? &c->actB : which == 2 ? &c->partA : which == 3 ? &c->partB : nullptr;
     if (!b || !b->p || b->cap < npx * 128) return fail(RSR_E_BAD_ARG, "node %d not available for %zu pixels", which, npx);
-    if (which >= 2) {
-        CUDA_TRY(cudaMemcpy(out, b->p, npx * 128, cudaMemcpyDeviceToHost));
-        return 0;
-    }
     std::vector<__nv_bfloat16> tmp(npx * 64);
     CUDA_TRY(cudaMemcpy(tmp.data(), b->p, npx * 128, cudaMemcpyDeviceToHost));
     for (size_t i = 0; i < npx; ++i)
         for (int ch = 0; ch < 32; ++ch)
             out[i * 32 + ch] = __bfloat162float(tmp[i * 64 + ch]) + __bfloat162float(tmp[i * 64 + 32 + ch]);
     return 0;
+}
+
+extern "C" int rsr_debug_profile(rsr_ctx* c, int enable) {
+    if (!c) return fail(RSR_E_BAD_ARG, "ctx is null");
+    CUDA_TRY(cudaSetDevice(c->device));
+    if (enable && !c->prof) {
+        CUDA_TRY(cudaMalloc((void**)&c->prof, sizeof(long long) * K_COUNT * 256 * 16));
+        CUDA_TRY(cudaMemset(c->prof, 0, sizeof(long long) * K_COUNT * 256 * 16));
+    } else if (!enable && c->prof) {
+        if (int rc = rsr_synchronize(c)) return rc;
+        cudaFree(c->prof);
+        c->prof = nullptr;
+    }
+    return 0;
+}
+// out: [grid][16] counters of launch `kindex` of the most recent call; returns the grid size.
+extern "C" int rsr_debug_read_profile(rsr_ctx* c, int kindex, long long* out, int cap_rows) {
+    if (!c || !out || kindex < 1 || kindex >= K_COUNT || !c->prof) return fail(RSR_E_BAD_ARG, "profile not enabled");
+    if (int rc = rsr_synchronize(c)) return rc;
+    const int rows = c->prof_grid[kindex] < cap_rows ? c->prof_grid[kindex] : cap_rows;
+    CUDA_TRY(cudaMemcpy(out, c->prof + (size_t)kindex * 256 * 16, sizeof(long long) * rows * 16, cudaMemcpyDeviceToHost));
+    return rows;
 }

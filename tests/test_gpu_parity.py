@@ -176,7 +176,7 @@ def test_error_paths(R, ups):
         u.forward_u8(np.zeros((4, 4, 2), np.uint8))
     with pytest.raises(ValueError):
         u.forward(np.zeros((4, 4, 4), np.float32))
-    with pytest.raises(R.RsrError):
+    with pytest.raises(ValueError):
         u.forward_band(np.zeros((4, 4, 3), np.float32), 3, 3)
 
 
