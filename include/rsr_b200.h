@@ -74,6 +74,16 @@ int rsr_upscale_device_u8(rsr_ctx* ctx, const uint8_t* d_in, int n, int w, int h
                           float* d_out_f32, uint8_t* d_out_rgba);
 int rsr_synchronize(rsr_ctx* ctx);
 
+/* Pipelined host entry points: submit returns at once with a ticket (>= 0, or a negative error);
+ * the frame's host->device copy, forward pass and device->host copy are enqueued on three streams
+ * so that the copies of neighbouring frames overlap the compute of the current one (3 frames in
+ * flight).  `in` and `out_rgba` must stay valid — and should be pinned host memory for the copies to
+ * be asynchronous — until rsr_wait(ticket) returns.  Frames complete in submission order. */
+int rsr_submit_u8(rsr_ctx* ctx, const uint8_t* in, int w, int h, int in_channels, uint8_t* out_rgba);
+int rsr_submit_f32(rsr_ctx* ctx, const float* in_hwc3, int w, int h, float* out_hwc3);
+int rsr_wait(rsr_ctx* ctx, int ticket);
+int rsr_wait_all(rsr_ctx* ctx);
+
 /* Spatial-band entry point for sharding one large frame across GPUs (scheme
  * "overlap-recompute"): `in` holds rows [band_y0 - top_halo, band_y1 + bottom_halo) of a frame,
  * where the halos are min(7, rows available) — 7 = receptive field of the net.  Writes the

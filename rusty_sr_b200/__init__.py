@@ -117,6 +117,33 @@ class Upscaler:
             return out
         raise ValueError("expected [H][W][C] or [N][H][W][C]")
 
+    # -- pipelined host calls: copies of neighbouring frames overlap the compute -----------------
+    def submit_u8(self, img: np.ndarray, out: np.ndarray) -> int:
+        """Enqueue one frame (u8 [H][W][3|4] -> u8 RGBA `out`, both C-contiguous and ideally pinned);
+        returns a ticket for wait().  Buffers must stay alive until then."""
+        assert img.dtype == np.uint8 and img.flags.c_contiguous and out.dtype == np.uint8 and out.flags.c_contiguous
+        H, W, C = img.shape
+        assert out.shape == (H * self.factor, W * self.factor, 4)
+        t = self._L.rsr_submit_u8(self._h, _as_ptr(img), W, H, C, _as_ptr(out))
+        if t < 0:
+            _lib.check(t)
+        return t
+
+    def submit_f32(self, x: np.ndarray, out: np.ndarray) -> int:
+        assert x.dtype == np.float32 and x.flags.c_contiguous and out.dtype == np.float32 and out.flags.c_contiguous
+        H, W, _ = x.shape
+        assert out.shape == (H * self.factor, W * self.factor, 3)
+        t = self._L.rsr_submit_f32(self._h, _as_ptr(x), W, H, _as_ptr(out))
+        if t < 0:
+            _lib.check(t)
+        return t
+
+    def wait(self, ticket: int) -> None:
+        _lib.check(self._L.rsr_wait(self._h, ticket))
+
+    def wait_all(self) -> None:
+        _lib.check(self._L.rsr_wait_all(self._h))
+
     def forward_band(self, rows: np.ndarray, top_halo: int, bottom_halo: int) -> np.ndarray:
         """One horizontal band of a larger frame (spatial sharding, overlap-recompute)."""
         x = np.ascontiguousarray(rows, dtype=np.float32)

@@ -19,7 +19,7 @@ RSR_E_UNSUPPORTED = -5
 EXPORTS = (
     "rsr_num_params", "rsr_create", "rsr_destroy", "rsr_upscale_f32", "rsr_upscale_u8",
     "rsr_upscale_batch_f32", "rsr_upscale_batch_u8", "rsr_upscale_device_f32",
-    "rsr_upscale_device_u8", "rsr_synchronize", "rsr_upscale_band_f32", "rsr_set_stream",
+    "rsr_upscale_device_u8", "rsr_synchronize", "rsr_submit_u8", "rsr_submit_f32", "rsr_wait", "rsr_wait_all", "rsr_upscale_band_f32", "rsr_set_stream",
     "rsr_last_kernel_times", "rsr_kernel_name", "rsr_last_launch_count", "rsr_last_error",
     "rsr_last_error_code", "rsr_version", "rsr_debug_stop_after", "rsr_debug_read_node",
     "rsr_debug_profile", "rsr_debug_read_profile",
@@ -57,6 +57,10 @@ def load() -> ctypes.CDLL:
     L.rsr_upscale_device_f32.argtypes = [vp, vp, ci, ci, ci, vp, vp]
     L.rsr_upscale_device_u8.argtypes = [vp, vp, ci, ci, ci, ci, vp, vp]
     L.rsr_synchronize.argtypes = [vp]
+    L.rsr_submit_u8.argtypes = [vp, u8p, ci, ci, ci, u8p]
+    L.rsr_submit_f32.argtypes = [vp, vp, ci, ci, vp]
+    L.rsr_wait.argtypes = [vp, ci]
+    L.rsr_wait_all.argtypes = [vp]
     L.rsr_upscale_band_f32.argtypes = [vp, vp, ci, ci, ci, ci, vp]
     L.rsr_set_stream.argtypes = [vp, vp]
     L.rsr_last_kernel_times.argtypes = [vp, fp, ci]
@@ -75,7 +79,8 @@ def load() -> ctypes.CDLL:
     L.rsr_debug_read_profile.argtypes = [vp, ci, vp, ci]
     L.rsr_debug_read_profile.restype = ci
     for name in ("rsr_upscale_f32", "rsr_upscale_u8", "rsr_upscale_batch_f32", "rsr_upscale_batch_u8",
-                 "rsr_upscale_device_f32", "rsr_upscale_device_u8", "rsr_synchronize",
+                 "rsr_upscale_device_f32", "rsr_upscale_device_u8", "rsr_synchronize", "rsr_submit_u8",
+                 "rsr_submit_f32", "rsr_wait", "rsr_wait_all", "rsr_submit_u8", "rsr_submit_f32", "rsr_wait", "rsr_wait_all",
                  "rsr_upscale_band_f32", "rsr_set_stream", "rsr_last_kernel_times",
                  "rsr_last_launch_count"):
         getattr(L, name).restype = ci

@@ -159,6 +159,14 @@ struct rsr_ctx {
     bool timed = false;
     int last_launches = 0;
     int stop_after = -1;  // test hook
+    // pipelined host API: 3 frames in flight
+    struct Slot {
+        DevBuf in, out;
+        cudaEvent_t ev_in = nullptr, ev_done = nullptr, ev_out = nullptr;
+        bool used = false;
+    } slot[3];
+    cudaStream_t s_h2d = nullptr, s_d2h = nullptr;
+    long next_ticket = 0;
     long long* prof = nullptr;  // test hook: [K_COUNT][256][16] wait-cycle counters
     int prof_grid[K_COUNT] = {};
     PFN_cuTensorMapEncodeTiled_v12000 encode = nullptr;
@@ -227,6 +235,14 @@ extern "C" void rsr_destroy(rsr_ctx* c) {
     release(c->xcol); release(c->xf4); release(c->actA); release(c->actB); release(c->partA);
     release(c->partB); release(c->out_f32); release(c->out_u8); release(c->in_stage);
     for (auto& e : c->ev) if (e) cudaEventDestroy(e);
+    for (auto& sl : c->slot) {
+        release(sl.in); release(sl.out);
+        if (sl.ev_in) cudaEventDestroy(sl.ev_in);
+        if (sl.ev_done) cudaEventDestroy(sl.ev_done);
+        if (sl.ev_out) cudaEventDestroy(sl.ev_out);
+    }
+    if (c->s_h2d) cudaStreamDestroy(c->s_h2d);
+    if (c->s_d2h) cudaStreamDestroy(c->s_d2h);
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
     delete c;
 }
@@ -255,6 +271,13 @@ static int create_impl(rsr_ctx* c, const float* params) {
     CUDA_TRY(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
     c->stream = c->own_stream;
     for (auto& e : c->ev) CUDA_TRY(cudaEventCreate(&e));
+    CUDA_TRY(cudaStreamCreateWithFlags(&c->s_h2d, cudaStreamNonBlocking));
+    CUDA_TRY(cudaStreamCreateWithFlags(&c->s_d2h, cudaStreamNonBlocking));
+    for (auto& sl : c->slot) {
+        CUDA_TRY(cudaEventCreateWithFlags(&sl.ev_in, cudaEventDisableTiming));
+        CUDA_TRY(cudaEventCreateWithFlags(&sl.ev_done, cudaEventDisableTiming));
+        CUDA_TRY(cudaEventCreateWithFlags(&sl.ev_out, cudaEventDisableTiming));
+    }
     CUDA_TRY(cudaMalloc((void**)&c->fault, sizeof(int)));
     CUDA_TRY(cudaMemset(c->fault, 0, sizeof(int)));
 
@@ -575,6 +598,71 @@ static int upscale_host(rsr_ctx* c, const void* in, bool u8, int in_ch, int n, i
         CUDA_TRY(cudaMemcpyAsync(out_u8, d_u8 + (size_t)out_row_begin * orow_px * 4,
                                  (out_rows < 0 ? opx : (size_t)out_rows * orow_px) * 4, cudaMemcpyDeviceToHost,
                                  c->stream));
+    return rsr_synchronize(c);
+}
+
+// ---- pipelined host API ---------------------------------------------------------------------
+static int submit_host(rsr_ctx* c, const void* in, bool u8, int in_ch, int w, int h, float* out_f32, uint8_t* out_u8) {
+    if (!c) return fail(RSR_E_BAD_ARG, "ctx is null");
+    if (!in || (!out_f32 && !out_u8)) return fail(RSR_E_BAD_ARG, "null buffer");
+    if (w < 1 || h < 1) return fail(RSR_E_BAD_ARG, "bad dimensions w=%d h=%d", w, h);
+    if (u8 && in_ch != 3 && in_ch != 4) return fail(RSR_E_BAD_ARG, "in_channels must be 3 or 4 (got %d)", in_ch);
+    CUDA_TRY(cudaSetDevice(c->device));
+    const long ticket = c->next_ticket;
+    rsr_ctx::Slot& sl = c->slot[ticket % 3];
+    const int F = c->factor;
+    const size_t npx = (size_t)w * h, opx = npx * F * F;
+    const size_t in_bytes = u8 ? npx * in_ch : npx * 3 * sizeof(float);
+    const size_t out_bytes = out_f32 ? opx * 3 * sizeof(float) : opx * 4;
+    if (in_bytes > sl.in.cap || out_bytes > sl.out.cap) {
+        // growing a slot re-allocates: drain whatever still uses it first
+        if (sl.used) CUDA_TRY(cudaEventSynchronize(sl.ev_out));
+        if (int rc = ensure(sl.in, in_bytes)) return rc;
+        if (int rc = ensure(sl.out, out_bytes)) return rc;
+    }
+    // H2D may overwrite the slot's input only after the forward pass that read it has finished
+    if (sl.used) CUDA_TRY(cudaStreamWaitEvent(c->s_h2d, sl.ev_done, 0));
+    CUDA_TRY(cudaMemcpyAsync(sl.in.p, in, in_bytes, cudaMemcpyHostToDevice, c->s_h2d));
+    CUDA_TRY(cudaEventRecord(sl.ev_in, c->s_h2d));
+    CUDA_TRY(cudaStreamWaitEvent(c->stream, sl.ev_in, 0));
+    // the forward pass may overwrite the slot's output only after its previous D2H has finished
+    if (sl.used) CUDA_TRY(cudaStreamWaitEvent(c->stream, sl.ev_out, 0));
+    if (int rc = forward_device(c, sl.in.p, u8, in_ch, 1, w, h, out_f32 ? (float*)sl.out.p : nullptr,
+                                out_u8 ? (uint8_t*)sl.out.p : nullptr)) return rc;
+    CUDA_TRY(cudaEventRecord(sl.ev_done, c->stream));
+    CUDA_TRY(cudaStreamWaitEvent(c->s_d2h, sl.ev_done, 0));
+    CUDA_TRY(cudaMemcpyAsync(out_f32 ? (void*)out_f32 : (void*)out_u8, sl.out.p, out_bytes, cudaMemcpyDeviceToHost, c->s_d2h));
+    CUDA_TRY(cudaEventRecord(sl.ev_out, c->s_d2h));
+    sl.used = true;
+    c->next_ticket++;
+    return (int)(ticket & 0x3fffffff);
+}
+extern "C" int rsr_submit_u8(rsr_ctx* c, const uint8_t* in, int w, int h, int in_channels, uint8_t* out_rgba) {
+    return submit_host(c, in, true, in_channels, w, h, nullptr, out_rgba);
+}
+extern "C" int rsr_submit_f32(rsr_ctx* c, const float* in, int w, int h, float* out) {
+    return submit_host(c, in, false, 3, w, h, out, nullptr);
+}
+extern "C" int rsr_wait(rsr_ctx* c, int ticket) {
+    if (!c) return fail(RSR_E_BAD_ARG, "ctx is null");
+    const long newest = c->next_ticket - 1;
+    const long t = newest - ((newest - ticket) & 0x3fffffff);   // undo the 30-bit wrap
+    if (ticket < 0 || t > newest) return fail(RSR_E_BAD_ARG, "unknown ticket %d", ticket);
+    if (newest - t >= 3) return 0;  // slot already recycled: frames complete in order, so it is done
+    CUDA_TRY(cudaSetDevice(c->device));
+    cudaError_t e = cudaEventSynchronize(c->slot[t % 3].ev_out);
+    if (e != cudaSuccess) {
+        int f = 0;
+        cudaMemcpy(&f, c->fault, sizeof f, cudaMemcpyDeviceToHost);
+        return fail(RSR_E_CUDA, "frame failed: %s (fault word 0x%x)", cudaGetErrorString(e), f);
+    }
+    return 0;
+}
+extern "C" int rsr_wait_all(rsr_ctx* c) {
+    if (!c) return fail(RSR_E_BAD_ARG, "ctx is null");
+    CUDA_TRY(cudaSetDevice(c->device));
+    for (auto& sl : c->slot)
+        if (sl.used) CUDA_TRY(cudaEventSynchronize(sl.ev_out));
     return rsr_synchronize(c);
 }
 

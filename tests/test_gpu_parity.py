@@ -137,6 +137,24 @@ def test_u8_path_matches_f32_path(ups):
     assert np.array_equal(ab[0], a)
 
 
+def test_pipelined_submit_wait_matches_sync(ups):
+    """rsr_submit_u8 / rsr_wait (3 frames in flight) returns exactly what the synchronous call does."""
+    u = ups["imagenet"]
+    rng = np.random.default_rng(5)
+    frames = [rng.integers(0, 256, size=(96, 200, 3), dtype=np.uint8) for _ in range(7)]
+    outs = [np.zeros((288, 600, 4), np.uint8) for _ in range(7)]
+    tickets = [u.submit_u8(f, o) for f, o in zip(frames, outs)]
+    u.wait(tickets[2])
+    assert np.array_equal(outs[2], u.forward_u8(frames[2]))
+    u.wait_all()
+    for f, o in zip(frames, outs):
+        assert np.array_equal(o, u.forward_u8(f))
+    x = frames[0].astype(np.float32) / 255.0
+    o32 = np.zeros((288, 600, 3), np.float32)
+    u.wait(u.submit_f32(x, o32))
+    assert np.array_equal(o32, u.forward(x))
+
+
 def test_band_mode_equals_full_frame(ups, weights):
     """Spatial sharding (overlap-recompute): bands with 7-row halos reproduce the
     unsharded frame exactly (same accumulation order => bit-identical)."""
