@@ -137,7 +137,7 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0  # the CPU arm runs on rank 0 only
-    rows = 216  # 1/5 of a 1080p frame per step: ~2 s of host work per step
+    rows = 540  # half of a 1080p frame per step: enough rows to occupy 64-128 host threads, ~2 s per step
     mpix, times, threads = cpu_sample(rows, args.steps, min(args.warmup, 3))
     total = sum(times)
     value = mpix * len(times) / total
@@ -285,11 +285,11 @@ def run_ours(args):
         cpu_mpix, cpu_times, cpu_threads = (None, None, None)
         cpu = None
         if world == 1:
-            rows = 216
-            cpu_mpix, cpu_times, cpu_threads = cpu_sample(rows, 3, 1)
+            rows = 540
+            cpu_mpix, cpu_times, cpu_threads = cpu_sample(rows, 2, 1)
             cpu = {"value": cpu_mpix * len(cpu_times) / sum(cpu_times), "unit": "Mpix/s", "cores": cpu_threads,
                    "kind": "port",
-                   "sample": f"3 x ({W_LR}x{rows} slab of the same frame), img_to_data+forward(fp32)+data_to_img",
+                   "sample": f"2 x ({W_LR}x{rows} slab of the same frame), img_to_data+forward(fp32)+data_to_img",
                    "note": "CPU restatement of rusty_sr/alumina path (Rust toolchain unavailable)"}
         total_k = sum(ktimes.values())
         line = {

@@ -19,11 +19,10 @@
 // start address is shifted by b pixels.  Weights stream per tap through a small TMA ring.
 //
 // Partial pre-activation sums that an earlier launch produced for the same node (alumina nodes
-// sum all their writers: network.rs:61+65, :62+66+69, :67+70+72) are NOT added in the epilogue:
-// they are stored in the same split-bf16 pixel format, TMA-loaded as one more A tile and folded
-// into the accumulator by the tensor core with an identity B tile (4 tiny MMAs per row).
-// The epilogue therefore never waits on global memory: TMEM -> registers -> bias / BeLU / split
-// -> swizzled shared staging -> TMA store.  R output rows are accumulated per pass in TMEM, double
+// sum all their writers: network.rs:61+65, :62+66+69, :67+70+72) travel as fp32 [pixel][32] tiles:
+// a producer warp TMA-loads each 128-pixel tile into shared memory ahead of time and the epilogue
+// adds it from there, so the epilogue never waits on global memory:
+// TMEM -> registers (+ partial from smem) -> bias / BeLU / split -> swizzled staging -> TMA store.  R output rows are accumulated per pass in TMEM, double
 // buffered, so the epilogue of pass j overlaps the MMAs of pass j + 1.
 //
 // Warp roles (256 threads): warp 0 = input-row producer, warp 3 = weight producer, warp 2 = TMEM
@@ -49,13 +48,13 @@ namespace rsr {
 enum EpiKind : int {
     EPI_NONE = 0,
     EPI_ACT = 1,      // y = BeLU(acc + bias; slope); store split-bf16 activation
-    EPI_RAW = 2,      // store acc as split-bf16 (partial pre-activation sum for a later launch)
+    EPI_RAW = 2,      // store acc (+ partial) as fp32 [pixel][32]: partial sum for a later launch
     EPI_SHUFFLE = 3,  // acc + bias; depth-to-space + bilinear skip; store image
 };
 
 struct EpiGroup {
     int kind;
-    int has_pin;          // a partial sum from an earlier launch is folded into this group
+    int has_pin;          // a partial sum from an earlier launch is added to this group
     const float* bias;    // 32 floats (zero padded) or null
     const float* slope;   // 32 floats: BeLU p (EPI_ACT)
 };
@@ -63,9 +62,8 @@ struct EpiGroup {
 struct ConvParams {
     CUtensorMap tmA;       // input node, rank 4: (RB/2 elems, W, H, NIMG), box (RB/2, BOXW, 1, 1)
     CUtensorMap tmB;       // packed weights, rank 2: (RB/2 elems, taps * NCOL), box (RB/2, NCOL)
-    CUtensorMap tmI;       // identity tile [32][64] bf16 (partial-sum fold)
-    CUtensorMap tmPin[3];  // per group: partial-sum input, rank 4 (64, W, H, NIMG), box (64, 128, 1, 1)
-    CUtensorMap tmOut[3];  // per group: split-bf16 output, rank 4 (64, W, H, NIMG), box (64, 32, 1, 1)
+    CUtensorMap tmPin[3];  // per group: fp32 partial-sum input, rank 4 (32, W, H, NIMG), box (32, 128, 1, 1)
+    CUtensorMap tmOut[3];  // per group: output, rank 4, box (.., 32 px, 1, 1): split-bf16 (64 elems) or fp32 (32)
     int W, H, NIMG;
     int row_begin, row_end;  // output rows computed; [0, H) normally
     int n_strips;
@@ -114,16 +112,14 @@ struct ConvCfg {
     static constexpr int BST = TPS * TAP_BYTES;                        // bytes per weight stage
     static constexpr int KC = RB / 64;                                 // 16-channel chunks per plane
     static constexpr int PIN_BYTES = 128 * 128;                        // one partial-sum tile
-    static constexpr int IDENT_BYTES = NPIN > 0 ? 32 * 128 : 0;
     static constexpr int ACC_COLS = 2 * R * NCOL;                      // double-buffered accumulators
     static constexpr int TMEM_COLS = ACC_COLS <= 32 ? 32 : ACC_COLS <= 64 ? 64 : ACC_COLS <= 128 ? 128
                                    : ACC_COLS <= 256 ? 256 : 512;
     static constexpr int OFF_B = NR * SLOT;
     static constexpr int OFF_P = OFF_B + NBS * BST;
-    static constexpr int OFF_I = OFF_P + NPIN * PIN_BYTES;
-    static constexpr int OFF_O = OFF_I + IDENT_BYTES;
+    static constexpr int OFF_O = OFF_P + NPIN * PIN_BYTES;
     static constexpr int OFF_BAR = OFF_O + 4 * NOUT * 4096;
-    static constexpr int NBAR = 2 * NR + 2 * NBS + 2 * (NPIN > 0 ? NPIN : 1) + 4 + 1;
+    static constexpr int NBAR = 2 * NR + 2 * NBS + 2 * (NPIN > 0 ? NPIN : 1) + 4;
     static constexpr int SMEM_BYTES = 1024 + OFF_BAR + NBAR * 8 + 16;
     static constexpr uint32_t SWZ = RB == 128 ? UMMA_SW_128B : UMMA_SW_64B;
     static_assert(ACC_COLS <= 512, "accumulators exceed TMEM");
@@ -271,6 +267,29 @@ __device__ __forceinline__ void shuffle_pixel(const float (&v)[32], const SkipNb
     }
 }
 
+// fp32 [pixel][32] row (128 B) into the warp's staging tile, 128-byte swizzle.
+__device__ __forceinline__ void epi_raw_to_stage(const float (&v)[32], uint32_t stage_addr, int lane) {
+    const uint32_t row = stage_addr + lane * 128;
+    const uint32_t sw = lane & 7;
+    #pragma unroll
+    for (int j = 0; j < 8; ++j)
+        st_shared_v4(row + ((j ^ sw) << 4), __float_as_uint(v[4 * j]), __float_as_uint(v[4 * j + 1]),
+                     __float_as_uint(v[4 * j + 2]), __float_as_uint(v[4 * j + 3]));
+}
+
+// v += the pixel's 32 fp32 partial sums from a TMA-loaded (128 B swizzled) tile of 128 pixels.
+__device__ __forceinline__ void epi_add_partial_tile(float (&v)[32], uint32_t tile_addr, int row) {
+    const uint32_t base = tile_addr + row * 128;
+    const uint32_t sw = row & 7;
+    #pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        float4 t;
+        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                     : "=f"(t.x), "=f"(t.y), "=f"(t.z), "=f"(t.w) : "r"(base + ((j ^ sw) << 4)));
+        v[4 * j + 0] += t.x; v[4 * j + 1] += t.y; v[4 * j + 2] += t.z; v[4 * j + 3] += t.w;
+    }
+}
+
 // ---- the kernel ------------------------------------------------------------------------------
 template <class C>
 __global__ void __launch_bounds__(256, 1) conv_strip_kernel(const __grid_constant__ ConvParams p) {
@@ -279,7 +298,6 @@ __global__ void __launch_bounds__(256, 1) conv_strip_kernel(const __grid_constan
     uint8_t* sA = smem;
     uint8_t* sB = smem + C::OFF_B;
     uint8_t* sP = smem + C::OFF_P;
-    uint8_t* sI = smem + C::OFF_I;
     uint8_t* sO = smem + C::OFF_O;
     uint64_t* a_full = reinterpret_cast<uint64_t*>(smem + C::OFF_BAR);
     uint64_t* a_empty = a_full + C::NR;
@@ -290,8 +308,7 @@ __global__ void __launch_bounds__(256, 1) conv_strip_kernel(const __grid_constan
     uint64_t* p_empty = p_full + NPB;
     uint64_t* t_full = p_empty + NPB;
     uint64_t* t_empty = t_full + 2;
-    uint64_t* i_full = t_empty + 2;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(i_full + 1);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(t_empty + 2);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -308,16 +325,11 @@ __global__ void __launch_bounds__(256, 1) conv_strip_kernel(const __grid_constan
     if (threadIdx.x == 0) {
         for (int i = 0; i < C::NR; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
         for (int i = 0; i < C::NBS; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
-        for (int i = 0; i < NPB; ++i) { mbar_init(&p_full[i], 1); mbar_init(&p_empty[i], 1); }
+        for (int i = 0; i < NPB; ++i) { mbar_init(&p_full[i], 1); mbar_init(&p_empty[i], 4); }
         for (int i = 0; i < 2; ++i) { mbar_init(&t_full[i], 1); mbar_init(&t_empty[i], 4); }
-        mbar_init(i_full, 1);
         fence_mbar_init();
         tma_prefetch_desc(&p.tmA);
         tma_prefetch_desc(&p.tmB);
-        if (C::NPIN > 0 && npg > 0) {
-            mbar_arrive_expect_tx(i_full, C::IDENT_BYTES);
-            tma_load_2d(sI, &p.tmI, i_full, 0, 0);
-        }
     }
     if (warp == 2) { tmem_alloc(tmem_slot, C::TMEM_COLS); tmem_relinquish(); }
     tc_fence_before();
@@ -371,15 +383,15 @@ __global__ void __launch_bounds__(256, 1) conv_strip_kernel(const __grid_constan
         }
     } else if (warp == 2) {
         // ===== partial-sum tile producer =====
-        // Tile order: per pass, group-major then row (the MMA issuer folds them in the same order).
+        // Tile order: per pass, row then group (the order in which the epilogue consumes them).
         if (C::NPIN > 0 && n_pin > 0) {
             uint32_t st = 0, par = 1;
             ItemIter it = item_begin(p);
             WorkItem w;
             while (item_next<C>(p, it, w)) {
                 for (int j = 0; j < w.npass; ++j)
-                    for (int k = 0; k < npg; ++k)
-                        for (int r = 0; r < C::R; ++r) {
+                    for (int r = 0; r < C::R; ++r)
+                        for (int k = 0; k < npg; ++k) {
                             RSR_WAIT(&p_empty[st], par, 7, 0);
                             if (elect_one()) {
                                 if (ABL_NO_PIN) { mbar_arrive(&p_full[st]); }
@@ -402,22 +414,17 @@ __global__ void __launch_bounds__(256, 1) conv_strip_kernel(const __grid_constan
         // offsets are immediates.  The issue thread must stay ahead of an 8-deep MMA queue
         // (tests/cuda/umma_queue.cu), so every instruction here counts.
         constexpr uint32_t HI = (uint32_t)make_sdesc_hi(8 * C::RB, C::SWZ);
-        constexpr uint32_t HI128 = (uint32_t)make_sdesc_hi(1024, UMMA_SW_128B);
         constexpr uint32_t IDESC = make_idesc_bf16(128, C::NCOL);
-        constexpr uint32_t IDESC32 = make_idesc_bf16(128, 32);
         constexpr uint32_t LBO = 1u << 16;
         constexpr uint32_t MID = (C::RB / 2) >> 4;   // encoded offset of the mid plane
         constexpr int WIN = C::R + 2 * C::PH;        // input rows one pass reads
         constexpr int NEARLY = C::R < C::KH ? C::R : C::KH;   // rows retired during the pass
         const uint32_t sA_e = (smem_u32(sA) >> 4) | LBO, sB_e = (smem_u32(sB) >> 4) | LBO;
-        const uint32_t sP_e = (smem_u32(sP) >> 4) | LBO, sI_e = (smem_u32(sI) >> 4) | LBO;
         auto desc = [](uint32_t hi, uint32_t lo) { return ((uint64_t)hi << 32) | lo; };
         uint32_t slot0 = 0;              // ring slot of the first window row of the current pass
         uint32_t wslot = 0, wpar = 0;    // next row slot to wait for, and its parity
         uint32_t bst = 0, bpar = 0;      // weight stage ring
-        uint32_t pst = 0, ppar = 0;      // partial-sum tile ring
         uint32_t buf = 0, tpar = 1;      // accumulator buffer, parity of its t_empty barrier
-        if (n_pin > 0) mbar_wait(i_full, 0, p.fault, 8);
         ItemIter it = item_begin(p);
         WorkItem w;
         while (item_next<C>(p, it, w)) {
@@ -441,7 +448,6 @@ __global__ void __launch_bounds__(256, 1) conv_strip_kernel(const __grid_constan
                     }
                 }
                 const uint32_t d_pass = tmem_base + buf * (C::R * C::NCOL);
-                int pin_k = 0;
                 #pragma unroll
                 for (int sp = 0; sp < C::NSTG; ++sp) {
                     RSR_WAIT(&b_full[bst], bpar, 5, 2);
@@ -480,31 +486,6 @@ __global__ void __launch_bounds__(256, 1) conv_strip_kernel(const __grid_constan
                     __syncwarp();
                     if (RSR_PROF_ON) prof_acc[4] += clock64() - ti0;
                     if (++bst == C::NBS) { bst = 0; bpar ^= 1; }
-                    // fold the partial-sum tiles of group k (all R rows) after a fixed stage, so that
-                    // the accumulation order of a pixel never depends on how rows pair up into passes
-                    if (C::NPIN > 0) {
-                        while (pin_k < npg && sp == ((2 * pin_k + 1) * C::NSTG) / (2 * npg)) {
-                            const int g = pin_g[pin_k];
-                            for (int r = 0; r < C::R; ++r) {
-                                RSR_WAIT(&p_full[pst], ppar, 9, 3);
-                                tc_fence_after();
-                                const uint32_t pa = sP_e + pst * (C::PIN_BYTES >> 4);
-                                const uint32_t d = d_pass + r * C::NCOL + g * 32;
-                                if (elect_one()) {
-                                    #pragma unroll
-                                    for (int pl = 0; pl < 2; ++pl)
-                                        #pragma unroll
-                                        for (int c = 0; c < 2; ++c)
-                                            if (!ABL_NO_MMA && !ABL_NO_PIN_MMA)
-                                                umma_f16(d, desc(HI128, pa + pl * 4 + c * 2), desc(HI128, sI_e + c * 2), IDESC32, 1);
-                                    umma_commit(&p_empty[pst]);
-                                }
-                                __syncwarp();
-                                if (++pst == NPB) { pst = 0; ppar ^= 1; }
-                            }
-                            ++pin_k;
-                        }
-                    }
                 }
                 const bool last = j == w.npass - 1;
                 const int n_retire = last ? WIN : C::R;
@@ -530,6 +511,8 @@ __global__ void __launch_bounds__(256, 1) conv_strip_kernel(const __grid_constan
         const int ew = warp - 4;  // == warp % 4: TMEM lane quarter this warp may read
         const uint32_t stage0 = smem_u32(sO) + ew * (C::NOUT * 4096);
         uint32_t buf = 0, tpar = 0, oc = 0;
+        uint32_t pst = 0, ppar = 0;  // partial-sum tile ring (consumed in producer order: row, then group)
+        const uint32_t sP_u = smem_u32(sP);
         ItemIter it = item_begin(p);
         WorkItem w;
         while (item_next<C>(p, it, w)) {
@@ -548,18 +531,35 @@ __global__ void __launch_bounds__(256, 1) conv_strip_kernel(const __grid_constan
                 #pragma unroll 1
                 for (int r = 0; r < C::R; ++r) {
                     const int y = w.y_b + j * C::R + r;
-                    if (y >= w.y_e) break;   // warp-uniform
-                    if (xw >= p.W) break;    // warp-uniform: slice entirely right of the image
+                    const bool row_live = y < w.y_e && xw < p.W;   // warp-uniform
                     #pragma unroll 1
                     for (int g = 0; g < C::NG; ++g) {
                         const EpiGroup& eg = p.grp[g];
                         if (eg.kind == EPI_NONE) continue;
+                        const bool pin = C::NPIN > 0 && eg.has_pin;
+                        if (!row_live) {
+                            // nothing to store, but the partial tile the producer fetched must be released
+                            if (pin) {
+                                RSR_WAIT(&p_full[pst], ppar, 9, 3);
+                                __syncwarp();
+                                if (lane == 0) mbar_arrive(&p_empty[pst]);
+                                if (++pst == NPB) { pst = 0; ppar ^= 1; }
+                            }
+                            continue;
+                        }
                         uint32_t raw[32];
                         tmem_ld_32x32(tmem_base + ((uint32_t)(ew * 32) << 16) + buf * (C::R * C::NCOL) + r * C::NCOL + g * 32, raw);
                         tmem_ld_wait();
                         float v[32];
                         #pragma unroll
                         for (int k = 0; k < 32; ++k) v[k] = __uint_as_float(raw[k]);
+                        if (pin) {
+                            RSR_WAIT(&p_full[pst], ppar, 9, 3);
+                            epi_add_partial_tile(v, sP_u + pst * C::PIN_BYTES, ew * 32 + lane);
+                            __syncwarp();
+                            if (lane == 0) mbar_arrive(&p_empty[pst]);
+                            if (++pst == NPB) { pst = 0; ppar ^= 1; }
+                        }
                         if (ABL_NO_EPI_OUT) { if (v[0] == 123.456f && p.out_f32) p.out_f32[0] = v[1]; ++oc; continue; }
                         const uint32_t stage = stage0 + (oc % C::NOUT) * 4096;
                         // the staging tile used NOUT stores ago must have been read out by the TMA engine
@@ -571,7 +571,8 @@ __global__ void __launch_bounds__(256, 1) conv_strip_kernel(const __grid_constan
                             if (RSR_PROF_ON) prof_acc[1] += clock64() - t0s;
                         }
                         if (!C::SHUF) {
-                            epi_split_to_stage(eg, v, stage, lane);
+                            if (eg.kind == EPI_RAW) epi_raw_to_stage(v, stage, lane);
+                            else epi_split_to_stage(eg, v, stage, lane);
                             fence_proxy_async_smem();
                             __syncwarp();
                             if (elect_one()) {

@@ -84,7 +84,7 @@ static Layout make_layout(int factor) {
 using Cfg0 = ConvCfg<5, 1,  64, 1, 4, 12, 5, 2, 0, 2, false>;  // conv0 on the x-im2col'd input (K = 5 taps x 16)
 using Cfg1 = ConvCfg<5, 5, 128, 3, 2,  7, 2, 3, 0, 2, false>;  // f  -> conv1 | conv2 | conv3
 using Cfg2 = ConvCfg<3, 3, 128, 3, 2,  5, 2, 3, 2, 2, false>;  // l1 -> conv5 | conv6 | conv7   (+ P2, P3)
-using Cfg3 = ConvCfg<3, 3, 128, 2, 2,  6, 2, 3, 2, 2, false>;  // l2 -> conv8 | conv9           (+ P3, E)
+using Cfg3 = ConvCfg<3, 3, 128, 2, 2,  5, 2, 3, 3, 2, false>;  // l2 -> conv8 | conv9           (+ P3, E)
 using Cfg4 = ConvCfg<3, 3, 128, 1, 2,  6, 3, 3, 3, 2, true>;   // l3 -> conv10 (+ E) + expand + bilinear skip
 
 enum { K_PACK = 0, K_CONV0, K_F, K_L1, K_L2, K_L3, K_COUNT };
@@ -150,7 +150,6 @@ struct rsr_ctx {
     cudaStream_t own_stream = nullptr, stream = nullptr;
     // packed weights (bf16 hi|mid), biases / slopes (32 floats each, zero padded)
     __nv_bfloat16 *w0 = nullptr, *w1 = nullptr, *w2 = nullptr, *w3 = nullptr, *w4 = nullptr;
-    __nv_bfloat16* ident = nullptr;  // [32][64] identity tile (partial-sum fold)
     float* vecs = nullptr;  // 9 x 32 floats: f_bias f_activ l1_bias l1_activ l2_bias l2_activ l3_bias l3_activ expand_bias
     // workspace
     DevBuf xcol, xf4, actA, actB, partA, partB, out_f32, out_u8, in_stage;
@@ -231,7 +230,7 @@ extern "C" void rsr_destroy(rsr_ctx* c) {
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
     cudaFree(c->w0); cudaFree(c->w1); cudaFree(c->w2); cudaFree(c->w3); cudaFree(c->w4);
-    cudaFree(c->vecs); cudaFree(c->fault); cudaFree(c->ident); cudaFree(c->prof);
+    cudaFree(c->vecs); cudaFree(c->fault); cudaFree(c->prof);
     release(c->xcol); release(c->xf4); release(c->actA); release(c->actB); release(c->partA);
     release(c->partB); release(c->out_f32); release(c->out_u8); release(c->in_stage);
     for (auto& e : c->ev) if (e) cudaEventDestroy(e);
@@ -328,11 +327,6 @@ static int create_impl(rsr_ctx* c, const float* params) {
         for (int i = 0; i < 9; ++i) memcpy(&v[i * 32], params + src[i], sizeof(float) * (i == 8 ? L.ce : 32));
         if (int rc = upload(&c->vecs, v.data(), v.size() * 4)) return rc;
     }
-    {
-        std::vector<__nv_bfloat16> id((size_t)32 * 64, __float2bfloat16_rn(0.f));
-        for (int n = 0; n < 32; ++n) id[(size_t)n * 64 + n] = __float2bfloat16_rn(1.0f);
-        if (int rc = upload(&c->ident, id.data(), id.size() * 2)) return rc;
-    }
     CUDA_TRY(cudaFuncSetAttribute(conv_strip_kernel<Cfg0>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg0::SMEM_BYTES));
     CUDA_TRY(cudaFuncSetAttribute(conv_strip_kernel<Cfg1>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg1::SMEM_BYTES));
     CUDA_TRY(cudaFuncSetAttribute(conv_strip_kernel<Cfg2>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg2::SMEM_BYTES));
@@ -414,6 +408,17 @@ static int make_map_act(rsr_ctx* c, CUtensorMap* m, const void* base, int elems,
     if (r != CUDA_SUCCESS) return fail(RSR_E_CUDA, "cuTensorMapEncodeTiled(activation %dx%dx%d) failed: %d", W, H, N, (int)r);
     return 0;
 }
+static int make_map_part(rsr_ctx* c, CUtensorMap* m, const void* base, int W, int H, int N, int boxw) {
+    cuuint64_t dims[4] = {32, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+    cuuint64_t strides[3] = {128, (cuuint64_t)128 * W, (cuuint64_t)128 * W * H};
+    cuuint32_t box[4] = {32, (cuuint32_t)boxw, 1, 1};
+    cuuint32_t es[4] = {1, 1, 1, 1};
+    CUresult r = c->encode(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<void*>(base), dims, strides, box, es,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(RSR_E_CUDA, "cuTensorMapEncodeTiled(partial %dx%dx%d) failed: %d", W, H, N, (int)r);
+    return 0;
+}
 static int make_map_w(rsr_ctx* c, CUtensorMap* m, const void* base, int elems, int rows, int boxrows) {
     const cuuint64_t rb = (cuuint64_t)elems * 2;
     cuuint64_t dims[2] = {(cuuint64_t)elems, (cuuint64_t)rows};
@@ -463,11 +468,9 @@ static int forward_device(rsr_ctx* c, const void* d_in, bool u8, int in_ch, int 
     __nv_bfloat16* l1_act = (__nv_bfloat16*)c->actB.p;  // l1, later l3
     __nv_bfloat16* l2_act = f_act;
     __nv_bfloat16* l3_act = l1_act;
-    __nv_bfloat16* P2 = (__nv_bfloat16*)c->partA.p;  // conv2(f): partial of l2_conv; later E (expand partial)
-    __nv_bfloat16* P3 = (__nv_bfloat16*)c->partB.p;  // conv3(f) (+conv6(l1)): partial of l3_conv
-    __nv_bfloat16* P3b = P3;                          // P3 + conv6(l1), updated in place (aliasing)
-    __nv_bfloat16* E = P2;                            // conv7(l1)
-    __nv_bfloat16* Eb = E;                            // E + conv9(l2), updated in place
+    float* P2 = (float*)c->partA.p;  // conv2(f): fp32 partial of l2_conv; later E (expand partial)
+    float* P3 = (float*)c->partB.p;  // conv3(f) (+conv6(l1)): fp32 partial of l3_conv, updated in place
+    float* E = P2;                   // conv7(l1) (+conv9(l2)), updated in place (aliasing)
     const float* V = c->vecs;
     const float *f_bias = V, *f_slope = V + 32, *l1_bias = V + 64, *l1_slope = V + 96, *l2_bias = V + 128,
                 *l2_slope = V + 160, *l3_bias = V + 192, *l3_slope = V + 224, *e_bias = V + 256;
@@ -487,9 +490,9 @@ static int forward_device(rsr_ctx* c, const void* d_in, bool u8, int in_ch, int 
     ConvParams p{};
     p.W = w; p.H = h; p.NIMG = n; p.row_begin = 0; p.row_end = h; p.factor = c->factor; p.fault = c->fault;
     p.xf4 = (const float4*)c->xf4.p;
-    if (int rc = make_map_w(c, &p.tmI, c->ident, 64, 32, 32)) return rc;
     const EpiGroup none{EPI_NONE, 0, nullptr, nullptr};
     auto in_map = [&](CUtensorMap* m, const void* base, int boxw) { return make_map_act(c, m, base, 64, w, h, n, boxw); };
+    auto part_map = [&](CUtensorMap* m, const void* base, int boxw) { return make_map_part(c, m, base, w, h, n, boxw); };
 
     // conv0: xcol -> f = BeLU(conv0(x) + f_bias)                       network.rs:33-35
     if (int rc = make_map_act(c, &p.tmA, xcol, 32, w, h, n, Cfg0::BOXW)) return rc;
@@ -505,8 +508,8 @@ static int forward_device(rsr_ctx* c, const void* d_in, bool u8, int in_ch, int 
     if (int rc = in_map(&p.tmA, f_act, Cfg1::BOXW)) return rc;
     if (int rc = make_map_w(c, &p.tmB, c->w1, 64, 25 * 96, Cfg1::TPS * 96)) return rc;
     if (int rc = in_map(&p.tmOut[0], l1_act, 32)) return rc;
-    if (int rc = in_map(&p.tmOut[1], P2, 32)) return rc;
-    if (int rc = in_map(&p.tmOut[2], P3, 32)) return rc;
+    if (int rc = part_map(&p.tmOut[1], P2, 32)) return rc;
+    if (int rc = part_map(&p.tmOut[2], P3, 32)) return rc;
     p.grp[0] = EpiGroup{EPI_ACT, 0, l1_bias, l1_slope};
     p.grp[1] = EpiGroup{EPI_RAW, 0, nullptr, nullptr};
     p.grp[2] = EpiGroup{EPI_RAW, 0, nullptr, nullptr};
@@ -514,16 +517,16 @@ static int forward_device(rsr_ctx* c, const void* d_in, bool u8, int in_ch, int 
     CUDA_TRY(cudaEventRecord(c->ev[3], c->stream));
     if (c->stop_after == 2) return 0;
 
-    // l1 -> l2 = BeLU(P2 + conv5(l1) + l2_bias); P3b = P3 + conv6(l1); E = conv7(l1)   :65-67,51,55
+    // l1 -> l2 = BeLU(P2 + conv5(l1) + l2_bias); P3 += conv6(l1); E = conv7(l1)   :65-67,51,55
     // (l2 overwrites f, E overwrites P2: both are dead; a thread block only overwrites pixels whose
     //  partial tile it has already consumed — see DESIGN.md "aliasing")
     if (int rc = in_map(&p.tmA, l1_act, Cfg2::BOXW)) return rc;
     if (int rc = make_map_w(c, &p.tmB, c->w2, 64, 9 * 96, Cfg2::TPS * 96)) return rc;
-    if (int rc = in_map(&p.tmPin[0], P2, 128)) return rc;
-    if (int rc = in_map(&p.tmPin[1], P3, 128)) return rc;
+    if (int rc = part_map(&p.tmPin[0], P2, 128)) return rc;
+    if (int rc = part_map(&p.tmPin[1], P3, 128)) return rc;
     if (int rc = in_map(&p.tmOut[0], l2_act, 32)) return rc;
-    if (int rc = in_map(&p.tmOut[1], P3b, 32)) return rc;
-    if (int rc = in_map(&p.tmOut[2], E, 32)) return rc;
+    if (int rc = part_map(&p.tmOut[1], P3, 32)) return rc;
+    if (int rc = part_map(&p.tmOut[2], E, 32)) return rc;
     p.grp[0] = EpiGroup{EPI_ACT, 1, l2_bias, l2_slope};
     p.grp[1] = EpiGroup{EPI_RAW, 1, nullptr, nullptr};
     p.grp[2] = EpiGroup{EPI_RAW, 0, nullptr, nullptr};
@@ -531,13 +534,13 @@ static int forward_device(rsr_ctx* c, const void* d_in, bool u8, int in_ch, int 
     CUDA_TRY(cudaEventRecord(c->ev[4], c->stream));
     if (c->stop_after == 3) return 0;
 
-    // l2 -> l3 = BeLU(P3b + conv8(l2) + l3_bias); Eb = E + conv9(l2)                  :69-70,52,56
+    // l2 -> l3 = BeLU(P3 + conv8(l2) + l3_bias); E += conv9(l2)                  :69-70,52,56
     if (int rc = in_map(&p.tmA, l2_act, Cfg3::BOXW)) return rc;
     if (int rc = make_map_w(c, &p.tmB, c->w3, 64, 9 * 64, Cfg3::TPS * 64)) return rc;
-    if (int rc = in_map(&p.tmPin[0], P3b, 128)) return rc;
-    if (int rc = in_map(&p.tmPin[1], E, 128)) return rc;
+    if (int rc = part_map(&p.tmPin[0], P3, 128)) return rc;
+    if (int rc = part_map(&p.tmPin[1], E, 128)) return rc;
     if (int rc = in_map(&p.tmOut[0], l3_act, 32)) return rc;
-    if (int rc = in_map(&p.tmOut[1], Eb, 32)) return rc;
+    if (int rc = part_map(&p.tmOut[1], E, 32)) return rc;
     p.grp[0] = EpiGroup{EPI_ACT, 1, l3_bias, l3_slope};
     p.grp[1] = EpiGroup{EPI_RAW, 1, nullptr, nullptr};
     p.grp[2] = none;
@@ -545,10 +548,10 @@ static int forward_device(rsr_ctx* c, const void* d_in, bool u8, int in_ch, int 
     CUDA_TRY(cudaEventRecord(c->ev[5], c->stream));
     if (c->stop_after == 4) return 0;
 
-    // l3 -> output = Expand(Eb + conv10(l3) + expand_bias) + LinearInterp(x)          :72,38-39,27
+    // l3 -> output = Expand(E + conv10(l3) + expand_bias) + LinearInterp(x)          :72,38-39,27
     if (int rc = in_map(&p.tmA, l3_act, Cfg4::BOXW)) return rc;
     if (int rc = make_map_w(c, &p.tmB, c->w4, 64, 9 * 32, Cfg4::TPS * 32)) return rc;
-    if (int rc = in_map(&p.tmPin[0], Eb, 128)) return rc;
+    if (int rc = part_map(&p.tmPin[0], E, 128)) return rc;
     p.grp[0] = EpiGroup{EPI_SHUFFLE, 1, e_bias, nullptr};
     p.grp[1] = none; p.grp[2] = none;
     p.out_f32 = d_out_f32;
@@ -709,6 +712,10 @@ extern "C" int rsr_debug_read_node(rsr_ctx* c, int which, float* out, size_t npx
     if (int rc = rsr_synchronize(c)) return rc;
     DevBuf* b = which == 0 ? &c->actA : which == 1 ? &c->actB : which == 2 ? &c->partA : which == 3 ? &c->partB : nullptr;
     if (!b || !b->p || b->cap < npx * 128) return fail(RSR_E_BAD_ARG, "node %d not available for %zu pixels", which, npx);
+    if (which >= 2) {
+        CUDA_TRY(cudaMemcpy(out, b->p, npx * 128, cudaMemcpyDeviceToHost));
+        return 0;
+    }
     std::vector<__nv_bfloat16> tmp(npx * 64);
     CUDA_TRY(cudaMemcpy(tmp.data(), b->p, npx * 128, cudaMemcpyDeviceToHost));
     for (size_t i = 0; i < npx; ++i)

@@ -11,4 +11,4 @@ print({k:round(v*1e3,1) for k,v in d["kernel_ms"].items()})
 print(d["clocks"], d.get("cpu_baseline"))
 PY
 tail -3 gpurun_out/bench.err
-bash tools/ablate.sh run
+ABL_VARIANTS="8" bash tools/ablate.sh run
