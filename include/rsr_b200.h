@@ -92,6 +92,20 @@ int rsr_wait_all(rsr_ctx* ctx);
 int rsr_upscale_band_f32(rsr_ctx* ctx, const float* in_rows, int w, int rows_in, int top_halo,
                          int bottom_halo, float* out_rows);
 
+/* The two parameter-free modes of the reference CLI (no conv net, no rsr_ctx):
+ *   rsr_bilinear_*   = bilinear_net(factor)   (network.rs:111-123; `-p bilinear`, main.rs:153-155):
+ *                      sRGB -> linear, LinearInterp x factor (half-pixel centres, edge clamp), linear -> sRGB
+ *   rsr_downsample_* = downsample_net(factor) (network.rs:125-138; `-d`, main.rs:139-141):
+ *                      sRGB -> linear, factor x factor average pooling, linear -> sRGB;
+ *                      output is ceil(h/factor) x ceil(w/factor), edge windows average the pixels they cover.
+ * The transfer functions are the IEC 61966-2-1 sRGB curves.  alumina's own op sources are not available, so
+ * these two modes are NOT pinned by any reference artefact.  f32 variants follow the tensor
+ * contract of graph.forward ([h][w][3] in, unclamped out); u8 variants apply img_to_data / data_to_img. */
+int rsr_bilinear_f32(int device, const float* in_hwc3, int w, int h, int factor, float* out_hwc3);
+int rsr_bilinear_u8(int device, const uint8_t* in, int w, int h, int in_channels, int factor, uint8_t* out_rgba);
+int rsr_downsample_f32(int device, const float* in_hwc3, int w, int h, int factor, float* out_hwc3);
+int rsr_downsample_u8(int device, const uint8_t* in, int w, int h, int in_channels, int factor, uint8_t* out_rgba);
+
 /* Use an externally created CUDA stream (cudaStream_t passed as void*) instead of the
  * context's own; NULL restores the internal stream. */
 int rsr_set_stream(rsr_ctx* ctx, void* cuda_stream);

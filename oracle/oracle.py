@@ -76,6 +76,9 @@ def lib() -> ctypes.CDLL:
                 fn.restype = ctypes.c_int
                 fn.argtypes = [fp, ctypes.c_size_t, ctypes.c_int, fp, ctypes.c_int, ctypes.c_int,
                                op, ctypes.c_void_p]
+            for name in ("sr_oracle_bilinear_f64", "sr_oracle_downsample_f64"):
+                getattr(L, name).argtypes = [fp, ctypes.c_int, ctypes.c_int, ctypes.c_int, dp]
+                getattr(L, name).restype = None
             L.sr_oracle_img_to_data.argtypes = [ctypes.c_char_p, ctypes.c_int, ctypes.c_int,
                                                 ctypes.c_int, fp]
             L.sr_oracle_data_to_img.argtypes = [fp, ctypes.c_int, ctypes.c_int, ctypes.c_char_p]
@@ -144,6 +147,26 @@ def forward(params: np.ndarray, image_hwc3: np.ndarray, factor: int = 3, dtype=n
     if rc != 0:
         raise MemoryError("oracle allocation failed")
     return (out, tap_arrays) if taps else out
+
+
+def bilinear(image_hwc3: np.ndarray, factor: int = 3) -> np.ndarray:
+    """bilinear_net(factor) (reference network.rs:111-123), fp64.  Unpinned semantics, see sr_oracle.c."""
+    x = np.ascontiguousarray(image_hwc3, dtype=np.float32)
+    H, W = x.shape[:2]
+    out = np.empty((H * factor, W * factor, 3), np.float64)
+    lib().sr_oracle_bilinear_f64(x.ctypes.data_as(ctypes.POINTER(ctypes.c_float)), W, H, factor,
+                                 out.ctypes.data_as(ctypes.POINTER(ctypes.c_double)))
+    return out
+
+
+def downsample(image_hwc3: np.ndarray, factor: int = 3) -> np.ndarray:
+    """downsample_net(factor) (reference network.rs:125-138), fp64.  Unpinned semantics, see sr_oracle.c."""
+    x = np.ascontiguousarray(image_hwc3, dtype=np.float32)
+    H, W = x.shape[:2]
+    out = np.empty((-(-H // factor), -(-W // factor), 3), np.float64)
+    lib().sr_oracle_downsample_f64(x.ctypes.data_as(ctypes.POINTER(ctypes.c_float)), W, H, factor,
+                                   out.ctypes.data_as(ctypes.POINTER(ctypes.c_double)))
+    return out
 
 
 def img_to_data(img_u8: np.ndarray) -> np.ndarray:

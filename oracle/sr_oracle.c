@@ -162,3 +162,54 @@ void sr_oracle_data_to_img(const float *data, int w, int h, uint8_t *rgba) {
         rgba[i * 4 + 3] = 255;
     }
 }
+
+/* ---- the two parameter-free graphs of the reference CLI (test oracle for rsr_bilinear_* / rsr_downsample_*)
+ * bilinear_net  (network.rs:111-123): SrgbToLinear -> LinearInterp(factor) -> LinearToSrgb
+ * downsample_net(network.rs:125-138): SrgbToLinear -> Pooling(factor, average) -> LinearToSrgb
+ * Transfer functions: IEC 61966-2-1.  alumina's op sources are unavailable and the reference commits no
+ * output of these two modes, so this part of the oracle is NOT pinned ("parity unpinned"); it documents
+ * the semantics the GPU path implements.  Edge windows of the pooling average the pixels they cover. */
+static double sr_srgb_to_linear(double v) { return v <= 0.04045 ? v / 12.92 : pow((v + 0.055) / 1.055, 2.4); }
+static double sr_linear_to_srgb(double v) { return v <= 0.0031308 ? v * 12.92 : 1.055 * pow(v, 1.0 / 2.4) - 0.055; }
+
+void sr_oracle_bilinear_f64(const float *in, int W, int H, int F, double *out) {
+    const int OW = W * F, OH = H * F;
+#pragma omp parallel for schedule(static)
+    for (int Y = 0; Y < OH; Y++) {
+        const double sy = (Y + 0.5) / F - 0.5, fy = floor(sy), ty = sy - fy;
+        int y0 = (int)fy, y1 = y0 + 1;
+        y0 = y0 < 0 ? 0 : (y0 > H - 1 ? H - 1 : y0);
+        y1 = y1 < 0 ? 0 : (y1 > H - 1 ? H - 1 : y1);
+        for (int X = 0; X < OW; X++) {
+            const double sx = (X + 0.5) / F - 0.5, fx = floor(sx), tx = sx - fx;
+            int x0 = (int)fx, x1 = x0 + 1;
+            x0 = x0 < 0 ? 0 : (x0 > W - 1 ? W - 1 : x0);
+            x1 = x1 < 0 ? 0 : (x1 > W - 1 ? W - 1 : x1);
+            for (int c = 0; c < 3; c++) {
+                const double v00 = sr_srgb_to_linear(in[((size_t)y0 * W + x0) * 3 + c]);
+                const double v01 = sr_srgb_to_linear(in[((size_t)y0 * W + x1) * 3 + c]);
+                const double v10 = sr_srgb_to_linear(in[((size_t)y1 * W + x0) * 3 + c]);
+                const double v11 = sr_srgb_to_linear(in[((size_t)y1 * W + x1) * 3 + c]);
+                const double top = v00 + (v01 - v00) * tx, bot = v10 + (v11 - v10) * tx;
+                out[((size_t)Y * OW + X) * 3 + c] = sr_linear_to_srgb(top + (bot - top) * ty);
+            }
+        }
+    }
+}
+
+void sr_oracle_downsample_f64(const float *in, int W, int H, int F, double *out) {
+    const int OW = (W + F - 1) / F, OH = (H + F - 1) / F;
+#pragma omp parallel for schedule(static)
+    for (int Y = 0; Y < OH; Y++)
+        for (int X = 0; X < OW; X++)
+            for (int c = 0; c < 3; c++) {
+                double acc = 0;
+                int cnt = 0;
+                for (int dy = 0; dy < F; dy++)
+                    for (int dx = 0; dx < F; dx++) {
+                        const int y = Y * F + dy, x = X * F + dx;
+                        if (y < H && x < W) { acc += sr_srgb_to_linear(in[((size_t)y * W + x) * 3 + c]); cnt++; }
+                    }
+                out[((size_t)Y * OW + X) * 3 + c] = sr_linear_to_srgb(acc / cnt);
+            }
+}

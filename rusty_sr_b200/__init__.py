@@ -19,7 +19,7 @@ from ._lib import RsrError
 from .network import FACTOR, num_params, param_layout
 from .rsr_format import decode_rsr, encode_rsr
 
-__all__ = ["Upscaler", "upscale", "load_builtin_params", "decode_rsr", "encode_rsr", "RsrError",
+__all__ = ["Upscaler", "upscale", "bilinear", "downsample", "load_builtin_params", "decode_rsr", "encode_rsr", "RsrError",
            "num_params", "param_layout", "FACTOR", "BUILTIN_PARAMETERS"]
 
 _RES = os.path.join(os.path.dirname(os.path.abspath(__file__)), "res")
@@ -202,6 +202,39 @@ class Upscaler:
 
     def last_launch_count(self) -> int:
         return int(self._L.rsr_last_launch_count(self._h))
+
+
+def bilinear(image: np.ndarray, factor: int = FACTOR, device: int = 0) -> np.ndarray:
+    """`-p bilinear` = bilinear_net(factor) (network.rs:111-123, main.rs:153-155): interpolation in linear light.
+    u8 [H][W][3|4] -> u8 RGBA, or f32 [H][W][3] -> f32 [fH][fW][3]."""
+    L = _lib.load()
+    a = np.ascontiguousarray(image)
+    H, W = a.shape[:2]
+    if a.dtype == np.uint8:
+        out = np.empty((H * factor, W * factor, 4), np.uint8)
+        _lib.check(L.rsr_bilinear_u8(device, _as_ptr(a), W, H, a.shape[2], factor, _as_ptr(out)))
+    else:
+        a = np.ascontiguousarray(a, dtype=np.float32)
+        out = np.empty((H * factor, W * factor, 3), np.float32)
+        _lib.check(L.rsr_bilinear_f32(device, _as_ptr(a), W, H, factor, _as_ptr(out)))
+    return out
+
+
+def downsample(image: np.ndarray, factor: int = FACTOR, device: int = 0) -> np.ndarray:
+    """`-d` = downsample_net(factor) (network.rs:125-138, main.rs:139-141): average pooling in linear light;
+    this is also how the training branch synthesises its low-resolution inputs (network.rs:90-92)."""
+    L = _lib.load()
+    a = np.ascontiguousarray(image)
+    H, W = a.shape[:2]
+    oh, ow = -(-H // factor), -(-W // factor)
+    if a.dtype == np.uint8:
+        out = np.empty((oh, ow, 4), np.uint8)
+        _lib.check(L.rsr_downsample_u8(device, _as_ptr(a), W, H, a.shape[2], factor, _as_ptr(out)))
+    else:
+        a = np.ascontiguousarray(a, dtype=np.float32)
+        out = np.empty((oh, ow, 3), np.float32)
+        _lib.check(L.rsr_downsample_f32(device, _as_ptr(a), W, H, factor, _as_ptr(out)))
+    return out
 
 
 def upscale(input_image: np.ndarray, parameters: str = "imagenet", custom: Optional[str] = None,

@@ -4,7 +4,7 @@
                                                        [-c FILE.rsr] [-d]
 
 Image decode/encode is host I/O (the reference uses the `image` crate, main.rs:164,175); here PIL.
-`-p bilinear` and `-d` are not conv-net paths (network.rs:111-138) and are not on the GPU path yet.
+`-p bilinear` and `-d` (network.rs:111-138) run as small elementwise GPU kernels.
 """
 from __future__ import annotations
 
@@ -28,13 +28,21 @@ def main(argv=None) -> int:
     ap.add_argument("--device", type=int, default=0, help="CUDA device ordinal (extension)")
     args = ap.parse_args(argv)
 
-    if args.downsample or args.parameters == "bilinear":
-        print("rusty_sr_b200: -d and -p bilinear do not use the conv net (network.rs:111-138) and are not "
-              "implemented on the GPU path", file=sys.stderr)
-        return 2
-
     from PIL import Image
     import rusty_sr_b200 as R
+
+    if args.downsample or args.parameters == "bilinear":
+        img = np.asarray(Image.open(args.INPUT_FILE).convert("RGBA"))
+        if args.downsample:
+            print("Downsampling using average pooling of linear RGB values...", end="", flush=True)   # main.rs:140
+            out = R.downsample(img, R.FACTOR, device=args.device)
+        else:
+            print("Upscaling using bilinear interpolation...", end="", flush=True)                    # main.rs:154
+            out = R.bilinear(img, R.FACTOR, device=args.device)
+        print(" Writing file...", end="", flush=True)
+        Image.fromarray(out, "RGBA").save(args.OUTPUT_FILE)
+        print(" Done")
+        return 0
 
     name = args.parameters or "imagenet"  # default: main.rs:144
     if args.custom:

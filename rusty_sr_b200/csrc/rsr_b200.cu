@@ -745,3 +745,120 @@ extern "C" int rsr_debug_read_profile(rsr_ctx* c, int kindex, long long* out, in
     CUDA_TRY(cudaMemcpy(out, c->prof + (size_t)kindex * 256 * 16, sizeof(long long) * rows * 16, cudaMemcpyDeviceToHost));
     return rows;
 }
+
+// ------------------------------------------------------------------ parameter-free CLI modes
+// bilinear_net / downsample_net (network.rs:111-138): elementwise + small-stencil, HBM bound.
+__device__ __forceinline__ float srgb_to_linear(float v) {
+    return v <= 0.04045f ? v * (1.0f / 12.92f) : powf((v + 0.055f) * (1.0f / 1.055f), 2.4f);
+}
+__device__ __forceinline__ float linear_to_srgb(float v) {
+    return v <= 0.0031308f ? v * 12.92f : 1.055f * powf(v, 1.0f / 2.4f) - 0.055f;
+}
+template <bool U8>
+__device__ __forceinline__ float load_px(const void* in, size_t idx, int ch, int c) {
+    return U8 ? (float)reinterpret_cast<const uint8_t*>(in)[idx * ch + c] / 255.0f
+              : reinterpret_cast<const float*>(in)[idx * 3 + c];
+}
+template <bool U8>
+__device__ __forceinline__ void store_px(void* out, size_t idx, float r, float g, float b) {
+    if (U8) {
+        uchar4 q;
+        q.x = (unsigned char)(fminf(fmaxf(r, 0.f), 1.f) * 255.0f + 0.5f);
+        q.y = (unsigned char)(fminf(fmaxf(g, 0.f), 1.f) * 255.0f + 0.5f);
+        q.z = (unsigned char)(fminf(fmaxf(b, 0.f), 1.f) * 255.0f + 0.5f);
+        q.w = 255;
+        reinterpret_cast<uchar4*>(out)[idx] = q;
+    } else {
+        float* o = reinterpret_cast<float*>(out) + idx * 3;
+        o[0] = r; o[1] = g; o[2] = b;
+    }
+}
+template <bool U8>
+__global__ void __launch_bounds__(256) bilinear_kernel(const void* __restrict__ in, int ch, int W, int H, int F, void* __restrict__ out) {
+    const size_t n = (size_t)W * F * H * F;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const int X = (int)(i % ((size_t)W * F)), Y = (int)(i / ((size_t)W * F));
+        const float sy = ((float)Y + 0.5f) / (float)F - 0.5f, sx = ((float)X + 0.5f) / (float)F - 0.5f;
+        const float fy = floorf(sy), fx = floorf(sx);
+        const float ty = sy - fy, tx = sx - fx;
+        const int y0 = min(max((int)fy, 0), H - 1), y1 = min(max((int)fy + 1, 0), H - 1);
+        const int x0 = min(max((int)fx, 0), W - 1), x1 = min(max((int)fx + 1, 0), W - 1);
+        float o[3];
+        #pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const float v00 = srgb_to_linear(load_px<U8>(in, (size_t)y0 * W + x0, ch, c));
+            const float v01 = srgb_to_linear(load_px<U8>(in, (size_t)y0 * W + x1, ch, c));
+            const float v10 = srgb_to_linear(load_px<U8>(in, (size_t)y1 * W + x0, ch, c));
+            const float v11 = srgb_to_linear(load_px<U8>(in, (size_t)y1 * W + x1, ch, c));
+            const float top = v00 + (v01 - v00) * tx, bot = v10 + (v11 - v10) * tx;
+            o[c] = linear_to_srgb(top + (bot - top) * ty);
+        }
+        store_px<U8>(out, i, o[0], o[1], o[2]);
+    }
+}
+template <bool U8>
+__global__ void __launch_bounds__(256) downsample_kernel(const void* __restrict__ in, int ch, int W, int H, int F, void* __restrict__ out) {
+    const int OW = (W + F - 1) / F, OH = (H + F - 1) / F;
+    const size_t n = (size_t)OW * OH;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const int X = (int)(i % OW), Y = (int)(i / OW);
+        float acc[3] = {0.f, 0.f, 0.f};
+        int cnt = 0;
+        for (int dy = 0; dy < F; ++dy)
+            for (int dx = 0; dx < F; ++dx) {
+                const int y = Y * F + dy, x = X * F + dx;
+                if (y < H && x < W) {
+                    ++cnt;
+                    #pragma unroll
+                    for (int c = 0; c < 3; ++c) acc[c] += srgb_to_linear(load_px<U8>(in, (size_t)y * W + x, ch, c));
+                }
+            }
+        const float inv = 1.0f / (float)cnt;
+        store_px<U8>(out, i, linear_to_srgb(acc[0] * inv), linear_to_srgb(acc[1] * inv), linear_to_srgb(acc[2] * inv));
+    }
+}
+
+template <bool U8, bool DOWN>
+static int aux_run(int device, const void* in, int w, int h, int in_ch, int factor, void* out) {
+    if (!in || !out) return fail(RSR_E_BAD_ARG, "null buffer");
+    if (w < 1 || h < 1 || factor < 1 || factor > 16) return fail(RSR_E_BAD_ARG, "bad dimensions w=%d h=%d factor=%d", w, h, factor);
+    if (U8 && in_ch != 3 && in_ch != 4) return fail(RSR_E_BAD_ARG, "in_channels must be 3 or 4 (got %d)", in_ch);
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        return fail(RSR_E_CUDA, "no CUDA device available (this library has no CPU fallback)");
+    }
+    if (device < 0 || device >= ndev) return fail(RSR_E_BAD_ARG, "device %d out of range", device);
+    CUDA_TRY(cudaSetDevice(device));
+    const size_t ipx = (size_t)w * h;
+    const size_t opx = DOWN ? (size_t)((w + factor - 1) / factor) * ((h + factor - 1) / factor) : ipx * factor * factor;
+    const size_t in_bytes = U8 ? ipx * in_ch : ipx * 12, out_bytes = U8 ? opx * 4 : opx * 12;
+    void *d_in = nullptr, *d_out = nullptr;
+    CUDA_TRY(cudaMalloc(&d_in, in_bytes));
+    cudaError_t e = cudaMalloc(&d_out, out_bytes);
+    if (e != cudaSuccess) { cudaFree(d_in); return fail(RSR_E_OOM, "cudaMalloc failed: %s", cudaGetErrorString(e)); }
+    e = cudaMemcpy(d_in, in, in_bytes, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) {
+        const int blocks = (int)std::min<size_t>((opx + 255) / 256, 148 * 16);
+        if (DOWN) downsample_kernel<U8><<<blocks, 256>>>(d_in, in_ch, w, h, factor, d_out);
+        else      bilinear_kernel<U8><<<blocks, 256>>>(d_in, in_ch, w, h, factor, d_out);
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaMemcpy(out, d_out, out_bytes, cudaMemcpyDeviceToHost);
+    cudaFree(d_in);
+    cudaFree(d_out);
+    if (e != cudaSuccess) return fail(RSR_E_CUDA, "%s", cudaGetErrorString(e));
+    return 0;
+}
+extern "C" int rsr_bilinear_f32(int device, const float* in, int w, int h, int factor, float* out) {
+    return aux_run<false, false>(device, in, w, h, 3, factor, out);
+}
+extern "C" int rsr_bilinear_u8(int device, const uint8_t* in, int w, int h, int in_channels, int factor, uint8_t* out) {
+    return aux_run<true, false>(device, in, w, h, in_channels, factor, out);
+}
+extern "C" int rsr_downsample_f32(int device, const float* in, int w, int h, int factor, float* out) {
+    return aux_run<false, true>(device, in, w, h, 3, factor, out);
+}
+extern "C" int rsr_downsample_u8(int device, const uint8_t* in, int w, int h, int in_channels, int factor, uint8_t* out) {
+    return aux_run<true, true>(device, in, w, h, in_channels, factor, out);
+}
