@@ -106,6 +106,14 @@ int rsr_bilinear_u8(int device, const uint8_t* in, int w, int h, int in_channels
 int rsr_downsample_f32(int device, const float* in_hwc3, int w, int h, int factor, float* out_hwc3);
 int rsr_downsample_u8(int device, const uint8_t* in, int w, int h, int in_channels, int factor, uint8_t* out_rgba);
 
+/* Generic "Same"-padded 3x3 convolution with the same kernel template as the sr_net launches (BASELINE config 5:
+ * per-layer conv sweep).  x: host f32 [h][w][cin], weights: host f32 [cout][3][3][cin] (alumina Convolution
+ * layout), out: host f32 [h][w][cout]; cin and cout must be multiples of 32.  The kernel part
+ * (input already packed, device resident) is repeated `iters` times and its mean duration in ms is written to
+ * *kernel_ms (may be NULL).  No context needed. */
+int rsr_conv2d_3x3_f32(int device, const float* x, const float* weights, int w, int h, int cin, int cout,
+                       float* out, int iters, float* kernel_ms);
+
 /* Use an externally created CUDA stream (cudaStream_t passed as void*) instead of the
  * context's own; NULL restores the internal stream. */
 int rsr_set_stream(rsr_ctx* ctx, void* cuda_stream);

@@ -79,6 +79,8 @@ def lib() -> ctypes.CDLL:
             for name in ("sr_oracle_bilinear_f64", "sr_oracle_downsample_f64"):
                 getattr(L, name).argtypes = [fp, ctypes.c_int, ctypes.c_int, ctypes.c_int, dp]
                 getattr(L, name).restype = None
+            L.sr_oracle_conv2d_f64.argtypes = [fp, ctypes.c_int, ctypes.c_int, ctypes.c_int, fp, ctypes.c_int, ctypes.c_int, dp]
+            L.sr_oracle_conv2d_f64.restype = ctypes.c_int
             L.sr_oracle_img_to_data.argtypes = [ctypes.c_char_p, ctypes.c_int, ctypes.c_int,
                                                 ctypes.c_int, fp]
             L.sr_oracle_data_to_img.argtypes = [fp, ctypes.c_int, ctypes.c_int, ctypes.c_char_p]
@@ -166,6 +168,22 @@ def downsample(image_hwc3: np.ndarray, factor: int = 3) -> np.ndarray:
     out = np.empty((-(-H // factor), -(-W // factor), 3), np.float64)
     lib().sr_oracle_downsample_f64(x.ctypes.data_as(ctypes.POINTER(ctypes.c_float)), W, H, factor,
                                    out.ctypes.data_as(ctypes.POINTER(ctypes.c_double)))
+    return out
+
+
+def conv2d(x: np.ndarray, weights: np.ndarray) -> np.ndarray:
+    """Zero-padded KxK cross-correlation, x f32 [H][W][Ci], weights f32 [Co][K][K][Ci] -> f64 [H][W][Co]
+    (alumina Convolution with Padding::Same; reference network.rs:33,60-72)."""
+    x = np.ascontiguousarray(x, dtype=np.float32)
+    w = np.ascontiguousarray(weights, dtype=np.float32)
+    H, W, ci = x.shape
+    co, k = w.shape[0], w.shape[1]
+    out = np.empty((H, W, co), np.float64)
+    fp = ctypes.POINTER(ctypes.c_float)
+    rc = lib().sr_oracle_conv2d_f64(x.ctypes.data_as(fp), W, H, ci, w.ctypes.data_as(fp), co, k,
+                                    out.ctypes.data_as(ctypes.POINTER(ctypes.c_double)))
+    if rc:
+        raise MemoryError("oracle conv2d failed")
     return out
 
 

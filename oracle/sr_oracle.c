@@ -213,3 +213,27 @@ void sr_oracle_downsample_f64(const float *in, int W, int H, int F, double *out)
                 out[((size_t)Y * OW + X) * 3 + c] = sr_linear_to_srgb(acc / cnt);
             }
 }
+
+/* Generic zero-padded KxK convolution (the op behind every `Convolution::new(.., Padding::Same, ..)`,
+ * network.rs:33,60-72) exposed for the per-layer sweep tests of rsr_conv2d_3x3_f32: in f32 [H][W][Ci],
+ * weights f32 [Co][K][K][Ci], out f64 [H][W][Co].  Returns 0 or -1. */
+int sr_oracle_conv2d_f64(const float *in, int W, int H, int Ci, const float *w_okki, int Co, int K, double *out) {
+    const size_t n = (size_t)W * H;
+    double *x = (double *)malloc(n * Ci * sizeof(double));
+    if (!x) return -1;
+    for (size_t i = 0; i < n * Ci; i++) x[i] = in[i];
+    memset(out, 0, n * Co * sizeof(double));
+    int rc = 0;
+    /* conv_acc handles up to 96 output channels per call (register tile); do wider layers in slices */
+    for (int co0 = 0; co0 < Co && !rc; co0 += 32) {
+        const int nco = Co - co0 < 32 ? Co - co0 : 32;
+        double *tmp = (double *)calloc(n * nco, sizeof(double));
+        if (!tmp) { rc = -1; break; }
+        rc = conv_acc_f64(x, H, W, Ci, w_okki + (size_t)co0 * K * K * Ci, nco, K, tmp);
+        for (size_t i = 0; i < n && !rc; i++)
+            for (int o = 0; o < nco; o++) out[i * Co + co0 + o] = tmp[i * nco + o];
+        free(tmp);
+    }
+    free(x);
+    return rc;
+}

@@ -19,7 +19,7 @@ from ._lib import RsrError
 from .network import FACTOR, num_params, param_layout
 from .rsr_format import decode_rsr, encode_rsr
 
-__all__ = ["Upscaler", "upscale", "bilinear", "downsample", "load_builtin_params", "decode_rsr", "encode_rsr", "RsrError",
+__all__ = ["Upscaler", "upscale", "bilinear", "downsample", "conv2d_3x3", "load_builtin_params", "decode_rsr", "encode_rsr", "RsrError",
            "num_params", "param_layout", "FACTOR", "BUILTIN_PARAMETERS"]
 
 _RES = os.path.join(os.path.dirname(os.path.abspath(__file__)), "res")
@@ -235,6 +235,22 @@ def downsample(image: np.ndarray, factor: int = FACTOR, device: int = 0) -> np.n
         out = np.empty((oh, ow, 3), np.float32)
         _lib.check(L.rsr_downsample_f32(device, _as_ptr(a), W, H, factor, _as_ptr(out)))
     return out
+
+
+def conv2d_3x3(x: np.ndarray, weights: np.ndarray, device: int = 0, iters: int = 1):
+    """Generic zero-padded 3x3 convolution on the sr_net kernel template (BASELINE config 5 sweep).
+    x: f32 [H][W][Cin], weights: f32 [Cout][3][3][Cin] (alumina layout); Cin, Cout multiples of 32.
+    Returns (out f32 [H][W][Cout], mean kernel milliseconds over `iters` runs)."""
+    L = _lib.load()
+    x = np.ascontiguousarray(x, dtype=np.float32)
+    wt = np.ascontiguousarray(weights, dtype=np.float32)
+    H, W, ci = x.shape
+    co = wt.shape[0]
+    assert wt.shape == (co, 3, 3, ci)
+    out = np.empty((H, W, co), np.float32)
+    ms = ctypes.c_float(0.0)
+    _lib.check(L.rsr_conv2d_3x3_f32(device, _as_ptr(x), _as_ptr(wt), W, H, ci, co, _as_ptr(out), iters, ctypes.byref(ms)))
+    return out, float(ms.value)
 
 
 def upscale(input_image: np.ndarray, parameters: str = "imagenet", custom: Optional[str] = None,

@@ -23,7 +23,7 @@ EXPORTS = (
     "rsr_last_kernel_times", "rsr_kernel_name", "rsr_last_launch_count", "rsr_last_error",
     "rsr_last_error_code", "rsr_version", "rsr_debug_stop_after", "rsr_debug_read_node",
     "rsr_debug_profile", "rsr_debug_read_profile",
-    "rsr_bilinear_f32", "rsr_bilinear_u8", "rsr_downsample_f32", "rsr_downsample_u8",
+    "rsr_bilinear_f32", "rsr_bilinear_u8", "rsr_downsample_f32", "rsr_downsample_u8", "rsr_conv2d_3x3_f32",
 )
 
 _lib = None
@@ -77,6 +77,8 @@ def load() -> ctypes.CDLL:
     L.rsr_downsample_u8.argtypes = [ci, vp, ci, ci, ci, ci, vp]
     for _n in ("rsr_bilinear_f32", "rsr_bilinear_u8", "rsr_downsample_f32", "rsr_downsample_u8"):
         getattr(L, _n).restype = ci
+    L.rsr_conv2d_3x3_f32.argtypes = [ci, vp, vp, ci, ci, ci, ci, vp, ci, fp]
+    L.rsr_conv2d_3x3_f32.restype = ci
     L.rsr_debug_stop_after.argtypes = [vp, ci]
     L.rsr_debug_stop_after.restype = ci
     L.rsr_debug_read_node.argtypes = [vp, ci, vp, ctypes.c_size_t]

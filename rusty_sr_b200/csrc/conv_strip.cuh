@@ -57,19 +57,23 @@ struct EpiGroup {
     int has_pin;          // a partial sum from an earlier launch is added to this group
     const float* bias;    // 32 floats (zero padded) or null
     const float* slope;   // 32 floats: BeLU p (EPI_ACT)
+    int c0;               // channel offset of this group in the output tensor (TMA coordinate 0)
+    int pad_;
 };
 
 struct ConvParams {
     CUtensorMap tmA;       // input node, rank 4: (RB/2 elems, W, H, NIMG), box (RB/2, BOXW, 1, 1)
     CUtensorMap tmB;       // packed weights, rank 2: (RB/2 elems, taps * NCOL), box (RB/2, NCOL)
     CUtensorMap tmPin[3];  // per group: fp32 partial-sum input, rank 4 (32, W, H, NIMG), box (32, 128, 1, 1)
-    CUtensorMap tmOut[3];  // per group: output, rank 4, box (.., 32 px, 1, 1): split-bf16 (64 elems) or fp32 (32)
+    CUtensorMap tmOut[8];  // per group: output, rank 4, box (.., 32 px, 1, 1): split-bf16 (64 elems) or fp32 (32)
     int W, H, NIMG;
     int row_begin, row_end;  // output rows computed; [0, H) normally
     int n_strips;
     long long total_rowtiles;  // NIMG * n_strips * (row_end - row_begin)
     int factor;
-    EpiGroup grp[3];
+    EpiGroup grp[8];
+    int n_cb;           // input channel blocks of 32 accumulated per output (1 for the sr_net launches; the
+                        // generic conv of csrc/conv2d.cu uses Cin / 32, planes stored as images img * n_cb + cb)
     const float4* xf4;  // EPI_SHUFFLE: input image as float4 [N][H][W] (bilinear skip)
     float* out_f32;     // EPI_SHUFFLE: [N][fH][fW][3] (or null)
     uint8_t* out_u8;    // EPI_SHUFFLE: [N][fH][fW][4] RGBA (or null)
@@ -347,18 +351,25 @@ __global__ void __launch_bounds__(256, 1) conv_strip_kernel(const __grid_constan
         ItemIter it = item_begin(p);
         WorkItem w;
         while (item_next<C>(p, it, w)) {
-            const int nrows = w.npass * C::R + 2 * C::PH;
-            for (int i = 0; i < nrows; ++i) {
-                RSR_WAIT(&a_empty[slot], par, 1, 0);
-                if (elect_one()) {
-                    if (ABL_NO_A_LOAD) { mbar_arrive(&a_full[slot]); }
-                    else {
-                        mbar_arrive_expect_tx(&a_full[slot], C::ROW_BYTES);
-                        tma_load_4d(sA + slot * C::SLOT, &p.tmA, &a_full[slot], 0, w.x0 - C::PW, w.y_b - C::PH + i, w.img);
+            // n_cb == 1: one sliding window over the item's rows.  n_cb > 1: every (pass, channel block)
+            // loads its own window of R + 2*PH rows from plane img * n_cb + cb.
+            const int nseg = p.n_cb == 1 ? 1 : w.npass * p.n_cb;
+            const int nrows = p.n_cb == 1 ? w.npass * C::R + 2 * C::PH : C::R + 2 * C::PH;
+            for (int sg = 0; sg < nseg; ++sg) {
+                const int cb = p.n_cb == 1 ? 0 : sg % p.n_cb;
+                const int y0 = w.y_b - C::PH + (p.n_cb == 1 ? 0 : (sg / p.n_cb) * C::R);
+                for (int i = 0; i < nrows; ++i) {
+                    RSR_WAIT(&a_empty[slot], par, 1, 0);
+                    if (elect_one()) {
+                        if (ABL_NO_A_LOAD) { mbar_arrive(&a_full[slot]); }
+                        else {
+                            mbar_arrive_expect_tx(&a_full[slot], C::ROW_BYTES);
+                            tma_load_4d(sA + slot * C::SLOT, &p.tmA, &a_full[slot], 0, w.x0 - C::PW, y0 + i, w.img * p.n_cb + cb);
+                        }
                     }
+                    __syncwarp();
+                    if (++slot == C::NR) { slot = 0; par ^= 1; }
                 }
-                __syncwarp();
-                if (++slot == C::NR) { slot = 0; par ^= 1; }
             }
         }
     } else if (warp == 3) {
@@ -368,18 +379,19 @@ __global__ void __launch_bounds__(256, 1) conv_strip_kernel(const __grid_constan
         WorkItem w;
         while (item_next<C>(p, it, w)) {
             for (int j = 0; j < w.npass; ++j)
-                for (int sp = 0; sp < C::NSTG; ++sp) {
-                    RSR_WAIT(&b_empty[st], par, 2, 0);
-                    if (elect_one()) {
-                        if (ABL_NO_B_LOAD) { mbar_arrive(&b_full[st]); }
-                        else {
-                            mbar_arrive_expect_tx(&b_full[st], C::BST);   // rows past the last tap are zero-filled
-                            tma_load_2d(sB + st * C::BST, &p.tmB, &b_full[st], 0, sp * C::TPS * C::NCOL);
+                for (int cb = 0; cb < p.n_cb; ++cb)
+                    for (int sp = 0; sp < C::NSTG; ++sp) {
+                        RSR_WAIT(&b_empty[st], par, 2, 0);
+                        if (elect_one()) {
+                            if (ABL_NO_B_LOAD) { mbar_arrive(&b_full[st]); }
+                            else {
+                                mbar_arrive_expect_tx(&b_full[st], C::BST);   // rows past the last tap: next block / zero fill
+                                tma_load_2d(sB + st * C::BST, &p.tmB, &b_full[st], 0, (cb * C::TAPS + sp * C::TPS) * C::NCOL);
+                            }
                         }
+                        __syncwarp();
+                        if (++st == C::NBS) { st = 0; par ^= 1; }
                     }
-                    __syncwarp();
-                    if (++st == C::NBS) { st = 0; par ^= 1; }
-                }
         }
     } else if (warp == 2) {
         // ===== partial-sum tile producer =====
@@ -430,8 +442,11 @@ __global__ void __launch_bounds__(256, 1) conv_strip_kernel(const __grid_constan
         while (item_next<C>(p, it, w)) {
             for (int j = 0; j < w.npass; ++j) {
                 RSR_WAIT(&t_empty[buf], tpar, 3, 0);
-                // rows this pass adds to the window: all of it for the first pass of an item, else R
-                const int nnew = j == 0 ? WIN : C::R;
+                for (int cb = 0; cb < p.n_cb; ++cb) {
+                // rows this segment adds to the window: all of it for the first pass of an item (and for every
+                // channel block of the generic conv), else R
+                const bool fresh = j == 0 || p.n_cb > 1;
+                const int nnew = fresh ? WIN : C::R;
                 for (int i = 0; i < nnew; ++i) {
                     RSR_WAIT(&a_full[wslot], wpar, 4, 1);
                     if (++wslot == C::NR) { wslot = 0; wpar ^= 1; }
@@ -468,7 +483,7 @@ __global__ void __launch_bounds__(256, 1) conv_strip_kernel(const __grid_constan
                                     #pragma unroll
                                     for (int c = 0; c < C::KC; ++c) {
                                         if (ABL_NO_MMA) continue;
-                                        umma_f16(d, desc(HI, a_e + 2 * c), desc(HI, b_e + 2 * c), IDESC, (t | c) != 0);
+                                        umma_f16(d, desc(HI, a_e + 2 * c), desc(HI, b_e + 2 * c), IDESC, (t | c) != 0 ? 1u : (uint32_t)(cb != 0));
                                         umma_f16(d, desc(HI, a_e + MID + 2 * c), desc(HI, b_e + 2 * c), IDESC, 1);
                                         umma_f16(d, desc(HI, a_e + 2 * c), desc(HI, b_e + MID + 2 * c), IDESC, 1);
                                     }
@@ -487,10 +502,10 @@ __global__ void __launch_bounds__(256, 1) conv_strip_kernel(const __grid_constan
                     if (RSR_PROF_ON) prof_acc[4] += clock64() - ti0;
                     if (++bst == C::NBS) { bst = 0; bpar ^= 1; }
                 }
-                const bool last = j == w.npass - 1;
+                const bool last = j == w.npass - 1 || p.n_cb > 1;
                 const int n_retire = last ? WIN : C::R;
                 if (elect_one()) {
-                    umma_commit(&t_full[buf]);
+                    if (cb == p.n_cb - 1) umma_commit(&t_full[buf]);
                     uint32_t sl = slot0 + NEARLY;
                     if (sl >= C::NR) sl -= C::NR;
                     for (int i = NEARLY; i < n_retire; ++i) {
@@ -502,6 +517,7 @@ __global__ void __launch_bounds__(256, 1) conv_strip_kernel(const __grid_constan
                 slot0 += n_retire;
                 if (slot0 >= C::NR) slot0 -= C::NR;
                 if (slot0 >= C::NR) slot0 -= C::NR;
+                }  // channel blocks
                 buf ^= 1;
                 if (buf == 0) tpar ^= 1;
             }
@@ -578,7 +594,7 @@ __global__ void __launch_bounds__(256, 1) conv_strip_kernel(const __grid_constan
                             if (elect_one()) {
                                 asm volatile(
                                     "cp.async.bulk.tensor.4d.global.shared::cta.tile.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
-                                    ::"l"(reinterpret_cast<uint64_t>(&p.tmOut[g])), "r"(stage), "r"(0), "r"(xw), "r"(y),
+                                    ::"l"(reinterpret_cast<uint64_t>(&p.tmOut[g])), "r"(stage), "r"(eg.c0), "r"(xw), "r"(y),
                                       "r"(w.img)
                                     : "memory");
                                 asm volatile("cp.async.bulk.commit_group;" ::: "memory");

@@ -489,8 +489,9 @@ static int forward_device(rsr_ctx* c, const void* d_in, bool u8, int in_ch, int 
 
     ConvParams p{};
     p.W = w; p.H = h; p.NIMG = n; p.row_begin = 0; p.row_end = h; p.factor = c->factor; p.fault = c->fault;
+    p.n_cb = 1;
     p.xf4 = (const float4*)c->xf4.p;
-    const EpiGroup none{EPI_NONE, 0, nullptr, nullptr};
+    const EpiGroup none{EPI_NONE, 0, nullptr, nullptr, 0, 0};
     auto in_map = [&](CUtensorMap* m, const void* base, int boxw) { return make_map_act(c, m, base, 64, w, h, n, boxw); };
     auto part_map = [&](CUtensorMap* m, const void* base, int boxw) { return make_map_part(c, m, base, w, h, n, boxw); };
 
@@ -498,7 +499,7 @@ static int forward_device(rsr_ctx* c, const void* d_in, bool u8, int in_ch, int 
     if (int rc = make_map_act(c, &p.tmA, xcol, 32, w, h, n, Cfg0::BOXW)) return rc;
     if (int rc = make_map_w(c, &p.tmB, c->w0, 32, 5 * 32, Cfg0::TPS * 32)) return rc;
     if (int rc = in_map(&p.tmOut[0], f_act, 32)) return rc;
-    p.grp[0] = EpiGroup{EPI_ACT, 0, f_bias, f_slope};
+    p.grp[0] = EpiGroup{EPI_ACT, 0, f_bias, f_slope, 0, 0};
     p.grp[1] = none; p.grp[2] = none;
     if (int rc = launch_conv<Cfg0>(c, p, 1)) return rc;
     CUDA_TRY(cudaEventRecord(c->ev[2], c->stream));
@@ -510,9 +511,9 @@ static int forward_device(rsr_ctx* c, const void* d_in, bool u8, int in_ch, int 
     if (int rc = in_map(&p.tmOut[0], l1_act, 32)) return rc;
     if (int rc = part_map(&p.tmOut[1], P2, 32)) return rc;
     if (int rc = part_map(&p.tmOut[2], P3, 32)) return rc;
-    p.grp[0] = EpiGroup{EPI_ACT, 0, l1_bias, l1_slope};
-    p.grp[1] = EpiGroup{EPI_RAW, 0, nullptr, nullptr};
-    p.grp[2] = EpiGroup{EPI_RAW, 0, nullptr, nullptr};
+    p.grp[0] = EpiGroup{EPI_ACT, 0, l1_bias, l1_slope, 0, 0};
+    p.grp[1] = EpiGroup{EPI_RAW, 0, nullptr, nullptr, 0, 0};
+    p.grp[2] = EpiGroup{EPI_RAW, 0, nullptr, nullptr, 0, 0};
     if (int rc = launch_conv<Cfg1>(c, p, 2)) return rc;
     CUDA_TRY(cudaEventRecord(c->ev[3], c->stream));
     if (c->stop_after == 2) return 0;
@@ -527,9 +528,9 @@ static int forward_device(rsr_ctx* c, const void* d_in, bool u8, int in_ch, int 
     if (int rc = in_map(&p.tmOut[0], l2_act, 32)) return rc;
     if (int rc = part_map(&p.tmOut[1], P3, 32)) return rc;
     if (int rc = part_map(&p.tmOut[2], E, 32)) return rc;
-    p.grp[0] = EpiGroup{EPI_ACT, 1, l2_bias, l2_slope};
-    p.grp[1] = EpiGroup{EPI_RAW, 1, nullptr, nullptr};
-    p.grp[2] = EpiGroup{EPI_RAW, 0, nullptr, nullptr};
+    p.grp[0] = EpiGroup{EPI_ACT, 1, l2_bias, l2_slope, 0, 0};
+    p.grp[1] = EpiGroup{EPI_RAW, 1, nullptr, nullptr, 0, 0};
+    p.grp[2] = EpiGroup{EPI_RAW, 0, nullptr, nullptr, 0, 0};
     if (int rc = launch_conv<Cfg2>(c, p, 3)) return rc;
     CUDA_TRY(cudaEventRecord(c->ev[4], c->stream));
     if (c->stop_after == 3) return 0;
@@ -541,8 +542,8 @@ static int forward_device(rsr_ctx* c, const void* d_in, bool u8, int in_ch, int 
     if (int rc = part_map(&p.tmPin[1], E, 128)) return rc;
     if (int rc = in_map(&p.tmOut[0], l3_act, 32)) return rc;
     if (int rc = part_map(&p.tmOut[1], E, 32)) return rc;
-    p.grp[0] = EpiGroup{EPI_ACT, 1, l3_bias, l3_slope};
-    p.grp[1] = EpiGroup{EPI_RAW, 1, nullptr, nullptr};
+    p.grp[0] = EpiGroup{EPI_ACT, 1, l3_bias, l3_slope, 0, 0};
+    p.grp[1] = EpiGroup{EPI_RAW, 1, nullptr, nullptr, 0, 0};
     p.grp[2] = none;
     if (int rc = launch_conv<Cfg3>(c, p, 4)) return rc;
     CUDA_TRY(cudaEventRecord(c->ev[5], c->stream));
@@ -552,7 +553,7 @@ static int forward_device(rsr_ctx* c, const void* d_in, bool u8, int in_ch, int 
     if (int rc = in_map(&p.tmA, l3_act, Cfg4::BOXW)) return rc;
     if (int rc = make_map_w(c, &p.tmB, c->w4, 64, 9 * 32, Cfg4::TPS * 32)) return rc;
     if (int rc = part_map(&p.tmPin[0], E, 128)) return rc;
-    p.grp[0] = EpiGroup{EPI_SHUFFLE, 1, e_bias, nullptr};
+    p.grp[0] = EpiGroup{EPI_SHUFFLE, 1, e_bias, nullptr, 0, 0};
     p.grp[1] = none; p.grp[2] = none;
     p.out_f32 = d_out_f32;
     p.out_u8 = d_out_u8;
@@ -861,4 +862,193 @@ extern "C" int rsr_downsample_f32(int device, const float* in, int w, int h, int
 }
 extern "C" int rsr_downsample_u8(int device, const uint8_t* in, int w, int h, int in_channels, int factor, uint8_t* out) {
     return aux_run<true, true>(device, in, w, h, in_channels, factor, out);
+}
+
+// --------------------------------------------------------------- generic 3x3 convolution (config 5 sweep)
+// Same kernel template; the input's Cin/32 channel blocks are stored as planes in the activation format
+// ([cb][H][W][32 hi | 32 mid]) and accumulated in TMEM (ConvParams::n_cb), the output is fp32 [H][W][Cout]
+// written 32 channels at a time by the RAW epilogue through a tensor map with a channel coordinate.
+//                        KH KW  RB NG R NR TPS NBS NPIN NOUT SHUF
+using CvN32  = ConvCfg<3, 3, 128, 1, 2, 6, 3, 3, 0, 2, false>;
+using CvN64  = ConvCfg<3, 3, 128, 2, 2, 6, 2, 3, 0, 2, false>;
+using CvN128 = ConvCfg<3, 3, 128, 4, 2, 6, 1, 4, 0, 2, false>;
+using CvN256 = ConvCfg<3, 3, 128, 8, 1, 5, 1, 3, 0, 2, false>;
+
+__global__ void __launch_bounds__(256) pack_planes_kernel(const float* __restrict__ x, int W, int H, int Ci,
+                                                           __nv_bfloat16* __restrict__ planes) {
+    // one thread = one pixel x one channel block of 32
+    const size_t npx = (size_t)W * H;
+    const int ncb = Ci / 32;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < npx * ncb; i += (size_t)gridDim.x * blockDim.x) {
+        const size_t px = i % npx;
+        const int cb = (int)(i / npx);
+        const float* src = x + px * Ci + cb * 32;
+        uint32_t hi[16], mid[16];
+        #pragma unroll
+        for (int k = 0; k < 16; ++k) split_pair(src[2 * k], src[2 * k + 1], hi[k], mid[k]);
+        uint4* dst = reinterpret_cast<uint4*>(planes + ((size_t)cb * npx + px) * 64);
+        #pragma unroll
+        for (int k = 0; k < 4; ++k) dst[k] = make_uint4(hi[4 * k], hi[4 * k + 1], hi[4 * k + 2], hi[4 * k + 3]);
+        #pragma unroll
+        for (int k = 0; k < 4; ++k) dst[4 + k] = make_uint4(mid[4 * k], mid[4 * k + 1], mid[4 * k + 2], mid[4 * k + 3]);
+    }
+}
+
+struct AuxMaps {
+    PFN_cuTensorMapEncodeTiled_v12000 encode;
+};
+static int encode_map(PFN_cuTensorMapEncodeTiled_v12000 enc, CUtensorMap* m, CUtensorMapDataType dt, int rank, const void* base,
+                      const cuuint64_t* dims, const cuuint64_t* strides, const cuuint32_t* box) {
+    cuuint32_t es[4] = {1, 1, 1, 1};
+    CUresult r = enc(m, dt, rank, const_cast<void*>(base), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(RSR_E_CUDA, "cuTensorMapEncodeTiled failed: %d", (int)r);
+    return 0;
+}
+
+template <class C>
+static int conv2d_block(PFN_cuTensorMapEncodeTiled_v12000 enc, int num_sms, cudaStream_t st, const __nv_bfloat16* planes,
+                        const __nv_bfloat16* wpack, float* d_out, int W, int H, int Ci, int Co, int co0, int* fault) {
+    ConvParams p{};
+    p.W = W; p.H = H; p.NIMG = 1; p.row_begin = 0; p.row_end = H; p.factor = 3; p.fault = fault;
+    p.n_cb = Ci / 32;
+    {
+        cuuint64_t dims[4] = {64, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)p.n_cb};
+        cuuint64_t strides[3] = {128, (cuuint64_t)128 * W, (cuuint64_t)128 * W * H};
+        cuuint32_t box[4] = {64, (cuuint32_t)C::BOXW, 1, 1};
+        if (int rc = encode_map(enc, &p.tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, planes, dims, strides, box)) return rc;
+    }
+    {
+        cuuint64_t dims[2] = {64, (cuuint64_t)p.n_cb * 9 * C::NCOL};
+        cuuint64_t strides[1] = {128};
+        cuuint32_t box[2] = {64, (cuuint32_t)(C::TPS * C::NCOL)};
+        if (int rc = encode_map(enc, &p.tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, wpack, dims, strides, box)) return rc;
+    }
+    for (int g = 0; g < C::NG; ++g) {
+        cuuint64_t dims[4] = {(cuuint64_t)Co, (cuuint64_t)W, (cuuint64_t)H, 1};
+        cuuint64_t strides[3] = {(cuuint64_t)Co * 4, (cuuint64_t)Co * 4 * W, (cuuint64_t)Co * 4 * W * H};
+        cuuint32_t box[4] = {32, 32, 1, 1};
+        if (int rc = encode_map(enc, &p.tmOut[g], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, d_out, dims, strides, box)) return rc;
+        p.grp[g] = EpiGroup{EPI_RAW, 0, nullptr, nullptr, co0 + g * 32, 0};
+    }
+    p.n_strips = (W + 127) / 128;
+    p.total_rowtiles = (long long)p.n_strips * H;
+    const int grid = (int)std::min<long long>(p.total_rowtiles, num_sms);
+    CUDA_TRY(cudaFuncSetAttribute(conv_strip_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+    conv_strip_kernel<C><<<grid, 256, C::SMEM_BYTES, st>>>(p);
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int rsr_conv2d_3x3_f32(int device, const float* x, const float* weights, int w, int h, int cin, int cout,
+                                  float* out, int iters, float* kernel_ms) {
+    if (!x || !weights || !out) return fail(RSR_E_BAD_ARG, "null buffer");
+    if (w < 1 || h < 1 || cin < 32 || cout < 32 || cin % 32 || cout % 32)
+        return fail(RSR_E_UNSUPPORTED, "conv2d: cin and cout must be positive multiples of 32 (got %d, %d)", cin, cout);
+    if (iters < 1) iters = 1;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        return fail(RSR_E_CUDA, "no CUDA device available (this library has no CPU fallback)");
+    }
+    if (device < 0 || device >= ndev) return fail(RSR_E_BAD_ARG, "device %d out of range", device);
+    CUDA_TRY(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) return fail(RSR_E_CUDA, "device is sm_%d%d; sm_100a code only", prop.major, prop.minor);
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    CUDA_TRY(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+    if (qres != cudaDriverEntryPointSuccess || !fn) return fail(RSR_E_CUDA, "driver lacks cuTensorMapEncodeTiled");
+    auto enc = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(fn);
+
+    const size_t npx = (size_t)w * h;
+    const int ncb = cin / 32;
+    // output-channel blocks: the widest kernel (N = 256, 128, 64, 32) that fits what is left
+    struct Blk { int co0, n; };
+    std::vector<Blk> blocks;
+    for (int co0 = 0; co0 < cout;) {
+        const int left = cout - co0;
+        const int n = left >= 256 ? 256 : left >= 128 ? 128 : left >= 64 ? 64 : 32;
+        blocks.push_back({co0, n});
+        co0 += n;
+    }
+    // weights [cout][3][3][cin] -> per block [cb][tap][n][32 hi | 32 mid]
+    std::vector<std::vector<__nv_bfloat16>> packs(blocks.size());
+    for (size_t b = 0; b < blocks.size(); ++b) {
+        const int n = blocks[b].n, co0 = blocks[b].co0;
+        auto& pk = packs[b];
+        pk.assign((size_t)ncb * 9 * n * 64 + (size_t)n * 64 * 4, __float2bfloat16_rn(0.f));  // tail pad: last stage may over-read
+        for (int o = 0; o < n; ++o)
+            for (int t = 0; t < 9; ++t)
+                for (int ci = 0; ci < cin; ++ci) {
+                    __nv_bfloat16 hh, mm;
+                    split_bf16(weights[(((size_t)(co0 + o)) * 9 + t) * cin + ci], hh, mm);
+                    const size_t row = (((size_t)(ci / 32) * 9 + t) * n + o) * 64;
+                    pk[row + ci % 32] = hh;
+                    pk[row + 32 + ci % 32] = mm;
+                }
+    }
+    float* d_x = nullptr; float* d_out = nullptr; __nv_bfloat16* d_planes = nullptr; int* d_fault = nullptr;
+    std::vector<__nv_bfloat16*> d_w(blocks.size(), nullptr);
+    cudaStream_t st = nullptr;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    int rc = 0;
+    auto cleanup = [&]() {
+        cudaFree(d_x); cudaFree(d_out); cudaFree(d_planes); cudaFree(d_fault);
+        for (auto p : d_w) cudaFree(p);
+        if (e0) cudaEventDestroy(e0);
+        if (e1) cudaEventDestroy(e1);
+        if (st) cudaStreamDestroy(st);
+    };
+#define CV_TRY(expr) do { cudaError_t e__ = (expr); if (e__ != cudaSuccess) { rc = fail(e__ == cudaErrorMemoryAllocation ? RSR_E_OOM : RSR_E_CUDA, "%s: %s", #expr, cudaGetErrorString(e__)); cleanup(); return rc; } } while (0)
+    CV_TRY(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    CV_TRY(cudaEventCreate(&e0));
+    CV_TRY(cudaEventCreate(&e1));
+    CV_TRY(cudaMalloc((void**)&d_x, npx * cin * sizeof(float)));
+    CV_TRY(cudaMalloc((void**)&d_out, npx * cout * sizeof(float)));
+    CV_TRY(cudaMalloc((void**)&d_planes, npx * ncb * 128));
+    CV_TRY(cudaMalloc((void**)&d_fault, sizeof(int)));
+    CV_TRY(cudaMemsetAsync(d_fault, 0, sizeof(int), st));
+    for (size_t b = 0; b < blocks.size(); ++b) {
+        CV_TRY(cudaMalloc((void**)&d_w[b], packs[b].size() * 2));
+        CV_TRY(cudaMemcpyAsync(d_w[b], packs[b].data(), packs[b].size() * 2, cudaMemcpyHostToDevice, st));
+    }
+    CV_TRY(cudaMemcpyAsync(d_x, x, npx * cin * sizeof(float), cudaMemcpyHostToDevice, st));
+    {
+        const int nblk = (int)std::min<size_t>((npx * ncb + 255) / 256, (size_t)prop.multiProcessorCount * 16);
+        pack_planes_kernel<<<nblk, 256, 0, st>>>(d_x, w, h, cin, d_planes);
+        CV_TRY(cudaGetLastError());
+    }
+    for (int it = 0; it < iters + 1; ++it) {   // first round is a warm-up
+        if (it == 1) CV_TRY(cudaEventRecord(e0, st));
+        for (size_t b = 0; b < blocks.size(); ++b) {
+            const int n = blocks[b].n, co0 = blocks[b].co0;
+            if (n == 256)      rc = conv2d_block<CvN256>(enc, prop.multiProcessorCount, st, d_planes, d_w[b], d_out, w, h, cin, cout, co0, d_fault);
+            else if (n == 128) rc = conv2d_block<CvN128>(enc, prop.multiProcessorCount, st, d_planes, d_w[b], d_out, w, h, cin, cout, co0, d_fault);
+            else if (n == 64)  rc = conv2d_block<CvN64>(enc, prop.multiProcessorCount, st, d_planes, d_w[b], d_out, w, h, cin, cout, co0, d_fault);
+            else               rc = conv2d_block<CvN32>(enc, prop.multiProcessorCount, st, d_planes, d_w[b], d_out, w, h, cin, cout, co0, d_fault);
+            if (rc) { cleanup(); return rc; }
+        }
+    }
+    CV_TRY(cudaEventRecord(e1, st));
+    CV_TRY(cudaMemcpyAsync(out, d_out, npx * cout * sizeof(float), cudaMemcpyDeviceToHost, st));
+    {
+        cudaError_t e = cudaStreamSynchronize(st);
+        if (e != cudaSuccess) {
+            int f = 0;
+            cudaMemcpy(&f, d_fault, sizeof f, cudaMemcpyDeviceToHost);
+            rc = fail(RSR_E_CUDA, "conv2d kernel failed: %s (fault word 0x%x)", cudaGetErrorString(e), f);
+            cleanup();
+            return rc;
+        }
+    }
+    if (kernel_ms) {
+        float ms = 0.f;
+        CV_TRY(cudaEventElapsedTime(&ms, e0, e1));
+        *kernel_ms = ms / iters;
+    }
+#undef CV_TRY
+    cleanup();
+    return 0;
 }
