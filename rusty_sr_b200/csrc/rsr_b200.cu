@@ -153,7 +153,8 @@ struct rsr_ctx {
     float* vecs = nullptr;  // 9 x 32 floats: f_bias f_activ l1_bias l1_activ l2_bias l2_activ l3_bias l3_activ expand_bias
     // workspace
     DevBuf xcol, xf4, actA, actB, partA, partB, out_f32, out_u8, in_stage;
-    int* fault = nullptr;
+    int* fault = nullptr;       // device alias of fault_host (mapped pinned memory: readable after a kernel trap)
+    int* fault_host = nullptr;  // [0] = code, [4 + 4*warp ..] = which barrier each warp role was stuck on
     cudaEvent_t ev[K_COUNT + 1] = {};
     bool timed = false;
     int last_launches = 0;
@@ -230,7 +231,8 @@ extern "C" void rsr_destroy(rsr_ctx* c) {
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
     cudaFree(c->w0); cudaFree(c->w1); cudaFree(c->w2); cudaFree(c->w3); cudaFree(c->w4);
-    cudaFree(c->vecs); cudaFree(c->fault); cudaFree(c->prof);
+    cudaFree(c->vecs); cudaFree(c->prof);
+    if (c->fault_host) cudaFreeHost(c->fault_host);
     release(c->xcol); release(c->xf4); release(c->actA); release(c->actB); release(c->partA);
     release(c->partB); release(c->out_f32); release(c->out_u8); release(c->in_stage);
     for (auto& e : c->ev) if (e) cudaEventDestroy(e);
@@ -277,8 +279,9 @@ static int create_impl(rsr_ctx* c, const float* params) {
         CUDA_TRY(cudaEventCreateWithFlags(&sl.ev_done, cudaEventDisableTiming));
         CUDA_TRY(cudaEventCreateWithFlags(&sl.ev_out, cudaEventDisableTiming));
     }
-    CUDA_TRY(cudaMalloc((void**)&c->fault, sizeof(int)));
-    CUDA_TRY(cudaMemset(c->fault, 0, sizeof(int)));
+    CUDA_TRY(cudaHostAlloc((void**)&c->fault_host, 64 * sizeof(int), cudaHostAllocMapped));
+    memset(c->fault_host, 0, 64 * sizeof(int));
+    CUDA_TRY(cudaHostGetDevicePointer((void**)&c->fault, c->fault_host, 0));
 
     // conv0: [32][5][5][3] -> w0[a][n][k = dxi*3 + c | 16 + k]  (x-im2col form, 64 B rows)
     {
@@ -387,9 +390,13 @@ extern "C" int rsr_synchronize(rsr_ctx* c) {
     CUDA_TRY(cudaSetDevice(c->device));
     cudaError_t e = cudaStreamSynchronize(c->stream);
     if (e != cudaSuccess) {
-        int f = 0;
-        cudaMemcpy(&f, c->fault, sizeof f, cudaMemcpyDeviceToHost);
-        return fail(RSR_E_CUDA, "kernel failed: %s (fault word 0x%x)", cudaGetErrorString(e), f);
+        std::string log;
+        if (c->fault_host)
+            for (int wq = 0; wq < 12; ++wq) {
+                const int* r = c->fault_host + 4 + wq * 4;
+                if (r[0]) { char b[96]; snprintf(b, sizeof b, " [warp %d: tag %d cta %d parity %d bar@0x%x]", wq, r[0], r[1], r[2], r[3]); log += b; }
+            }
+        return fail(RSR_E_CUDA, "kernel failed: %s (fault word 0x%x)%s", cudaGetErrorString(e), c->fault_host ? c->fault_host[0] : 0, log.c_str());
     }
     return 0;
 }
@@ -592,6 +599,7 @@ static int upscale_host(rsr_ctx* c, const void* in, bool u8, int in_ch, int n, i
     if (out_f32) { if (int rc = ensure(c->out_f32, opx * 3 * sizeof(float))) return rc; d_f32 = (float*)c->out_f32.p; }
     if (out_u8) { if (int rc = ensure(c->out_u8, opx * 4)) return rc; d_u8 = (uint8_t*)c->out_u8.p; }
     if (int rc = forward_device(c, c->in_stage.p, u8, in_ch, n, w, h, d_f32, d_u8)) return rc;
+    if (int rc = rsr_synchronize(c)) return rc;   // surfaces a kernel fault (with its fault word) before the copies
     // band mode copies a row window of a single image; otherwise everything
     const size_t orow_px = (size_t)w * F;
     if (out_f32)
@@ -655,11 +663,8 @@ extern "C" int rsr_wait(rsr_ctx* c, int ticket) {
     if (newest - t >= 3) return 0;  // slot already recycled: frames complete in order, so it is done
     CUDA_TRY(cudaSetDevice(c->device));
     cudaError_t e = cudaEventSynchronize(c->slot[t % 3].ev_out);
-    if (e != cudaSuccess) {
-        int f = 0;
-        cudaMemcpy(&f, c->fault, sizeof f, cudaMemcpyDeviceToHost);
-        return fail(RSR_E_CUDA, "frame failed: %s (fault word 0x%x)", cudaGetErrorString(e), f);
-    }
+    if (e != cudaSuccess)
+        return fail(RSR_E_CUDA, "frame failed: %s (fault word 0x%x)", cudaGetErrorString(e), c->fault_host ? c->fault_host[0] : 0);
     return 0;
 }
 extern "C" int rsr_wait_all(rsr_ctx* c) {
@@ -1008,8 +1013,8 @@ extern "C" int rsr_conv2d_3x3_f32(int device, const float* x, const float* weigh
     CV_TRY(cudaMalloc((void**)&d_x, npx * cin * sizeof(float)));
     CV_TRY(cudaMalloc((void**)&d_out, npx * cout * sizeof(float)));
     CV_TRY(cudaMalloc((void**)&d_planes, npx * ncb * 128));
-    CV_TRY(cudaMalloc((void**)&d_fault, sizeof(int)));
-    CV_TRY(cudaMemsetAsync(d_fault, 0, sizeof(int), st));
+    CV_TRY(cudaMalloc((void**)&d_fault, 64 * sizeof(int)));   // fault code + per-warp records (ptx.cuh mbar_wait)
+    CV_TRY(cudaMemsetAsync(d_fault, 0, 64 * sizeof(int), st));
     for (size_t b = 0; b < blocks.size(); ++b) {
         CV_TRY(cudaMalloc((void**)&d_w[b], packs[b].size() * 2));
         CV_TRY(cudaMemcpyAsync(d_w[b], packs[b].data(), packs[b].size() * 2, cudaMemcpyHostToDevice, st));
