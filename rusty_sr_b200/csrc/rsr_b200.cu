@@ -82,7 +82,19 @@ static Layout make_layout(int factor) {
 // --------------------------------------------------------------------------- kernel configs
 //                      KH KW  RB NG R NR TPS NBS NPIN NOUT SHUF
 using Cfg0 = ConvCfg<5, 1,  64, 1, 4, 12, 5, 2, 0, 2, false>;  // conv0 on the x-im2col'd input (K = 5 taps x 16)
-using Cfg1 = ConvCfg<5, 5, 128, 3, 2,  7, 2, 3, 0, 2, false>;  // f  -> conv1 | conv2 | conv3
+#ifndef RSR_CFG1_NR
+#define RSR_CFG1_NR 7
+#endif
+#ifndef RSR_CFG1_TPS
+#define RSR_CFG1_TPS 2
+#endif
+#ifndef RSR_CFG1_NBS
+#define RSR_CFG1_NBS 3
+#endif
+#ifndef RSR_L2PROMO
+#define RSR_L2PROMO CU_TENSOR_MAP_L2_PROMOTION_L2_256B
+#endif
+using Cfg1 = ConvCfg<5, 5, 128, 3, 2, RSR_CFG1_NR, RSR_CFG1_TPS, RSR_CFG1_NBS, 0, 2, false>;  // f  -> conv1 | conv2 | conv3
 using Cfg2 = ConvCfg<3, 3, 128, 3, 2,  5, 2, 3, 2, 2, false>;  // l1 -> conv5 | conv6 | conv7   (+ P2, P3)
 using Cfg3 = ConvCfg<3, 3, 128, 2, 2,  5, 2, 3, 3, 2, false>;  // l2 -> conv8 | conv9           (+ P3, E)
 using Cfg4 = ConvCfg<3, 3, 128, 1, 2,  6, 3, 3, 3, 2, true>;   // l3 -> conv10 (+ E) + expand + bilinear skip
@@ -411,7 +423,7 @@ static int make_map_act(rsr_ctx* c, CUtensorMap* m, const void* base, int elems,
     CUresult r = c->encode(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, es,
                            CU_TENSOR_MAP_INTERLEAVE_NONE,
                            elems == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
-                           CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                           RSR_L2PROMO, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail(RSR_E_CUDA, "cuTensorMapEncodeTiled(activation %dx%dx%d) failed: %d", W, H, N, (int)r);
     return 0;
 }
@@ -435,7 +447,7 @@ static int make_map_w(rsr_ctx* c, CUtensorMap* m, const void* base, int elems, i
     CUresult r = c->encode(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, es,
                            CU_TENSOR_MAP_INTERLEAVE_NONE,
                            elems == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
-                           CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                           RSR_L2PROMO, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail(RSR_E_CUDA, "cuTensorMapEncodeTiled(weights) failed: %d", (int)r);
     return 0;
 }
@@ -906,7 +918,7 @@ static int encode_map(PFN_cuTensorMapEncodeTiled_v12000 enc, CUtensorMap* m, CUt
                       const cuuint64_t* dims, const cuuint64_t* strides, const cuuint32_t* box) {
     cuuint32_t es[4] = {1, 1, 1, 1};
     CUresult r = enc(m, dt, rank, const_cast<void*>(base), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                     CU_TENSOR_MAP_SWIZZLE_128B, RSR_L2PROMO, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail(RSR_E_CUDA, "cuTensorMapEncodeTiled failed: %d", (int)r);
     return 0;
 }
