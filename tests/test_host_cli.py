@@ -116,3 +116,17 @@ def test_cli_reproduces_the_reference_golden_image(tmp_path):
     assert run(os.path.join(GOLDEN, "butterfly_lr.png"), str(out2)).returncode == 0   # default parameters: imagenet (main.rs:144)
     got, want = np.asarray(Image.open(out2)), load_png("butterfly_rs")
     assert np.abs(got.astype(int) - want.astype(int)).max() <= 5
+
+
+@pytest.mark.gpu
+def test_python_cli_matches_compiled_cli(tmp_path):
+    """python -m rusty_sr_b200.cli has the same flag surface and produces the same image as bin/rusty_sr."""
+    import sys
+    a, b = tmp_path / "a.png", tmp_path / "b.png"
+    src = os.path.join(GOLDEN, "cartoon_lr.png")
+    assert run(src, str(a), "-p", "imagenetlinear").returncode == 0
+    r = subprocess.run([sys.executable, "-m", "rusty_sr_b200.cli", src, str(b), "-p", "imagenetlinear"], cwd=ROOT,
+                       stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr
+    assert "Upscaling using linear loss imagenet neural net parameters..." in r.stdout      # main.rs:148
+    assert np.array_equal(np.asarray(Image.open(a)), np.asarray(Image.open(b)))
