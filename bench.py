@@ -121,6 +121,11 @@ def cpu_sample(rows: int, steps: int, warmup: int):
     from oracle import oracle as O
     import rusty_sr_b200 as R
     params = R.load_builtin_params("imagenet")
+    # use every host core this process may run on, even when the launcher (torchrun) exported OMP_NUM_THREADS=1
+    try:
+        O.set_threads(len(os.sched_getaffinity(0)))
+    except AttributeError:
+        O.set_threads(os.cpu_count() or 1)
     img = make_inputs(0)[0][:rows]
     for _ in range(warmup):
         O.data_to_img(O.forward(params, O.img_to_data(img[:8]), 3, np.float32))
