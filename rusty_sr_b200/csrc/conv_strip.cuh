@@ -25,8 +25,10 @@
 // TMEM -> registers (+ partial from smem) -> bias / BeLU / split -> swizzled staging -> TMA store.  R output rows are accumulated per pass in TMEM, double
 // buffered, so the epilogue of pass j overlaps the MMAs of pass j + 1.
 //
-// Warp roles (256 threads): warp 0 = input-row producer, warp 3 = weight producer, warp 2 = TMEM
-// allocator + partial-sum producer, warp 1 = MMA issuer (one lane), warps 4..7 = epilogue.
+// Warp roles: warp 0 = input-row producer, warp 3 = weight producer, warp 2 = TMEM allocator +
+// partial-sum producer, warp 1 = MMA issuer (one lane), warps 4.. = epilogue (4 or 8 warps per config;
+// with 8, two warps per TMEM lane quarter take alternate (row, group) tiles of a pass, which hides the
+// instruction latency of the ALU-heavy epilogues: conv0 -11 %, conv5|6|7 -6 %, conv10 -10 %, measured).
 #pragma once
 #include <cuda_bf16.h>
 #include "ptx.cuh"
@@ -98,10 +100,13 @@ struct ConvParams {
         }                                                                \
     } while (0)
 
-template <int KH_, int KW_, int RB_, int NG_, int R_, int NR_, int TPS_, int NBS_, int NPIN_, int NOUT_, bool SHUF_>
+template <int KH_, int KW_, int RB_, int NG_, int R_, int NR_, int TPS_, int NBS_, int NPIN_, int NOUT_, bool SHUF_, int NEPI_ = 4>
 struct ConvCfg {
     static constexpr int KH = KH_, KW = KW_, RB = RB_, NG = NG_, R = R_;
-    static constexpr int NBS = NBS_, NPIN = NPIN_, NOUT = NOUT_;
+    static constexpr int NEPI = NEPI_;                                 // epilogue warps (4 or 8)
+    static_assert(NEPI == 4 || NEPI == 8, "4 or 8 epilogue warps");
+    static constexpr int NTHREADS = 128 + 32 * NEPI;
+    static constexpr int NBS = NBS_, NPIN = NPIN_, NOUT = NEPI == 8 ? 1 : NOUT_;   // staging tiles per epilogue warp
     static constexpr bool SHUF = SHUF_;
     static constexpr int NCOL = 32 * NG;
     static constexpr int PH = KH / 2, PW = KW / 2;
@@ -122,7 +127,7 @@ struct ConvCfg {
     static constexpr int OFF_B = NR * SLOT;
     static constexpr int OFF_P = OFF_B + NBS * BST;
     static constexpr int OFF_O = OFF_P + NPIN * PIN_BYTES;
-    static constexpr int OFF_BAR = OFF_O + 4 * NOUT * 4096;
+    static constexpr int OFF_BAR = OFF_O + NEPI * NOUT * 4096;
     static constexpr int NBAR = 2 * NR + 2 * NBS + 2 * (NPIN > 0 ? NPIN : 1) + 4;
     static constexpr int SMEM_BYTES = 1024 + OFF_BAR + NBAR * 8 + 16;
     static constexpr uint32_t SWZ = RB == 128 ? UMMA_SW_128B : UMMA_SW_64B;
@@ -296,7 +301,7 @@ __device__ __forceinline__ void epi_add_partial_tile(float (&v)[32], uint32_t ti
 
 // ---- the kernel ------------------------------------------------------------------------------
 template <class C>
-__global__ void __launch_bounds__(256, 1) conv_strip_kernel(const __grid_constant__ ConvParams p) {
+__global__ void __launch_bounds__(C::NTHREADS, 1) conv_strip_kernel(const __grid_constant__ ConvParams p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* sA = smem;
@@ -329,8 +334,8 @@ __global__ void __launch_bounds__(256, 1) conv_strip_kernel(const __grid_constan
     if (threadIdx.x == 0) {
         for (int i = 0; i < C::NR; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
         for (int i = 0; i < C::NBS; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
-        for (int i = 0; i < NPB; ++i) { mbar_init(&p_full[i], 1); mbar_init(&p_empty[i], 4); }
-        for (int i = 0; i < 2; ++i) { mbar_init(&t_full[i], 1); mbar_init(&t_empty[i], 4); }
+        for (int i = 0; i < NPB; ++i) { mbar_init(&p_full[i], 1); mbar_init(&p_empty[i], C::NEPI); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&t_full[i], 1); mbar_init(&t_empty[i], C::NEPI); }
         fence_mbar_init();
         tma_prefetch_desc(&p.tmA);
         tma_prefetch_desc(&p.tmB);
@@ -524,8 +529,10 @@ __global__ void __launch_bounds__(256, 1) conv_strip_kernel(const __grid_constan
         }
     } else if (warp >= 4) {
         // ===== epilogue =====
-        const int ew = warp - 4;  // == warp % 4: TMEM lane quarter this warp may read
-        const uint32_t stage0 = smem_u32(sO) + ew * (C::NOUT * 4096);
+        const int e = warp - 4;   // epilogue warp index
+        const int ew = e & 3;     // == warp % 4: TMEM lane quarter this warp may read
+        const int eh = e >> 2;    // with 8 epilogue warps: which half of the pass's (row, group) tiles this warp takes
+        const uint32_t stage0 = smem_u32(sO) + e * (C::NOUT * 4096);
         uint32_t buf = 0, tpar = 0, oc = 0;
         uint32_t pst = 0, ppar = 0;  // partial-sum tile ring (consumed in producer order: row, then group)
         const uint32_t sP_u = smem_u32(sP);
@@ -537,8 +544,9 @@ __global__ void __launch_bounds__(256, 1) conv_strip_kernel(const __grid_constan
             for (int j = 0; j < w.npass; ++j, buf ^= 1, tpar ^= (buf == 0)) {
                 SkipNb nb;
                 if (C::SHUF) {
-                    // the skip input does not depend on the MMAs: fetch the first row's before waiting
-                    const int y = w.y_b + j * C::R;
+                    // the skip input does not depend on the MMAs: fetch this warp's first row before waiting
+                    // (SHUF launches have one group, so tile u == row r; with 8 warps this warp owns rows r % 2 == eh)
+                    const int y = w.y_b + j * C::R + eh;
                     if (y < w.y_e && x < p.W) load_skip_nb(p, w.img, y, x, nb);
                 }
                 RSR_WAIT(&t_full[buf], tpar, 6, 0);
@@ -553,6 +561,19 @@ __global__ void __launch_bounds__(256, 1) conv_strip_kernel(const __grid_constan
                         const EpiGroup& eg = p.grp[g];
                         if (eg.kind == EPI_NONE) continue;
                         const bool pin = C::NPIN > 0 && eg.has_pin;
+                        const bool mine = C::NEPI == 4 || (((r * C::NG + g) & 1) == eh);   // warp-uniform tile ownership
+                        if (!mine) {
+                            // The other warp of this lane quarter handles the tile.  Every epilogue warp still
+                            // observes every partial-sum tile (wait full, arrive empty): a warp that skipped the
+                            // wait could fall two phases behind the barrier and mistake parity for completion.
+                            if (pin) {
+                                RSR_WAIT(&p_full[pst], ppar, 9, 3);
+                                __syncwarp();
+                                if (lane == 0) mbar_arrive(&p_empty[pst]);
+                                if (++pst == NPB) { pst = 0; ppar ^= 1; }
+                            }
+                            continue;
+                        }
                         if (!row_live) {
                             // nothing to store, but the partial tile the producer fetched must be released
                             if (pin) {
@@ -601,7 +622,7 @@ __global__ void __launch_bounds__(256, 1) conv_strip_kernel(const __grid_constan
                             }
                         } else {
                             // bias, depth-to-space, bilinear skip -> staging [3 dy][32 px * 9] -> coalesced stores
-                            if (r > 0 && x < p.W) load_skip_nb(p, w.img, y, x, nb);
+                            if (r > eh && x < p.W) load_skip_nb(p, w.img, y, x, nb);
                             {
                                 const float4* b4 = reinterpret_cast<const float4*>(eg.bias);
                                 #pragma unroll
@@ -622,7 +643,7 @@ __global__ void __launch_bounds__(256, 1) conv_strip_kernel(const __grid_constan
                             const size_t W3 = (size_t)p.W * 3;
                             const size_t orow0 = ((size_t)w.img * p.H * 3 + (size_t)y * 3) * W3 + (size_t)xw * 3;  // in output pixels
                             if (p.out_f32) {
-                                float* sf = reinterpret_cast<float*>(smem + C::OFF_O) + (ew * C::NOUT + (oc % C::NOUT)) * 1024;
+                                float* sf = reinterpret_cast<float*>(smem + C::OFF_O) + (e * C::NOUT + (oc % C::NOUT)) * 1024;
                                 #pragma unroll
                                 for (int dy = 0; dy < 3; ++dy)
                                     #pragma unroll
@@ -643,7 +664,7 @@ __global__ void __launch_bounds__(256, 1) conv_strip_kernel(const __grid_constan
                             if (p.out_u8) {
                                 // alumina data_to_img + to_rgba (main.rs:175): round(clamp(v,0,1)*255), alpha 255
                                 // (the host guarantees exactly one of out_f32 / out_u8, so the tile is shared)
-                                uint32_t* sq = reinterpret_cast<uint32_t*>(smem + C::OFF_O) + (ew * C::NOUT + (oc % C::NOUT)) * 1024;
+                                uint32_t* sq = reinterpret_cast<uint32_t*>(smem + C::OFF_O) + (e * C::NOUT + (oc % C::NOUT)) * 1024;
                                 #pragma unroll
                                 for (int dy = 0; dy < 3; ++dy)
                                     #pragma unroll

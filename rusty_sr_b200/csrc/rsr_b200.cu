@@ -80,8 +80,8 @@ static Layout make_layout(int factor) {
 }
 
 // --------------------------------------------------------------------------- kernel configs
-//                      KH KW  RB NG R NR TPS NBS NPIN NOUT SHUF
-using Cfg0 = ConvCfg<5, 1,  64, 1, 4, 12, 5, 2, 0, 2, false>;  // conv0 on the x-im2col'd input (K = 5 taps x 16)
+//                      KH KW  RB NG R NR TPS NBS NPIN NOUT SHUF NEPI
+using Cfg0 = ConvCfg<5, 1,  64, 1, 4, 12, 5, 2, 0, 2, false, 8>;  // conv0 on the x-im2col'd input (K = 5 taps x 16)
 #ifndef RSR_CFG1_NR
 #define RSR_CFG1_NR 7
 #endif
@@ -95,9 +95,9 @@ using Cfg0 = ConvCfg<5, 1,  64, 1, 4, 12, 5, 2, 0, 2, false>;  // conv0 on the x
 #define RSR_L2PROMO CU_TENSOR_MAP_L2_PROMOTION_L2_256B
 #endif
 using Cfg1 = ConvCfg<5, 5, 128, 3, 2, RSR_CFG1_NR, RSR_CFG1_TPS, RSR_CFG1_NBS, 0, 2, false>;  // f  -> conv1 | conv2 | conv3
-using Cfg2 = ConvCfg<3, 3, 128, 3, 2,  5, 2, 3, 2, 2, false>;  // l1 -> conv5 | conv6 | conv7   (+ P2, P3)
+using Cfg2 = ConvCfg<3, 3, 128, 3, 2,  5, 2, 3, 2, 2, false, 8>;  // l1 -> conv5 | conv6 | conv7   (+ P2, P3)
 using Cfg3 = ConvCfg<3, 3, 128, 2, 2,  5, 2, 3, 3, 2, false>;  // l2 -> conv8 | conv9           (+ P3, E)
-using Cfg4 = ConvCfg<3, 3, 128, 1, 2,  6, 3, 3, 3, 2, true>;   // l3 -> conv10 (+ E) + expand + bilinear skip
+using Cfg4 = ConvCfg<3, 3, 128, 1, 2,  6, 3, 3, 3, 2, true, 8>;  // l3 -> conv10 (+ E) + expand + bilinear skip
 
 enum { K_PACK = 0, K_CONV0, K_F, K_L1, K_L2, K_L3, K_COUNT };
 static const char* kKernelNames[K_COUNT] = {"pack_input", "conv0", "conv1|2|3", "conv5|6|7", "conv8|9",
@@ -459,7 +459,7 @@ static int launch_conv(rsr_ctx* c, ConvParams& p, int kindex) {
     const int grid = (int)std::min<long long>(p.total_rowtiles, c->num_sms);
     p.prof = (c->prof && grid <= 256) ? c->prof + (size_t)kindex * 256 * 16 : nullptr;
     c->prof_grid[kindex] = grid;
-    conv_strip_kernel<C><<<grid, 256, C::SMEM_BYTES, c->stream>>>(p);
+    conv_strip_kernel<C><<<grid, C::NTHREADS, C::SMEM_BYTES, c->stream>>>(p);
     CUDA_TRY(cudaGetLastError());
     c->last_launches++;
     return 0;
@@ -952,7 +952,7 @@ static int conv2d_block(PFN_cuTensorMapEncodeTiled_v12000 enc, int num_sms, cuda
     p.total_rowtiles = (long long)p.n_strips * H;
     const int grid = (int)std::min<long long>(p.total_rowtiles, num_sms);
     CUDA_TRY(cudaFuncSetAttribute(conv_strip_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
-    conv_strip_kernel<C><<<grid, 256, C::SMEM_BYTES, st>>>(p);
+    conv_strip_kernel<C><<<grid, C::NTHREADS, C::SMEM_BYTES, st>>>(p);
     CUDA_TRY(cudaGetLastError());
     return 0;
 }
