@@ -158,7 +158,7 @@ def run_reference(args):
         "e2e": {"value": value, "unit": "Mpix/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
     return 0
 
 
@@ -172,7 +172,7 @@ def run_ours(args):
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if not torch.cuda.is_available():
-        print(json.dumps({"error": "no CUDA device: rusty_sr_b200 has no CPU fallback"}), flush=True)
+        emit({"error": "no CUDA device: rusty_sr_b200 has no CPU fallback"})
         return 2
     torch.cuda.set_device(local)
     if world > 1:
@@ -324,14 +324,29 @@ def run_ours(args):
             "gpu_launches": launches,
             "clocks": clocks,
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
     up.close()
     if world > 1:
         dist.destroy_process_group()
     return 0
 
 
+_OUT = None
+
+
+def emit(obj) -> None:
+    """The one JSON line goes to the process's ORIGINAL stdout; everything else any library prints to fd 1
+    (NCCL's version banner, torchrun chatter) has been diverted to stderr by main()."""
+    (_OUT or sys.stdout).write(json.dumps(obj) + "\n")
+    (_OUT or sys.stdout).flush()
+
+
 def main():
+    global _OUT
+    sys.stdout.flush()
+    _OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)          # from here on fd 1 is stderr: only emit() reaches the real stdout
+    os.environ.setdefault("NCCL_DEBUG", "WARN")
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
