@@ -183,7 +183,8 @@ def run_ours(args):
     sampler = ClockSampler(local) if rank == 0 else None
     if sampler:
         sampler.start()
-    up = R.Upscaler(parameters="imagenet", device=local)
+    plan_flags = {"default": 0, "fused": R.RSR_FLAG_FUSED_MID, "split": R.RSR_FLAG_SPLIT_MID}[args.plan]
+    up = R.Upscaler(parameters="imagenet", device=local, flags=plan_flags)
     stream = torch.cuda.Stream(device=dev)
     up.set_stream(stream.cuda_stream)
 
@@ -225,6 +226,9 @@ def run_ours(args):
             kt_runs.append(up.last_kernel_times_ms())
         for k in kt_runs[0]:
             ktimes[k] = statistics.mean(r[k] for r in kt_runs)
+        fused = up.last_launch_count() == 5      # conv5|6|7 and conv8|9 run as one launch (conv_fused.cuh)
+        if fused:
+            ktimes["conv5|6|7+conv8|9 (fused)"] = ktimes.pop("conv5|6|7") + ktimes.pop("conv8|9")
 
     t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
     if world > 1:
@@ -304,6 +308,8 @@ def run_ours(args):
             "dtype": "bf16x3 split operands, f32 accumulate (fp32-equivalent)", "data": "synthetic",
             "config": {"workload": WORKLOAD, "factor": FACTOR, "weights": "imagenet.rsr",
                        "parallelism": f"image-batch sharding x{world}, no collective",
+                       "launch_plan": ("5 launches/frame: pack, conv0, conv1|2|3, conv5|6|7+conv8|9 fused, conv10+expand"
+                                       if fused else "6 launches/frame: pack, conv0, conv1|2|3, conv5|6|7, conv8|9, conv10+expand"),
                        "l2": f"working set ~1.3 GB/step >> 126 MB L2; input rotates over {N_ROTATE} distinct frames (149 MB)",
                        "io": "value: f32 in/out resident in HBM; e2e: u8 RGB host -> u8 RGBA host (pinned)"},
             "roofline": {"kernel": "conv1|2|3 (conv_strip_kernel<5,5,128,3,2>)", "bound": "tensor",
@@ -352,6 +358,8 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--plan", default="default", choices=["default", "fused", "split"],
+                    help="launch plan of the middle levels (include/rsr_b200.h RSR_FLAG_*_MID); default = library default")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

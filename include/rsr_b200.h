@@ -34,7 +34,14 @@ enum {
 
 /* Flags for rsr_create. */
 enum {
-    RSR_FLAG_NONE = 0
+    RSR_FLAG_NONE = 0,
+    /* Launch plan of the two middle levels of the DAG (network.rs:65-70).  Results agree to fp32 rounding.
+     * FUSED_MID: conv5|6|7 and conv8|9 run as ONE launch that keeps l2 in shared memory and the running
+     *            partial sums in tensor memory (5 launches per call, 768 B/pixel less HBM traffic);
+     * SPLIT_MID: two launches with l2 and the partial sums stored to HBM in between (6 launches per call).
+     * Neither flag: the library default (the RSR_B200_FUSED=0|1 environment variable overrides it). */
+    RSR_FLAG_FUSED_MID = 1,
+    RSR_FLAG_SPLIT_MID = 2
 };
 
 /* graph.num_params() of sr_net(factor, None): 130459 for factor 3 (main.rs:162; layout in
@@ -132,7 +139,8 @@ int rsr_last_launch_count(rsr_ctx* ctx);
  * rsr_kernel_name; negative = run everything; outputs are then not written).  rsr_debug_read_node
  * copies one workspace buffer of the most recent call to the host as f32 [n*h*w][32]:
  * which = 0: activation buffer A (f, later l2), 1: activation buffer B (l1, later l3),
- *         2: partial buffer A (conv2(f), later expand), 3: partial buffer B (l3_conv partial). */
+ *         2: partial buffer A (conv2(f), later expand), 3: partial buffer B (l3_conv partial),
+ *         4: partial buffer C (expand partial of the fused middle launch; there l3 lives in buffer A). */
 int rsr_debug_stop_after(rsr_ctx* ctx, int launch_index);
 int rsr_debug_read_node(rsr_ctx* ctx, int which, float* out, size_t n_pixels);
 /* Per-CTA wait-cycle counters of the conv launches (which mbarrier each warp role waited on, in SM

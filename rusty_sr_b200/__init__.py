@@ -15,12 +15,12 @@ from typing import Optional
 import numpy as np
 
 from . import _lib
-from ._lib import RsrError
+from ._lib import RsrError, RSR_FLAG_FUSED_MID, RSR_FLAG_SPLIT_MID
 from .network import FACTOR, num_params, param_layout
 from .rsr_format import decode_rsr, encode_rsr
 
 __all__ = ["Upscaler", "upscale", "bilinear", "downsample", "conv2d_3x3", "load_builtin_params", "decode_rsr", "encode_rsr", "RsrError",
-           "num_params", "param_layout", "FACTOR", "BUILTIN_PARAMETERS"]
+           "num_params", "param_layout", "FACTOR", "BUILTIN_PARAMETERS", "RSR_FLAG_FUSED_MID", "RSR_FLAG_SPLIT_MID"]
 
 _RES = os.path.join(os.path.dirname(os.path.abspath(__file__)), "res")
 
@@ -45,7 +45,9 @@ class Upscaler:
     main.rs:133-158).  Not thread-safe, like the reference's `&mut Graph`."""
 
     def __init__(self, params: Optional[np.ndarray] = None, parameters: str = "imagenet",
-                 factor: int = FACTOR, device: int = 0):
+                 factor: int = FACTOR, device: int = 0, flags: int = 0):
+        """`flags`: RSR_FLAG_FUSED_MID / RSR_FLAG_SPLIT_MID select the launch plan of the middle levels
+        (include/rsr_b200.h); 0 = library default."""
         if params is None:
             params = load_builtin_params(parameters)
         params = np.ascontiguousarray(params, dtype=np.float32).ravel()
@@ -54,7 +56,7 @@ class Upscaler:
         self.device = device
         self.n_params = int(params.size)
         h = self._L.rsr_create(params.ctypes.data_as(ctypes.POINTER(ctypes.c_float)), params.size,
-                               factor, device, 0)
+                               factor, device, int(flags))
         if not h:
             code = self._L.rsr_last_error_code()
             msg = self._L.rsr_last_error().decode("utf-8", "replace")

@@ -14,6 +14,8 @@ RSR_E_BAD_ARG = -2
 RSR_E_CUDA = -3
 RSR_E_OOM = -4
 RSR_E_UNSUPPORTED = -5
+RSR_FLAG_FUSED_MID = 1   # rsr_create flags (include/rsr_b200.h)
+RSR_FLAG_SPLIT_MID = 2
 
 # every symbol include/rsr_b200.h declares (checked by tests/test_abi.py)
 EXPORTS = (

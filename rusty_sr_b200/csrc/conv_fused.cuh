@@ -1,0 +1,455 @@
+// conv_fused.cuh — two levels of the sr_net DAG in ONE launch, the middle node kept in shared memory.
+//
+// Replaces the two launches `conv5|6|7` and `conv8|9` of conv_strip.cuh (reference src/network.rs:65-70
+// with Bias :51-52 and BeLU :55-56):
+//     l2 = BeLU(conv2(f) + conv5(l1) + l2_bias)                        (network.rs:61,65,51,55)
+//     l3 = BeLU(conv3(f) + conv6(l1) + conv8(l2) + l3_bias)            (network.rs:62,66,69,52,56)
+//     E  = conv7(l1) + conv9(l2)            (partial of `expand`;      network.rs:67,70)
+// Inputs from HBM: l1 (split bf16), P2 = conv2(f), P3 = conv3(f) (fp32, written by the conv1|2|3 launch).
+// Outputs to HBM: l3 (split bf16) and E (fp32).  l2, the updated P3 and the first half of E never leave
+// the SM: 640 B per pixel of HBM traffic instead of 1408 B for the two separate launches.
+//
+// How: a CTA walks down a 124-pixel-wide column strip, one image row per step.
+//   S1(y): tcgen05.mma M=128 N=96 over the 3x3 taps of l1 rows y-1..y+1 -> TMEM slot T[y] = [l2pre | P3acc | Eacc].
+//   E1(y): 4 warps: l2pre (+ P2 tile) -> bias, BeLU, split -> row y of a 3-slot l2 ring in shared memory, written
+//          in exactly the swizzled layout a TMA load would have produced (zero outside the image = Padding::Same).
+//   S2(y): tcgen05.mma N=64 over the taps of l2 rows y-1..y+1, ACCUMULATING onto T[y][32:96] (conv8 onto the
+//          conv6 partial, conv9 onto the conv7 partial) — the partial sums never leave TMEM.
+//   E2(y): 4 more warps: T[y][32:64] (+ P3 tile) -> bias, BeLU, split -> TMA store l3;  T[y][64:96] -> TMA store E.
+// 128 l1 pixels give 126 l2 pixels give 124 output pixels per strip (the M = 128 MMA rows past those are
+// discarded), so a strip recomputes 2 of 126 l2 columns; a work item also recomputes one l2 row above and
+// below its row range.  The MMA warp issues S1 three rows ahead of S2 so that E1 runs under the MMAs.
+//
+// Warp roles (13 warps): 0 l1-row producer (TMA), 1 MMA issuer, 2 TMEM allocator + P2 producer, 3 weight
+// producer (one tap per stage, 5-stage ring), 4-7 E1, 8-11 E2, 12 P3 producer.  All hand-offs are mbarriers
+// and every wait is bounded (ptx.cuh mbar_wait).
+#pragma once
+#include "conv_strip.cuh"
+
+namespace rsr {
+
+struct FusedParams {
+    CUtensorMap tmA;      // l1: rank 4 (64, W, H, NIMG) bf16, box (64, 128, 1, 1), SWIZZLE_128B
+    CUtensorMap tmB1;     // conv5|6|7 weights: rank 2 (64, 9 * 96), box (64, 96)
+    CUtensorMap tmB2;     // conv8|9 weights:   rank 2 (64, 9 * 64), box (64, 64)
+    CUtensorMap tmP2;     // conv2(f): rank 4 (32, W, H, NIMG) fp32, box (32, 128, 1, 1)
+    CUtensorMap tmP3;     // conv3(f): same
+    CUtensorMap tmL3[2];  // l3 out: bf16 box (64, 32, 1, 1) and (64, 28, 1, 1) (last 32-pixel slice of a strip)
+    CUtensorMap tmE[2];   // E out: fp32 box (32, 32, 1, 1) and (32, 28, 1, 1)
+    int W, H, NIMG, n_strips;
+    long long total_rowtiles;   // NIMG * n_strips * H
+    EpiGroup g_l2, g_l3;        // bias / slope of the two activations (kind = EPI_ACT)
+    int* fault;
+};
+
+struct FusedCfg {
+    static constexpr int STRIP = 124;          // output pixels per strip
+    static constexpr int L2W = 126;            // valid l2 pixels per strip row
+    static constexpr int SLOT = 128 * 128;     // one row slot: 128 pixels x 128 B
+    static constexpr int NR1 = 4;              // l1 ring (3-row window + 1 in flight)
+    static constexpr int NR2 = 3;              // l2 ring
+    static constexpr int NB = 5;               // weight stages (one tap each)
+    static constexpr int BST = 96 * 128;       // stage pitch (conv8|9 taps use 64 * 128 of it)
+    static constexpr int NT = 5;               // TMEM row slots of 96 columns
+    static constexpr int TCOLS = 96;
+    static constexpr int LOOKAHEAD = 4;        // S1 rows issued before the first S2 of a work item
+    static constexpr int NTHREADS = 13 * 32;
+    static constexpr int OFF_L2 = NR1 * SLOT;
+    static constexpr int OFF_B = OFF_L2 + NR2 * SLOT;
+    static constexpr int OFF_P2 = OFF_B + NB * BST;
+    static constexpr int OFF_P3 = OFF_P2 + SLOT;
+    static constexpr int OFF_O = OFF_P3 + SLOT;
+    static constexpr int OFF_BAR = OFF_O + 4 * 4096;
+    // a_full/a_empty[NR1] b_full/b_empty[NB] p2_full p2_empty p3_full p3_empty t1_full[NT] l2_full/l2_empty[NR2]
+    // t2_full[NT] t_empty[NT]
+    static constexpr int NBAR = 2 * NR1 + 2 * NB + 4 + NT + 2 * NR2 + NT + NT;
+    static constexpr int SMEM_BYTES = 1024 + OFF_BAR + NBAR * 8 + 16;
+    static_assert(OFF_BAR % 1024 == 0 && BST % 1024 == 0, "1024-byte swizzle atoms");
+    static_assert(SMEM_BYTES <= 232448, "shared memory budget");
+};
+
+struct FItem {
+    int img, x0, y_b, n;
+};
+__device__ __forceinline__ bool fitem_next(const FusedParams& p, long long& cur, long long end, FItem& w) {
+    if (cur >= end) return false;
+    const int col = (int)(cur / p.H);
+    const int y0 = (int)(cur % p.H);
+    const int n = (int)min((long long)(p.H - y0), end - cur);
+    w.img = col / p.n_strips;
+    w.x0 = (col % p.n_strips) * FusedCfg::STRIP;
+    w.y_b = y0;
+    w.n = n;
+    cur += n;
+    return true;
+}
+
+#define FW(bar, par, tag) mbar_wait(bar, par, p.fault, tag)
+
+__global__ void __launch_bounds__(FusedCfg::NTHREADS, 1) conv_fused_mid_kernel(const __grid_constant__ FusedParams p) {
+    using C = FusedCfg;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* sA = smem;
+    uint8_t* sL = smem + C::OFF_L2;
+    uint8_t* sB = smem + C::OFF_B;
+    uint8_t* sP2 = smem + C::OFF_P2;
+    uint8_t* sP3 = smem + C::OFF_P3;
+    uint8_t* sO = smem + C::OFF_O;
+    uint64_t* a_full = reinterpret_cast<uint64_t*>(smem + C::OFF_BAR);
+    uint64_t* a_empty = a_full + C::NR1;
+    uint64_t* b_full = a_empty + C::NR1;
+    uint64_t* b_empty = b_full + C::NB;
+    uint64_t* p2_full = b_empty + C::NB;
+    uint64_t* p2_empty = p2_full + 1;
+    uint64_t* p3_full = p2_empty + 1;
+    uint64_t* p3_empty = p3_full + 1;
+    uint64_t* t1_full = p3_empty + 1;
+    uint64_t* l2_full = t1_full + C::NT;
+    uint64_t* l2_empty = l2_full + C::NR2;
+    uint64_t* t2_full = l2_empty + C::NR2;
+    uint64_t* t_empty = t2_full + C::NT;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(t_empty + C::NT);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < C::NR1; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
+        for (int i = 0; i < C::NB; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
+        mbar_init(p2_full, 1); mbar_init(p2_empty, 4);
+        mbar_init(p3_full, 1); mbar_init(p3_empty, 4);
+        for (int i = 0; i < C::NT; ++i) { mbar_init(&t1_full[i], 1); mbar_init(&t2_full[i], 1); mbar_init(&t_empty[i], 4); }
+        for (int i = 0; i < C::NR2; ++i) { mbar_init(&l2_full[i], 4); mbar_init(&l2_empty[i], 1); }
+        fence_mbar_init();
+        tma_prefetch_desc(&p.tmA);
+        tma_prefetch_desc(&p.tmB1);
+        tma_prefetch_desc(&p.tmB2);
+        tma_prefetch_desc(&p.tmP2);
+        tma_prefetch_desc(&p.tmP3);
+    }
+    if (warp == 2) { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
+
+    long long cur = p.total_rowtiles * (long long)blockIdx.x / gridDim.x;
+    const long long end = p.total_rowtiles * (long long)(blockIdx.x + 1) / gridDim.x;
+    FItem w;
+
+    // Counters shared by convention between the roles (each role keeps its own copy, advanced identically):
+    //   c1 = number of S1 rows so far (all items): T slot c1 % NT, l2 slot c1 % NR2
+    //   a  = number of l1 rows loaded so far:      l1 slot a % NR1
+    // The "full" barrier of use number u of a slot completes phase u, so a consumer waits parity u & 1 and
+    // a producer waits parity (u & 1) ^ 1 of the "empty" barrier (returns at once on a fresh barrier).
+    if (warp == 0) {
+        // ===== l1 row producer: rows y_b-2 .. y_e+1 of the strip, pixels x0-2 .. x0+125 =====
+        uint32_t a = 0;
+        while (fitem_next(p, cur, end, w)) {
+            for (int i = 0; i < w.n + 4; ++i, ++a) {
+                const uint32_t sl = a % C::NR1, par = ((a / C::NR1) & 1) ^ 1;
+                FW(&a_empty[sl], par, 21);
+                if (elect_one()) {
+                    mbar_arrive_expect_tx(&a_full[sl], C::SLOT);
+                    tma_load_4d(sA + sl * C::SLOT, &p.tmA, &a_full[sl], 0, w.x0 - 2, w.y_b - 2 + i, w.img);
+                }
+                __syncwarp();
+            }
+        }
+    } else if (warp == 3) {
+        // ===== weight producer: one tap per stage, in the MMA warp's S1 / S2 order =====
+        uint32_t st = 0, par = 1;
+        auto taps = [&](const CUtensorMap* tm, int ncol) {
+            for (int t = 0; t < 9; ++t) {
+                FW(&b_empty[st], par, 22);
+                if (elect_one()) {
+                    mbar_arrive_expect_tx(&b_full[st], ncol * 128);
+                    tma_load_2d(sB + st * C::BST, tm, &b_full[st], 0, t * ncol);
+                }
+                __syncwarp();
+                if (++st == C::NB) { st = 0; par ^= 1; }
+            }
+        };
+        while (fitem_next(p, cur, end, w)) {
+            // op order of the MMA warp: S1 runs LOOKAHEAD rows ahead of S2
+            const int ns1 = w.n + 2;
+            for (int i1 = 0, r = 0; r < w.n;) {
+                const bool is_s1 = i1 < ns1 && i1 < r + C::LOOKAHEAD;
+                taps(is_s1 ? &p.tmB1 : &p.tmB2, is_s1 ? 96 : 64);
+                if (is_s1) ++i1; else ++r;
+            }
+        }
+    } else if (warp == 2) {
+        // ===== P2 tile producer: one tile per S1 row (pixels x0-1 .. x0+126 of row y_b-1+q) =====
+        uint32_t u = 0;
+        while (fitem_next(p, cur, end, w)) {
+            for (int q = 0; q < w.n + 2; ++q, ++u) {
+                FW(p2_empty, (u & 1) ^ 1, 23);
+                if (elect_one()) {
+                    mbar_arrive_expect_tx(p2_full, C::SLOT);
+                    tma_load_4d(sP2, &p.tmP2, p2_full, 0, w.x0 - 1, w.y_b - 1 + q, w.img);
+                }
+                __syncwarp();
+            }
+        }
+    } else if (warp == 12) {
+        // ===== P3 tile producer: one tile per S2 row (pixels x0 .. x0+127 of row y_b+r) =====
+        uint32_t u = 0;
+        while (fitem_next(p, cur, end, w)) {
+            for (int r = 0; r < w.n; ++r, ++u) {
+                FW(p3_empty, (u & 1) ^ 1, 24);
+                if (elect_one()) {
+                    mbar_arrive_expect_tx(p3_full, C::SLOT);
+                    tma_load_4d(sP3, &p.tmP3, p3_full, 0, w.x0, w.y_b + r, w.img);
+                }
+                __syncwarp();
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer =====
+        constexpr uint32_t HI = (uint32_t)make_sdesc_hi(1024, UMMA_SW_128B);
+        constexpr uint32_t IDESC1 = make_idesc_bf16(128, 96);
+        constexpr uint32_t IDESC2 = make_idesc_bf16(128, 64);
+        constexpr uint32_t LBO = 1u << 16;
+        constexpr uint32_t MID = 64 >> 4;   // encoded offset of the mid plane inside a pixel's 128 B
+        const uint32_t sA_e = (smem_u32(sA) >> 4) | LBO, sL_e = (smem_u32(sL) >> 4) | LBO, sB_e = (smem_u32(sB) >> 4) | LBO;
+        auto desc = [](uint32_t hi, uint32_t lo) { return ((uint64_t)hi << 32) | lo; };
+        uint32_t c1_item = 0, a_item = 0;   // counters at the start of the current item
+        uint32_t a_wait = 0, l2_wait = 0;   // rows already waited for
+        uint32_t c2 = 0;                    // S2 rows so far
+        uint32_t bst = 0, bpar = 0;
+        int n_item = 0;
+
+        // S1(q): l1 rows q..q+2 of the item -> T slot of row q
+        auto s1 = [&](int q) {
+            const uint32_t c = c1_item + q;
+            const uint32_t ts = c % C::NT;
+            FW(&t_empty[ts], ((c / C::NT) & 1) ^ 1, 25);
+            while (a_wait <= a_item + q + 2) {
+                FW(&a_full[a_wait % C::NR1], (a_wait / C::NR1) & 1, 26);
+                ++a_wait;
+            }
+            tc_fence_after();
+            uint32_t arow[3];
+            #pragma unroll
+            for (int ta = 0; ta < 3; ++ta) arow[ta] = sA_e + ((a_item + q + ta) % C::NR1) * (C::SLOT >> 4);
+            const uint32_t d = tmem_base + ts * C::TCOLS;
+            #pragma unroll
+            for (int t = 0; t < 9; ++t) {
+                const int ta = t / 3, tb = t % 3;
+                FW(&b_full[bst], bpar, 27);
+                tc_fence_after();
+                if (elect_one()) {
+                    const uint32_t b_e = sB_e + bst * (C::BST >> 4);
+                    const uint32_t a_e = arow[ta] + tb * (128 >> 4);
+                    #pragma unroll
+                    for (int k = 0; k < 2; ++k) {
+                        umma_f16(d, desc(HI, a_e + 2 * k), desc(HI, b_e + 2 * k), IDESC1, (t | k) != 0 ? 1u : 0u);
+                        umma_f16(d, desc(HI, a_e + MID + 2 * k), desc(HI, b_e + 2 * k), IDESC1, 1);
+                        umma_f16(d, desc(HI, a_e + 2 * k), desc(HI, b_e + MID + 2 * k), IDESC1, 1);
+                    }
+                    if (t == 2) umma_commit(&a_empty[(a_item + q) % C::NR1]);   // top window row is dead
+                    umma_commit(&b_empty[bst]);
+                }
+                __syncwarp();
+                if (++bst == C::NB) { bst = 0; bpar ^= 1; }
+            }
+            if (elect_one()) {
+                umma_commit(&t1_full[ts]);
+                if (q == n_item + 1) {   // last S1 of the item: the rest of its window is dead too
+                    umma_commit(&a_empty[(a_item + q + 1) % C::NR1]);
+                    umma_commit(&a_empty[(a_item + q + 2) % C::NR1]);
+                }
+            }
+            __syncwarp();
+        };
+        // S2(r): l2 rows r..r+2 of the item, accumulated onto columns 32..95 of the T slot of l2 row r+1
+        auto s2 = [&](int r) {
+            const uint32_t ts = (c1_item + r + 1) % C::NT;
+            while (l2_wait <= c1_item + r + 2) {
+                FW(&l2_full[l2_wait % C::NR2], (l2_wait / C::NR2) & 1, 28);
+                ++l2_wait;
+            }
+            tc_fence_after();
+            uint32_t lrow[3];
+            #pragma unroll
+            for (int ta = 0; ta < 3; ++ta) lrow[ta] = sL_e + ((c1_item + r + ta) % C::NR2) * (C::SLOT >> 4);
+            const uint32_t d = tmem_base + ts * C::TCOLS + 32;
+            #pragma unroll
+            for (int t = 0; t < 9; ++t) {
+                const int ta = t / 3, tb = t % 3;
+                FW(&b_full[bst], bpar, 29);
+                tc_fence_after();
+                if (elect_one()) {
+                    const uint32_t b_e = sB_e + bst * (C::BST >> 4);
+                    const uint32_t a_e = lrow[ta] + tb * (128 >> 4);
+                    #pragma unroll
+                    for (int k = 0; k < 2; ++k) {
+                        umma_f16(d, desc(HI, a_e + 2 * k), desc(HI, b_e + 2 * k), IDESC2, 1);
+                        umma_f16(d, desc(HI, a_e + MID + 2 * k), desc(HI, b_e + 2 * k), IDESC2, 1);
+                        umma_f16(d, desc(HI, a_e + 2 * k), desc(HI, b_e + MID + 2 * k), IDESC2, 1);
+                    }
+                    if (t == 2) umma_commit(&l2_empty[(c1_item + r) % C::NR2]);
+                    umma_commit(&b_empty[bst]);
+                }
+                __syncwarp();
+                if (++bst == C::NB) { bst = 0; bpar ^= 1; }
+            }
+            if (elect_one()) {
+                umma_commit(&t2_full[c2 % C::NT]);
+                if (r == n_item - 1) {
+                    umma_commit(&l2_empty[(c1_item + r + 1) % C::NR2]);
+                    umma_commit(&l2_empty[(c1_item + r + 2) % C::NR2]);
+                }
+            }
+            __syncwarp();
+            ++c2;
+        };
+        while (fitem_next(p, cur, end, w)) {
+            n_item = w.n;
+            // S1 runs LOOKAHEAD rows ahead of S2: S1(0..3) S2(0) S1(4) S2(1) ... ; all n+2 S1 rows precede S2(n-1)
+            const int ns1 = w.n + 2;
+            for (int i1 = 0, r = 0; r < w.n;) {
+                if (i1 < ns1 && i1 < r + C::LOOKAHEAD) s1(i1++);
+                else s2(r++);
+            }
+            c1_item += ns1;
+            a_item += w.n + 4;
+        }
+    } else if (warp >= 4 && warp < 8) {
+        // ===== E1: l2pre (+ P2) -> l2 row in the shared-memory ring =====
+        const int ew = warp - 4;
+        const int m = ew * 32 + lane;            // MMA row = l2 ring pixel index
+        const uint32_t sL_u = smem_u32(sL), sP2_u = smem_u32(sP2);
+        uint32_t c = 0;
+        while (fitem_next(p, cur, end, w)) {
+            for (int q = 0; q < w.n + 2; ++q, ++c) {
+                const uint32_t ts = c % C::NT, ls = c % C::NR2;
+                const int y = w.y_b - 1 + q, px = w.x0 - 1 + m;
+                FW(&t1_full[ts], (c / C::NT) & 1, 30);
+                tc_fence_after();
+                uint32_t raw[32];
+                tmem_ld_32x32(tmem_base + ((uint32_t)(ew * 32) << 16) + ts * C::TCOLS, raw);
+                tmem_ld_wait();
+                float v[32];
+                #pragma unroll
+                for (int k = 0; k < 32; ++k) v[k] = __uint_as_float(raw[k]);
+                FW(p2_full, c & 1, 31);
+                epi_add_partial_tile(v, sP2_u, m);
+                __syncwarp();
+                if (lane == 0) mbar_arrive(p2_empty);
+                {
+                    const float4* b4 = reinterpret_cast<const float4*>(p.g_l2.bias);
+                    const float4* s4 = reinterpret_cast<const float4*>(p.g_l2.slope);
+                    #pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const float4 b = __ldg(b4 + i), s = __ldg(s4 + i);
+                        v[4 * i + 0] = belu(v[4 * i + 0] + b.x, s.x); v[4 * i + 1] = belu(v[4 * i + 1] + b.y, s.y);
+                        v[4 * i + 2] = belu(v[4 * i + 2] + b.z, s.z); v[4 * i + 3] = belu(v[4 * i + 3] + b.w, s.w);
+                    }
+                }
+                // Padding::Same of conv8 / conv9: l2 is ZERO outside the image (not BeLU(bias)); lanes past the
+                // strip's 126 valid l2 pixels hold garbage accumulators and are zeroed too
+                const bool valid = y >= 0 && y < p.H && px >= 0 && px < p.W && m < C::L2W;
+                uint32_t hi[16], mid[16];
+                #pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    split_pair(v[2 * i], v[2 * i + 1], hi[i], mid[i]);
+                    if (!valid) { hi[i] = 0u; mid[i] = 0u; }
+                }
+                // the MMAs that read the previous occupant of this ring slot must have completed
+                FW(&l2_empty[ls], ((c / C::NR2) & 1) ^ 1, 32);
+                const uint32_t row = sL_u + ls * C::SLOT + m * 128;
+                const uint32_t sw = m & 7;
+                #pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    st_shared_v4(row + ((j ^ sw) << 4), hi[4 * j], hi[4 * j + 1], hi[4 * j + 2], hi[4 * j + 3]);
+                    st_shared_v4(row + (((4 + j) ^ sw) << 4), mid[4 * j], mid[4 * j + 1], mid[4 * j + 2], mid[4 * j + 3]);
+                }
+                fence_proxy_async_smem();   // generic-proxy writes -> visible to the tensor core's async-proxy reads
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) {
+                    mbar_arrive(&l2_full[ls]);
+                    // halo rows have no S2 / E2: their T slot is released here
+                    if (q == 0 || q == w.n + 1) mbar_arrive(&t_empty[ts]);
+                }
+            }
+        }
+    } else if (warp >= 8 && warp < 12) {
+        // ===== E2: T[32:64] (+ P3) -> l3;  T[64:96] -> E =====
+        const int ew = warp - 8;
+        const uint32_t stage = smem_u32(sO) + ew * 4096;
+        const uint32_t sP3_u = smem_u32(sP3);
+        const int bx = ew == 3 ? 1 : 0;   // the last 32-pixel slice of a strip holds 28 pixels
+        uint32_t c1_item = 0, c2 = 0;
+        while (fitem_next(p, cur, end, w)) {
+            const int xw = w.x0 + ew * 32;
+            const bool live = xw < p.W;   // warp-uniform
+            for (int r = 0; r < w.n; ++r, ++c2) {
+                const uint32_t ts = (c1_item + r + 1) % C::NT;
+                const int y = w.y_b + r;
+                FW(&t2_full[c2 % C::NT], (c2 / C::NT) & 1, 33);
+                tc_fence_after();
+                const uint32_t trow = tmem_base + ((uint32_t)(ew * 32) << 16) + ts * C::TCOLS;
+                uint32_t raw[32];
+                float v[32];
+                // --- l3 ---
+                tmem_ld_32x32(trow + 32, raw);
+                tmem_ld_wait();
+                #pragma unroll
+                for (int k = 0; k < 32; ++k) v[k] = __uint_as_float(raw[k]);
+                FW(p3_full, c2 & 1, 34);
+                epi_add_partial_tile(v, sP3_u, ew * 32 + lane);
+                __syncwarp();
+                if (lane == 0) mbar_arrive(p3_empty);
+                if (live) {
+                    if (elect_one()) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                    __syncwarp();
+                    epi_split_to_stage(p.g_l3, v, stage, lane);
+                    fence_proxy_async_smem();
+                    __syncwarp();
+                    if (elect_one()) {
+                        asm volatile(
+                            "cp.async.bulk.tensor.4d.global.shared::cta.tile.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+                            ::"l"(reinterpret_cast<uint64_t>(&p.tmL3[bx])), "r"(stage), "r"(0), "r"(xw), "r"(y), "r"(w.img)
+                            : "memory");
+                        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                    }
+                }
+                // --- E ---
+                tmem_ld_32x32(trow + 64, raw);
+                tmem_ld_wait();
+                #pragma unroll
+                for (int k = 0; k < 32; ++k) v[k] = __uint_as_float(raw[k]);
+                if (live) {
+                    if (elect_one()) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                    __syncwarp();
+                    epi_raw_to_stage(v, stage, lane);
+                    fence_proxy_async_smem();
+                    __syncwarp();
+                    if (elect_one()) {
+                        asm volatile(
+                            "cp.async.bulk.tensor.4d.global.shared::cta.tile.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+                            ::"l"(reinterpret_cast<uint64_t>(&p.tmE[bx])), "r"(stage), "r"(0), "r"(xw), "r"(y), "r"(w.img)
+                            : "memory");
+                        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                    }
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&t_empty[ts]);
+            }
+            c1_item += w.n + 2;
+        }
+        if (elect_one()) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) tmem_dealloc(tmem_base, 512);
+}
+
+#undef FW
+
+}  // namespace rsr

@@ -58,26 +58,28 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 
 // A wait that can never hang the GPU: after ~seconds of spinning it records the barrier id in
 // *g_fault (if given) and traps, which surfaces as a CUDA error on the host instead of a stuck
-// box.  `tag` identifies the waiting site.
+// box.  `tag` identifies the waiting site.  The reporting path is a cold out-of-line function so
+// that the many inlined wait sites stay small (ptxas time grows steeply with function size).
+__device__ __noinline__ void mbar_timeout(uint64_t* bar, uint32_t parity, int* g_fault, int tag) {
+    if (g_fault) {   // lives in mapped host memory (readable after the trap): plain stores + system fence
+        volatile int* f = reinterpret_cast<volatile int*>(g_fault);
+        f[0] = 0x1000 + tag;
+        if ((threadIdx.x & 31) == 0) {   // per-warp record: which barrier every warp role is stuck on
+            volatile int* r = f + 4 + (threadIdx.x >> 5) * 4;
+            r[0] = tag; r[1] = (int)blockIdx.x; r[2] = (int)parity; r[3] = (int)(smem_u32(bar) & 0xffff);
+        }
+        __threadfence_system();
+        // give the other warps of this CTA time to time out and log too before the context dies
+        for (int i = 0; i < 2000; ++i) __nanosleep(1000000);
+    }
+    __trap();
+}
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int* g_fault = nullptr,
                                           int tag = 0) {
     if (mbar_try_wait(bar, parity)) return;
     uint32_t spins = 0;
     while (!mbar_try_wait(bar, parity)) {
-        if (++spins > (1u << 24)) {  // each failed try_wait already sleeps a HW-defined interval
-            if (g_fault) {   // lives in mapped host memory (readable after the trap): plain stores + system fence
-                volatile int* f = reinterpret_cast<volatile int*>(g_fault);
-                f[0] = 0x1000 + tag;
-                if ((threadIdx.x & 31) == 0) {   // per-warp record: which barrier every warp role is stuck on
-                    volatile int* r = f + 4 + (threadIdx.x >> 5) * 4;
-                    r[0] = tag; r[1] = (int)blockIdx.x; r[2] = (int)parity; r[3] = (int)(smem_u32(bar) & 0xffff);
-                }
-                __threadfence_system();
-                // give the other warps of this CTA time to time out and log too before the context dies
-                for (int i = 0; i < 2000; ++i) __nanosleep(1000000);
-            }
-            __trap();
-        }
+        if (++spins > (1u << 24)) mbar_timeout(bar, parity, g_fault, tag);   // each failed try_wait already sleeps a HW-defined interval
     }
 }
 

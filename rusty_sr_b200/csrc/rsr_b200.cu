@@ -19,6 +19,7 @@
 
 #include "../../include/rsr_b200.h"
 #include "conv_strip.cuh"
+#include "conv_fused.cuh"
 
 using namespace rsr;
 
@@ -99,6 +100,9 @@ using Cfg2 = ConvCfg<3, 3, 128, 3, 2,  5, 2, 3, 2, 2, false, 8>;  // l1 -> conv5
 using Cfg3 = ConvCfg<3, 3, 128, 2, 2,  5, 2, 3, 3, 2, false>;  // l2 -> conv8 | conv9           (+ P3, E)
 using Cfg4 = ConvCfg<3, 3, 128, 1, 2,  6, 3, 3, 3, 2, true, 8>;  // l3 -> conv10 (+ E) + expand + bilinear skip
 
+#ifndef RSR_DEFAULT_FUSED_MID
+#define RSR_DEFAULT_FUSED_MID 0
+#endif
 enum { K_PACK = 0, K_CONV0, K_F, K_L1, K_L2, K_L3, K_COUNT };
 static const char* kKernelNames[K_COUNT] = {"pack_input", "conv0", "conv1|2|3", "conv5|6|7", "conv8|9",
                                             "conv10+expand+skip"};
@@ -164,7 +168,8 @@ struct rsr_ctx {
     __nv_bfloat16 *w0 = nullptr, *w1 = nullptr, *w2 = nullptr, *w3 = nullptr, *w4 = nullptr;
     float* vecs = nullptr;  // 9 x 32 floats: f_bias f_activ l1_bias l1_activ l2_bias l2_activ l3_bias l3_activ expand_bias
     // workspace
-    DevBuf xcol, xf4, actA, actB, partA, partB, out_f32, out_u8, in_stage;
+    DevBuf xcol, xf4, actA, actB, partA, partB, partC, out_f32, out_u8, in_stage;
+    bool fused_mid = false;     // conv5|6|7 + conv8|9 in one launch (conv_fused.cuh); RSR_FLAG_FUSED_MID
     int* fault = nullptr;       // device alias of fault_host (mapped pinned memory: readable after a kernel trap)
     int* fault_host = nullptr;  // [0] = code, [4 + 4*warp ..] = which barrier each warp role was stuck on
     cudaEvent_t ev[K_COUNT + 1] = {};
@@ -246,7 +251,7 @@ extern "C" void rsr_destroy(rsr_ctx* c) {
     cudaFree(c->vecs); cudaFree(c->prof);
     if (c->fault_host) cudaFreeHost(c->fault_host);
     release(c->xcol); release(c->xf4); release(c->actA); release(c->actB); release(c->partA);
-    release(c->partB); release(c->out_f32); release(c->out_u8); release(c->in_stage);
+    release(c->partB); release(c->partC); release(c->out_f32); release(c->out_u8); release(c->in_stage);
     for (auto& e : c->ev) if (e) cudaEventDestroy(e);
     for (auto& sl : c->slot) {
         release(sl.in); release(sl.out);
@@ -347,11 +352,11 @@ static int create_impl(rsr_ctx* c, const float* params) {
     CUDA_TRY(cudaFuncSetAttribute(conv_strip_kernel<Cfg2>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg2::SMEM_BYTES));
     CUDA_TRY(cudaFuncSetAttribute(conv_strip_kernel<Cfg3>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg3::SMEM_BYTES));
     CUDA_TRY(cudaFuncSetAttribute(conv_strip_kernel<Cfg4>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg4::SMEM_BYTES));
+    CUDA_TRY(cudaFuncSetAttribute(conv_fused_mid_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FusedCfg::SMEM_BYTES));
     return 0;
 }
 
 extern "C" rsr_ctx* rsr_create(const float* params, size_t n_params, int factor, int device, int flags) {
-    (void)flags;
     g_err.clear();
     g_err_code = 0;
     if (!params) { fail(RSR_E_BAD_ARG, "params is null"); return nullptr; }
@@ -380,6 +385,15 @@ extern "C" rsr_ctx* rsr_create(const float* params, size_t n_params, int factor,
     c->device = device;
     c->factor = factor;
     c->L = L;
+    {
+        // fused middle launch: explicit flag wins, then the RSR_B200_FUSED environment variable (A/B runs),
+        // then the build default
+        bool fused = RSR_DEFAULT_FUSED_MID != 0;
+        if (const char* e = getenv("RSR_B200_FUSED")) fused = e[0] == '1';
+        if (flags & RSR_FLAG_FUSED_MID) fused = true;
+        if (flags & RSR_FLAG_SPLIT_MID) fused = false;
+        c->fused_mid = fused;
+    }
     if (create_impl(c, params) != 0) {
         const std::string keep = g_err;
         const int code = g_err_code;
@@ -486,7 +500,7 @@ static int forward_device(rsr_ctx* c, const void* d_in, bool u8, int in_ch, int 
     __nv_bfloat16* f_act = (__nv_bfloat16*)c->actA.p;   // f, later l2
     __nv_bfloat16* l1_act = (__nv_bfloat16*)c->actB.p;  // l1, later l3
     __nv_bfloat16* l2_act = f_act;
-    __nv_bfloat16* l3_act = l1_act;
+    __nv_bfloat16* l3_act = l1_act;                     // (the fused middle launch puts l3 into f's buffer instead)
     float* P2 = (float*)c->partA.p;  // conv2(f): fp32 partial of l2_conv; later E (expand partial)
     float* P3 = (float*)c->partB.p;  // conv3(f) (+conv6(l1)): fp32 partial of l3_conv, updated in place
     float* E = P2;                   // conv7(l1) (+conv9(l2)), updated in place (aliasing)
@@ -537,36 +551,69 @@ static int forward_device(rsr_ctx* c, const void* d_in, bool u8, int in_ch, int 
     CUDA_TRY(cudaEventRecord(c->ev[3], c->stream));
     if (c->stop_after == 2) return 0;
 
-    // l1 -> l2 = BeLU(P2 + conv5(l1) + l2_bias); P3 += conv6(l1); E = conv7(l1)   :65-67,51,55
-    // (l2 overwrites f, E overwrites P2: both are dead; a thread block only overwrites pixels whose
-    //  partial tile it has already consumed — see DESIGN.md "aliasing")
-    if (int rc = in_map(&p.tmA, l1_act, Cfg2::BOXW)) return rc;
-    if (int rc = make_map_w(c, &p.tmB, c->w2, 64, 9 * 96, Cfg2::TPS * 96)) return rc;
-    if (int rc = part_map(&p.tmPin[0], P2, 128)) return rc;
-    if (int rc = part_map(&p.tmPin[1], P3, 128)) return rc;
-    if (int rc = in_map(&p.tmOut[0], l2_act, 32)) return rc;
-    if (int rc = part_map(&p.tmOut[1], P3, 32)) return rc;
-    if (int rc = part_map(&p.tmOut[2], E, 32)) return rc;
-    p.grp[0] = EpiGroup{EPI_ACT, 1, l2_bias, l2_slope, 0, 0};
-    p.grp[1] = EpiGroup{EPI_RAW, 1, nullptr, nullptr, 0, 0};
-    p.grp[2] = EpiGroup{EPI_RAW, 0, nullptr, nullptr, 0, 0};
-    if (int rc = launch_conv<Cfg2>(c, p, 3)) return rc;
-    CUDA_TRY(cudaEventRecord(c->ev[4], c->stream));
-    if (c->stop_after == 3) return 0;
+    if (c->fused_mid) {
+        // l1, P2, P3 -> l3, E in one launch; l2 lives in shared memory only (conv_fused.cuh)   :65-70,51-52,55-56
+        // l3 goes to the buffer of the (dead) f; E to a buffer of its own: the fused launch reads P2 rows of
+        // neighbouring work items (l2 halo rows), so E may not overwrite P2 here.
+        if (int rc = ensure(c->partC, npx * 128)) return rc;
+        l3_act = f_act;
+        E = (float*)c->partC.p;
+        FusedParams q{};
+        q.W = w; q.H = h; q.NIMG = n; q.fault = c->fault;
+        q.n_strips = (w + FusedCfg::STRIP - 1) / FusedCfg::STRIP;
+        q.total_rowtiles = (long long)n * q.n_strips * h;
+        if (int rc = in_map(&q.tmA, l1_act, 128)) return rc;
+        if (int rc = make_map_w(c, &q.tmB1, c->w2, 64, 9 * 96, 96)) return rc;
+        if (int rc = make_map_w(c, &q.tmB2, c->w3, 64, 9 * 64, 64)) return rc;
+        if (int rc = part_map(&q.tmP2, P2, 128)) return rc;
+        if (int rc = part_map(&q.tmP3, P3, 128)) return rc;
+        if (int rc = in_map(&q.tmL3[0], l3_act, 32)) return rc;
+        if (int rc = in_map(&q.tmL3[1], l3_act, 28)) return rc;
+        if (int rc = part_map(&q.tmE[0], E, 32)) return rc;
+        if (int rc = part_map(&q.tmE[1], E, 28)) return rc;
+        q.g_l2 = EpiGroup{EPI_ACT, 1, l2_bias, l2_slope, 0, 0};
+        q.g_l3 = EpiGroup{EPI_ACT, 1, l3_bias, l3_slope, 0, 0};
+        const int grid = (int)std::min<long long>(q.total_rowtiles, c->num_sms);
+        conv_fused_mid_kernel<<<grid, FusedCfg::NTHREADS, FusedCfg::SMEM_BYTES, c->stream>>>(q);
+        CUDA_TRY(cudaGetLastError());
+        c->last_launches++;
+        // reported in the conv5|6|7 slot of rsr_last_kernel_times; the conv8|9 slot then reads ~0
+        CUDA_TRY(cudaEventRecord(c->ev[4], c->stream));
+        CUDA_TRY(cudaEventRecord(c->ev[5], c->stream));
+        if (c->stop_after == 3 || c->stop_after == 4) return 0;
+    } else {
+        // l1 -> l2 = BeLU(P2 + conv5(l1) + l2_bias); P3 += conv6(l1); E = conv7(l1)   :65-67,51,55
+        // (l2 overwrites f, E overwrites P2: both are dead; a thread block only overwrites pixels whose
+        //  partial tile it has already consumed — see DESIGN.md "aliasing")
+        if (int rc = in_map(&p.tmA, l1_act, Cfg2::BOXW)) return rc;
+        if (int rc = make_map_w(c, &p.tmB, c->w2, 64, 9 * 96, Cfg2::TPS * 96)) return rc;
+        if (int rc = part_map(&p.tmPin[0], P2, 128)) return rc;
+        if (int rc = part_map(&p.tmPin[1], P3, 128)) return rc;
+        if (int rc = in_map(&p.tmOut[0], l2_act, 32)) return rc;
+        if (int rc = part_map(&p.tmOut[1], P3, 32)) return rc;
+        if (int rc = part_map(&p.tmOut[2], E, 32)) return rc;
+        p.grp[0] = EpiGroup{EPI_ACT, 1, l2_bias, l2_slope, 0, 0};
+        p.grp[1] = EpiGroup{EPI_RAW, 1, nullptr, nullptr, 0, 0};
+        p.grp[2] = EpiGroup{EPI_RAW, 0, nullptr, nullptr, 0, 0};
+        if (int rc = launch_conv<Cfg2>(c, p, 3)) return rc;
+        CUDA_TRY(cudaEventRecord(c->ev[4], c->stream));
+        if (c->stop_after == 3) return 0;
 
-    // l2 -> l3 = BeLU(P3 + conv8(l2) + l3_bias); E += conv9(l2)                  :69-70,52,56
-    if (int rc = in_map(&p.tmA, l2_act, Cfg3::BOXW)) return rc;
-    if (int rc = make_map_w(c, &p.tmB, c->w3, 64, 9 * 64, Cfg3::TPS * 64)) return rc;
-    if (int rc = part_map(&p.tmPin[0], P3, 128)) return rc;
-    if (int rc = part_map(&p.tmPin[1], E, 128)) return rc;
-    if (int rc = in_map(&p.tmOut[0], l3_act, 32)) return rc;
-    if (int rc = part_map(&p.tmOut[1], E, 32)) return rc;
-    p.grp[0] = EpiGroup{EPI_ACT, 1, l3_bias, l3_slope, 0, 0};
-    p.grp[1] = EpiGroup{EPI_RAW, 1, nullptr, nullptr, 0, 0};
-    p.grp[2] = none;
-    if (int rc = launch_conv<Cfg3>(c, p, 4)) return rc;
-    CUDA_TRY(cudaEventRecord(c->ev[5], c->stream));
-    if (c->stop_after == 4) return 0;
+        // l2 -> l3 = BeLU(P3 + conv8(l2) + l3_bias); E += conv9(l2)                  :69-70,52,56
+        if (int rc = in_map(&p.tmA, l2_act, Cfg3::BOXW)) return rc;
+        if (int rc = make_map_w(c, &p.tmB, c->w3, 64, 9 * 64, Cfg3::TPS * 64)) return rc;
+        if (int rc = part_map(&p.tmPin[0], P3, 128)) return rc;
+        if (int rc = part_map(&p.tmPin[1], E, 128)) return rc;
+        if (int rc = in_map(&p.tmOut[0], l3_act, 32)) return rc;
+        if (int rc = part_map(&p.tmOut[1], E, 32)) return rc;
+        p.grp[0] = EpiGroup{EPI_ACT, 1, l3_bias, l3_slope, 0, 0};
+        p.grp[1] = EpiGroup{EPI_RAW, 1, nullptr, nullptr, 0, 0};
+        p.grp[2] = none;
+        if (int rc = launch_conv<Cfg3>(c, p, 4)) return rc;
+        CUDA_TRY(cudaEventRecord(c->ev[5], c->stream));
+        if (c->stop_after == 4) return 0;
+
+    }
 
     // l3 -> output = Expand(E + conv10(l3) + expand_bias) + LinearInterp(x)          :72,38-39,27
     if (int rc = in_map(&p.tmA, l3_act, Cfg4::BOXW)) return rc;
@@ -728,7 +775,8 @@ extern "C" int rsr_debug_stop_after(rsr_ctx* c, int k) {
 extern "C" int rsr_debug_read_node(rsr_ctx* c, int which, float* out, size_t npx) {
     if (!c || !out) return fail(RSR_E_BAD_ARG, "null argument");
     if (int rc = rsr_synchronize(c)) return rc;
-    DevBuf* b = which == 0 ? &c->actA : which == 1 ? &c->actB : which == 2 ? &c->partA : which == 3 ? &c->partB : nullptr;
+    DevBuf* b = which == 0 ? &c->actA : which == 1 ? &c->actB : which == 2 ? &c->partA : which == 3 ? &c->partB
+              : which == 4 ? &c->partC : nullptr;
     if (!b || !b->p || b->cap < npx * 128) return fail(RSR_E_BAD_ARG, "node %d not available for %zu pixels", which, npx);
     if (which >= 2) {
         CUDA_TRY(cudaMemcpy(out, b->p, npx * 128, cudaMemcpyDeviceToHost));

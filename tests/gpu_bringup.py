@@ -61,6 +61,41 @@ def stage_check(params, x, label):
     return ok and err.max() < 1e-3
 
 
+def fused_check(params, x, label):
+    """The fused middle launch (conv_fused.cuh, RSR_FLAG_FUSED_MID): l3 and the output against the oracle,
+    and the output against the split launch plan."""
+    H, W = x.shape[:2]
+    ref, taps = O.forward(params, x, 3, np.float64, taps=True)
+    try:
+        up = R.Upscaler(params, flags=R.RSR_FLAG_FUSED_MID)
+        up.debug_stop_after(3)
+        up.forward(x)
+        l3 = up.debug_read_node(0, H * W).reshape(H, W, 32)
+        err = np.abs(l3 - taps["l3_activ"])
+        print(f"[fused {label}] l3_activ  max|err| = {err.max():.3e} worst at {np.unravel_index(err.argmax(), err.shape)}")
+        if not err.max() < 1e-3:
+            bad = err.max(axis=2) > 1e-3
+            ys, xs = np.nonzero(bad)
+            print(f"    bad pixels: {bad.sum()} of {bad.size}; y {ys.min()}..{ys.max()} x {xs.min()}..{xs.max()};"
+                  f" bad columns mod 124: {sorted(set((xs % 124).tolist()))[:20]}")
+        up.debug_stop_after(-1)
+        out = up.forward(x)
+        launches = up.last_launch_count()
+        times = up.last_kernel_times_ms()
+        up.close()
+        split = R.Upscaler(params, flags=R.RSR_FLAG_SPLIT_MID)
+        out_s = split.forward(x)
+        split.close()
+    except Exception as e:  # noqa
+        print(f"[fused {label}] EXCEPTION {e}")
+        return False
+    e_out = float(np.abs(out - ref).max())
+    e_split = float(np.abs(out - out_s).max())
+    print(f"[fused {label}] OUTPUT max|err| vs oracle = {e_out:.3e}, vs split plan = {e_split:.3e}; launches {launches}")
+    print(f"[fused {label}] kernel ms: {times}")
+    return bool(err.max() < 1e-3 and e_out < 1e-3 and e_split < 1e-4 and launches == 5)
+
+
 def main():
     P = {k: R.load_builtin_params(k) for k in R.BUILTIN_PARAMETERS}
     print(R._lib.load().rsr_version().decode())
@@ -71,6 +106,17 @@ def main():
     ok &= stage_check(P["imagenetlinear"], noise_image(7, 5, 6), "noise 5x7")
     ok &= stage_check(P["imagenet"], noise_image(1, 1, 7), "noise 1x1")
     print("BRINGUP", "PASS" if ok else "FAIL")
+    fok = True
+    for prm, x, label in ((P["anime"], O.img_to_data(load_png("cartoon_lr")), "cartoon 84x120"),
+                          (P["imagenet"], noise_image(40, 300, 5), "noise 300x40"),
+                          (P["imagenetlinear"], noise_image(7, 5, 6), "noise 5x7"),
+                          (P["imagenet"], noise_image(1, 1, 7), "noise 1x1"),
+                          (P["imagenet"], noise_image(300, 125, 8), "noise 125x300"),
+                          (P["imagenet"], O.img_to_data(load_png("butterfly_lr")), "butterfly 256x171")):
+        fok &= fused_check(prm, x, label)
+        if not fok:
+            break
+    print("FUSED_BRINGUP", "PASS" if fok else "FAIL")
     return 0 if ok else 1
 
 

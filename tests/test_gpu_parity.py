@@ -201,7 +201,8 @@ def test_error_paths(R, ups):
 def test_native_launches_are_counted(ups):
     u = ups["imagenet"]
     u.forward(noise_image(32, 32, 1))
-    assert u.last_launch_count() == 6
+    assert u.last_launch_count() in (5, 6)   # fused / split plan of the middle levels
     t = u.last_kernel_times_ms()
     assert list(t) == ["pack_input", "conv0", "conv1|2|3", "conv5|6|7", "conv8|9", "conv10+expand+skip"]
-    assert all(v > 0 for v in t.values())
+    # (the fused plan reports its middle launch in the conv5|6|7 slot; the conv8|9 slot is then ~0)
+    assert all(v > 0 for k, v in t.items() if not (k == "conv8|9" and u.last_launch_count() == 5))
