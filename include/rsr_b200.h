@@ -140,11 +140,17 @@ int rsr_last_launch_count(rsr_ctx* ctx);
  * copies one workspace buffer of the most recent call to the host as f32 [n*h*w][32]:
  * which = 0: activation buffer A (f, later l2), 1: activation buffer B (l1, later l3),
  *         2: partial buffer A (conv2(f), later expand), 3: partial buffer B (l3_conv partial),
- *         4: partial buffer C (expand partial of the fused middle launch; there l3 lives in buffer A). */
+ *         4: partial buffer C (expand partial of the fused middle launch; there l3 lives in buffer A),
+ *         5, 6: debug dumps of the fused middle launch (rsr_debug_fused). */
 int rsr_debug_stop_after(rsr_ctx* ctx, int launch_index);
 int rsr_debug_read_node(rsr_ctx* ctx, int which, float* out, size_t n_pixels);
 /* Per-CTA wait-cycle counters of the conv launches (which mbarrier each warp role waited on, in SM
  * cycles): enable, run a call, then read [grid][16] rows for launch index 1..5; returns the grid. */
+/* Fused middle launch: flags bit 0 = skip the second-level MMAs, bit 1 = dump l2 (read_node which = 5) and the raw
+ * accumulator columns conv6(l1)+conv8(l2) (which = 6) as f32 [n*h*w][32], bit 2 = MMA-warp wait-cycle counters,
+ * read as [grid][8] rows (t_empty, a_full, b_full S1, l2_full, b_full S2, -, -, total cycles). */
+int rsr_debug_fused(rsr_ctx* ctx, int flags);
+int rsr_debug_read_fused_profile(rsr_ctx* ctx, long long* out, int cap_rows);
 int rsr_debug_profile(rsr_ctx* ctx, int enable);
 int rsr_debug_read_profile(rsr_ctx* ctx, int launch_index, long long* out, int cap_rows);
 

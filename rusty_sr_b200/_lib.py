@@ -24,7 +24,7 @@ EXPORTS = (
     "rsr_upscale_device_u8", "rsr_synchronize", "rsr_submit_u8", "rsr_submit_f32", "rsr_wait", "rsr_wait_all", "rsr_upscale_band_f32", "rsr_set_stream",
     "rsr_last_kernel_times", "rsr_kernel_name", "rsr_last_launch_count", "rsr_last_error",
     "rsr_last_error_code", "rsr_version", "rsr_debug_stop_after", "rsr_debug_read_node",
-    "rsr_debug_profile", "rsr_debug_read_profile",
+    "rsr_debug_profile", "rsr_debug_read_profile", "rsr_debug_fused", "rsr_debug_read_fused_profile",
     "rsr_bilinear_f32", "rsr_bilinear_u8", "rsr_downsample_f32", "rsr_downsample_u8", "rsr_conv2d_3x3_f32",
 )
 
@@ -85,6 +85,10 @@ def load() -> ctypes.CDLL:
     L.rsr_debug_stop_after.restype = ci
     L.rsr_debug_read_node.argtypes = [vp, ci, vp, ctypes.c_size_t]
     L.rsr_debug_read_node.restype = ci
+    L.rsr_debug_fused.argtypes = [vp, ci]
+    L.rsr_debug_fused.restype = ci
+    L.rsr_debug_read_fused_profile.argtypes = [vp, vp, ci]
+    L.rsr_debug_read_fused_profile.restype = ci
     L.rsr_debug_profile.argtypes = [vp, ci]
     L.rsr_debug_profile.restype = ci
     L.rsr_debug_read_profile.argtypes = [vp, ci, vp, ci]

@@ -16,9 +16,12 @@
 //   S2(y): tcgen05.mma N=64 over the taps of l2 rows y-1..y+1, ACCUMULATING onto T[y][32:96] (conv8 onto the
 //          conv6 partial, conv9 onto the conv7 partial) — the partial sums never leave TMEM.
 //   E2(y): 4 more warps: T[y][32:64] (+ P3 tile) -> bias, BeLU, split -> TMA store l3;  T[y][64:96] -> TMA store E.
-// 128 l1 pixels give 126 l2 pixels give 124 output pixels per strip (the M = 128 MMA rows past those are
-// discarded), so a strip recomputes 2 of 126 l2 columns; a work item also recomputes one l2 row above and
-// below its row range.  The MMA warp issues S1 three rows ahead of S2 so that E1 runs under the MMAs.
+// 128 l1 pixels give 126 l2 pixels give 124 output pixels per strip, so a strip recomputes 2 of 126 l2 columns;
+// a work item also recomputes one l2 row above and below its row range.  MMA row (= TMEM lane) m stands for
+// pixel x0 - 1 + m in BOTH levels — S2 accumulates onto S1's columns, so the lanes must agree: S1 reads l1 ring
+// pixels m..m+2, S2 reads l2 ring pixels m-1..m+1, and the strip's outputs are lanes 1..124 (lane 0 and lanes
+// 125..127 see out-of-window pixels and are discarded).  The MMA warp issues S1 three rows ahead of S2 so that
+// E1 runs under the MMAs.
 //
 // Warp roles (13 warps): 0 l1-row producer (TMA), 1 MMA issuer, 2 TMEM allocator + P2 producer, 3 weight
 // producer (one tap per stage, 5-stage ring), 4-7 E1, 8-11 E2, 12 P3 producer.  All hand-offs are mbarriers
@@ -34,12 +37,18 @@ struct FusedParams {
     CUtensorMap tmB2;     // conv8|9 weights:   rank 2 (64, 9 * 64), box (64, 64)
     CUtensorMap tmP2;     // conv2(f): rank 4 (32, W, H, NIMG) fp32, box (32, 128, 1, 1)
     CUtensorMap tmP3;     // conv3(f): same
-    CUtensorMap tmL3[2];  // l3 out: bf16 box (64, 32, 1, 1) and (64, 28, 1, 1) (last 32-pixel slice of a strip)
-    CUtensorMap tmE[2];   // E out: fp32 box (32, 32, 1, 1) and (32, 28, 1, 1)
+    CUtensorMap tmL3[3];  // l3 out: bf16 boxes of 32, 31 (first slice of a strip) and 29 pixels (last slice)
+    CUtensorMap tmE[3];   // E out: fp32 boxes of 32, 31 and 29 pixels
     int W, H, NIMG, n_strips;
     long long total_rowtiles;   // NIMG * n_strips * H
     EpiGroup g_l2, g_l3;        // bias / slope of the two activations (kind = EPI_ACT)
     int* fault;
+    // test hooks (rsr_debug_fused): fp32 [NIMG][H][W][32] dumps of l2 (as written to the ring) and of the raw
+    // accumulator columns 32..63 (conv6(l1) + conv8(l2)); dbg_flags bit 0 = skip the S2 MMAs
+    float* dbg_l2;
+    float* dbg_t3;
+    int dbg_flags;
+    long long* prof;            // test hook: per-CTA wait-cycle counters of the MMA warp [gridDim.x][8]
 };
 
 struct FusedCfg {
@@ -85,6 +94,17 @@ __device__ __forceinline__ bool fitem_next(const FusedParams& p, long long& cur,
 }
 
 #define FW(bar, par, tag) mbar_wait(bar, par, p.fault, tag)
+// MMA-warp waits, charged to a counter when the profiling hook is on
+#define FWP(bar, par, tag, slot)                                   \
+    do {                                                            \
+        if (p.prof) {                                               \
+            const long long t0__ = clock64();                       \
+            mbar_wait(bar, par, p.fault, tag);                      \
+            prof_acc[slot] += clock64() - t0__;                     \
+        } else {                                                    \
+            mbar_wait(bar, par, p.fault, tag);                      \
+        }                                                           \
+    } while (0)
 
 __global__ void __launch_bounds__(FusedCfg::NTHREADS, 1) conv_fused_mid_kernel(const __grid_constant__ FusedParams p) {
     using C = FusedCfg;
@@ -194,14 +214,14 @@ __global__ void __launch_bounds__(FusedCfg::NTHREADS, 1) conv_fused_mid_kernel(c
             }
         }
     } else if (warp == 12) {
-        // ===== P3 tile producer: one tile per S2 row (pixels x0 .. x0+127 of row y_b+r) =====
+        // ===== P3 tile producer: one tile per S2 row (pixels x0-1 .. x0+126 of row y_b+r: tile row = TMEM lane) =====
         uint32_t u = 0;
         while (fitem_next(p, cur, end, w)) {
             for (int r = 0; r < w.n; ++r, ++u) {
                 FW(p3_empty, (u & 1) ^ 1, 24);
                 if (elect_one()) {
                     mbar_arrive_expect_tx(p3_full, C::SLOT);
-                    tma_load_4d(sP3, &p.tmP3, p3_full, 0, w.x0, w.y_b + r, w.img);
+                    tma_load_4d(sP3, &p.tmP3, p3_full, 0, w.x0 - 1, w.y_b + r, w.img);
                 }
                 __syncwarp();
             }
@@ -220,14 +240,16 @@ __global__ void __launch_bounds__(FusedCfg::NTHREADS, 1) conv_fused_mid_kernel(c
         uint32_t c2 = 0;                    // S2 rows so far
         uint32_t bst = 0, bpar = 0;
         int n_item = 0;
+        long long prof_acc[5] = {0, 0, 0, 0, 0};   // t_empty, a_full, b_full (S1), l2_full, b_full (S2)
+        const long long prof_t0 = p.prof ? clock64() : 0;
 
         // S1(q): l1 rows q..q+2 of the item -> T slot of row q
         auto s1 = [&](int q) {
             const uint32_t c = c1_item + q;
             const uint32_t ts = c % C::NT;
-            FW(&t_empty[ts], ((c / C::NT) & 1) ^ 1, 25);
+            FWP(&t_empty[ts], ((c / C::NT) & 1) ^ 1, 25, 0);
             while (a_wait <= a_item + q + 2) {
-                FW(&a_full[a_wait % C::NR1], (a_wait / C::NR1) & 1, 26);
+                FWP(&a_full[a_wait % C::NR1], (a_wait / C::NR1) & 1, 26, 1);
                 ++a_wait;
             }
             tc_fence_after();
@@ -238,7 +260,7 @@ __global__ void __launch_bounds__(FusedCfg::NTHREADS, 1) conv_fused_mid_kernel(c
             #pragma unroll
             for (int t = 0; t < 9; ++t) {
                 const int ta = t / 3, tb = t % 3;
-                FW(&b_full[bst], bpar, 27);
+                FWP(&b_full[bst], bpar, 27, 2);
                 tc_fence_after();
                 if (elect_one()) {
                     const uint32_t b_e = sB_e + bst * (C::BST >> 4);
@@ -264,11 +286,12 @@ __global__ void __launch_bounds__(FusedCfg::NTHREADS, 1) conv_fused_mid_kernel(c
             }
             __syncwarp();
         };
-        // S2(r): l2 rows r..r+2 of the item, accumulated onto columns 32..95 of the T slot of l2 row r+1
+        // S2(r): l2 rows r..r+2 of the item, accumulated onto columns 32..95 of the T slot of l2 row r+1; lane m is
+        // pixel x0-1+m as in S1 (lane 0 reads one pixel before the ring slot: garbage in, discarded)
         auto s2 = [&](int r) {
             const uint32_t ts = (c1_item + r + 1) % C::NT;
             while (l2_wait <= c1_item + r + 2) {
-                FW(&l2_full[l2_wait % C::NR2], (l2_wait / C::NR2) & 1, 28);
+                FWP(&l2_full[l2_wait % C::NR2], (l2_wait / C::NR2) & 1, 28, 3);
                 ++l2_wait;
             }
             tc_fence_after();
@@ -279,13 +302,14 @@ __global__ void __launch_bounds__(FusedCfg::NTHREADS, 1) conv_fused_mid_kernel(c
             #pragma unroll
             for (int t = 0; t < 9; ++t) {
                 const int ta = t / 3, tb = t % 3;
-                FW(&b_full[bst], bpar, 29);
+                FWP(&b_full[bst], bpar, 29, 4);
                 tc_fence_after();
                 if (elect_one()) {
                     const uint32_t b_e = sB_e + bst * (C::BST >> 4);
-                    const uint32_t a_e = lrow[ta] + tb * (128 >> 4);
+                    const uint32_t a_e = lrow[ta] + (tb - 1) * (128 >> 4);   // lane m reads ring pixels m-1..m+1
                     #pragma unroll
                     for (int k = 0; k < 2; ++k) {
+                        if (p.dbg_flags & 1) continue;
                         umma_f16(d, desc(HI, a_e + 2 * k), desc(HI, b_e + 2 * k), IDESC2, 1);
                         umma_f16(d, desc(HI, a_e + MID + 2 * k), desc(HI, b_e + 2 * k), IDESC2, 1);
                         umma_f16(d, desc(HI, a_e + 2 * k), desc(HI, b_e + MID + 2 * k), IDESC2, 1);
@@ -316,6 +340,11 @@ __global__ void __launch_bounds__(FusedCfg::NTHREADS, 1) conv_fused_mid_kernel(c
             }
             c1_item += ns1;
             a_item += w.n + 4;
+        }
+        if (p.prof && lane == 0) {
+            long long* dst = p.prof + (size_t)blockIdx.x * 8;
+            for (int i = 0; i < 5; ++i) dst[i] = prof_acc[i];
+            dst[7] = clock64() - prof_t0;
         }
     } else if (warp >= 4 && warp < 8) {
         // ===== E1: l2pre (+ P2) -> l2 row in the shared-memory ring =====
@@ -352,6 +381,11 @@ __global__ void __launch_bounds__(FusedCfg::NTHREADS, 1) conv_fused_mid_kernel(c
                 // Padding::Same of conv8 / conv9: l2 is ZERO outside the image (not BeLU(bias)); lanes past the
                 // strip's 126 valid l2 pixels hold garbage accumulators and are zeroed too
                 const bool valid = y >= 0 && y < p.H && px >= 0 && px < p.W && m < C::L2W;
+                if (p.dbg_l2 && valid) {
+                    float4* dst = reinterpret_cast<float4*>(p.dbg_l2 + (((size_t)w.img * p.H + y) * p.W + px) * 32);
+                    #pragma unroll
+                    for (int i = 0; i < 8; ++i) dst[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+                }
                 uint32_t hi[16], mid[16];
                 #pragma unroll
                 for (int i = 0; i < 16; ++i) {
@@ -379,14 +413,18 @@ __global__ void __launch_bounds__(FusedCfg::NTHREADS, 1) conv_fused_mid_kernel(c
         }
     } else if (warp >= 8 && warp < 12) {
         // ===== E2: T[32:64] (+ P3) -> l3;  T[64:96] -> E =====
+        // This warp's lanes are pixels xl .. xl+31 with xl = x0-1+32*ew; the strip's outputs are lanes 1..124, so
+        // warp 0 drops its lane 0 (staging row = lane-1, 31-pixel store at x0) and warp 3 its lanes 29..31.
         const int ew = warp - 8;
         const uint32_t stage = smem_u32(sO) + ew * 4096;
         const uint32_t sP3_u = smem_u32(sP3);
-        const int bx = ew == 3 ? 1 : 0;   // the last 32-pixel slice of a strip holds 28 pixels
+        const int bx = ew == 0 ? 1 : ew == 3 ? 2 : 0;     // tensor maps with 32 / 31 / 29 pixel boxes
+        const int srow = ew == 0 ? lane - 1 : lane;       // staging row of this lane (-1: not stored)
         uint32_t c1_item = 0, c2 = 0;
         while (fitem_next(p, cur, end, w)) {
-            const int xw = w.x0 + ew * 32;
-            const bool live = xw < p.W;   // warp-uniform
+            const int xl = w.x0 - 1 + ew * 32;
+            const int xs = ew == 0 ? w.x0 : xl;            // first pixel this warp stores
+            const bool live = xs < p.W;   // warp-uniform
             for (int r = 0; r < w.n; ++r, ++c2) {
                 const uint32_t ts = (c1_item + r + 1) % C::NT;
                 const int y = w.y_b + r;
@@ -400,6 +438,14 @@ __global__ void __launch_bounds__(FusedCfg::NTHREADS, 1) conv_fused_mid_kernel(c
                 tmem_ld_wait();
                 #pragma unroll
                 for (int k = 0; k < 32; ++k) v[k] = __uint_as_float(raw[k]);
+                if (p.dbg_t3 && live) {
+                    const int m = ew * 32 + lane, px = xl + lane;
+                    if (m >= 1 && m <= C::STRIP && px < p.W) {
+                        float4* dst = reinterpret_cast<float4*>(p.dbg_t3 + (((size_t)w.img * p.H + y) * p.W + px) * 32);
+                        #pragma unroll
+                        for (int i = 0; i < 8; ++i) dst[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+                    }
+                }
                 FW(p3_full, c2 & 1, 34);
                 epi_add_partial_tile(v, sP3_u, ew * 32 + lane);
                 __syncwarp();
@@ -407,13 +453,13 @@ __global__ void __launch_bounds__(FusedCfg::NTHREADS, 1) conv_fused_mid_kernel(c
                 if (live) {
                     if (elect_one()) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
                     __syncwarp();
-                    epi_split_to_stage(p.g_l3, v, stage, lane);
+                    if (srow >= 0) epi_split_to_stage(p.g_l3, v, stage, srow);
                     fence_proxy_async_smem();
                     __syncwarp();
                     if (elect_one()) {
                         asm volatile(
                             "cp.async.bulk.tensor.4d.global.shared::cta.tile.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
-                            ::"l"(reinterpret_cast<uint64_t>(&p.tmL3[bx])), "r"(stage), "r"(0), "r"(xw), "r"(y), "r"(w.img)
+                            ::"l"(reinterpret_cast<uint64_t>(&p.tmL3[bx])), "r"(stage), "r"(0), "r"(xs), "r"(y), "r"(w.img)
                             : "memory");
                         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                     }
@@ -426,13 +472,13 @@ __global__ void __launch_bounds__(FusedCfg::NTHREADS, 1) conv_fused_mid_kernel(c
                 if (live) {
                     if (elect_one()) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
                     __syncwarp();
-                    epi_raw_to_stage(v, stage, lane);
+                    if (srow >= 0) epi_raw_to_stage(v, stage, srow);
                     fence_proxy_async_smem();
                     __syncwarp();
                     if (elect_one()) {
                         asm volatile(
                             "cp.async.bulk.tensor.4d.global.shared::cta.tile.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
-                            ::"l"(reinterpret_cast<uint64_t>(&p.tmE[bx])), "r"(stage), "r"(0), "r"(xw), "r"(y), "r"(w.img)
+                            ::"l"(reinterpret_cast<uint64_t>(&p.tmE[bx])), "r"(stage), "r"(0), "r"(xs), "r"(y), "r"(w.img)
                             : "memory");
                         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                     }
@@ -451,5 +497,6 @@ __global__ void __launch_bounds__(FusedCfg::NTHREADS, 1) conv_fused_mid_kernel(c
 }
 
 #undef FW
+#undef FWP
 
 }  // namespace rsr

@@ -170,6 +170,8 @@ struct rsr_ctx {
     // workspace
     DevBuf xcol, xf4, actA, actB, partA, partB, partC, out_f32, out_u8, in_stage;
     bool fused_mid = false;     // conv5|6|7 + conv8|9 in one launch (conv_fused.cuh); RSR_FLAG_FUSED_MID
+    int fused_dbg = 0;          // test hook rsr_debug_fused: bit 0 skip S2 MMAs, bit 1 dump l2 / raw accumulators, bit 2 profile
+    DevBuf dbg_l2, dbg_t3, dbg_prof;
     int* fault = nullptr;       // device alias of fault_host (mapped pinned memory: readable after a kernel trap)
     int* fault_host = nullptr;  // [0] = code, [4 + 4*warp ..] = which barrier each warp role was stuck on
     cudaEvent_t ev[K_COUNT + 1] = {};
@@ -251,7 +253,7 @@ extern "C" void rsr_destroy(rsr_ctx* c) {
     cudaFree(c->vecs); cudaFree(c->prof);
     if (c->fault_host) cudaFreeHost(c->fault_host);
     release(c->xcol); release(c->xf4); release(c->actA); release(c->actB); release(c->partA);
-    release(c->partB); release(c->partC); release(c->out_f32); release(c->out_u8); release(c->in_stage);
+    release(c->partB); release(c->partC); release(c->dbg_l2); release(c->dbg_t3); release(c->dbg_prof); release(c->out_f32); release(c->out_u8); release(c->in_stage);
     for (auto& e : c->ev) if (e) cudaEventDestroy(e);
     for (auto& sl : c->slot) {
         release(sl.in); release(sl.out);
@@ -568,11 +570,27 @@ static int forward_device(rsr_ctx* c, const void* d_in, bool u8, int in_ch, int 
         if (int rc = part_map(&q.tmP2, P2, 128)) return rc;
         if (int rc = part_map(&q.tmP3, P3, 128)) return rc;
         if (int rc = in_map(&q.tmL3[0], l3_act, 32)) return rc;
-        if (int rc = in_map(&q.tmL3[1], l3_act, 28)) return rc;
+        if (int rc = in_map(&q.tmL3[1], l3_act, 31)) return rc;
+        if (int rc = in_map(&q.tmL3[2], l3_act, 29)) return rc;
         if (int rc = part_map(&q.tmE[0], E, 32)) return rc;
-        if (int rc = part_map(&q.tmE[1], E, 28)) return rc;
+        if (int rc = part_map(&q.tmE[1], E, 31)) return rc;
+        if (int rc = part_map(&q.tmE[2], E, 29)) return rc;
         q.g_l2 = EpiGroup{EPI_ACT, 1, l2_bias, l2_slope, 0, 0};
         q.g_l3 = EpiGroup{EPI_ACT, 1, l3_bias, l3_slope, 0, 0};
+        q.dbg_flags = c->fused_dbg & 1;
+        if (c->fused_dbg & 2) {
+            if (int rc = ensure(c->dbg_l2, npx * 128)) return rc;
+            if (int rc = ensure(c->dbg_t3, npx * 128)) return rc;
+            CUDA_TRY(cudaMemsetAsync(c->dbg_l2.p, 0, npx * 128, c->stream));
+            CUDA_TRY(cudaMemsetAsync(c->dbg_t3.p, 0, npx * 128, c->stream));
+            q.dbg_l2 = (float*)c->dbg_l2.p;
+            q.dbg_t3 = (float*)c->dbg_t3.p;
+        }
+        if (c->fused_dbg & 4) {
+            if (int rc = ensure(c->dbg_prof, 256 * 8 * sizeof(long long))) return rc;
+            CUDA_TRY(cudaMemsetAsync(c->dbg_prof.p, 0, 256 * 8 * sizeof(long long), c->stream));
+            q.prof = (long long*)c->dbg_prof.p;
+        }
         const int grid = (int)std::min<long long>(q.total_rowtiles, c->num_sms);
         conv_fused_mid_kernel<<<grid, FusedCfg::NTHREADS, FusedCfg::SMEM_BYTES, c->stream>>>(q);
         CUDA_TRY(cudaGetLastError());
@@ -776,7 +794,7 @@ extern "C" int rsr_debug_read_node(rsr_ctx* c, int which, float* out, size_t npx
     if (!c || !out) return fail(RSR_E_BAD_ARG, "null argument");
     if (int rc = rsr_synchronize(c)) return rc;
     DevBuf* b = which == 0 ? &c->actA : which == 1 ? &c->actB : which == 2 ? &c->partA : which == 3 ? &c->partB
-              : which == 4 ? &c->partC : nullptr;
+              : which == 4 ? &c->partC : which == 5 ? &c->dbg_l2 : which == 6 ? &c->dbg_t3 : nullptr;
     if (!b || !b->p || b->cap < npx * 128) return fail(RSR_E_BAD_ARG, "node %d not available for %zu pixels", which, npx);
     if (which >= 2) {
         CUDA_TRY(cudaMemcpy(out, b->p, npx * 128, cudaMemcpyDeviceToHost));
@@ -788,6 +806,20 @@ extern "C" int rsr_debug_read_node(rsr_ctx* c, int which, float* out, size_t npx
         for (int ch = 0; ch < 32; ++ch)
             out[i * 32 + ch] = __bfloat162float(tmp[i * 64 + ch]) + __bfloat162float(tmp[i * 64 + 32 + ch]);
     return 0;
+}
+
+extern "C" int rsr_debug_fused(rsr_ctx* c, int flags) {
+    if (!c) return fail(RSR_E_BAD_ARG, "ctx is null");
+    c->fused_dbg = flags;
+    return 0;
+}
+// [grid][8] wait-cycle counters of the fused launch's MMA warp (t_empty, a_full, b_full S1, l2_full, b_full S2, -, -, total)
+extern "C" int rsr_debug_read_fused_profile(rsr_ctx* c, long long* out, int cap_rows) {
+    if (!c || !out || !c->dbg_prof.p) return fail(RSR_E_BAD_ARG, "fused profile not enabled");
+    if (int rc = rsr_synchronize(c)) return rc;
+    const int rows = cap_rows < 256 ? cap_rows : 256;
+    CUDA_TRY(cudaMemcpy(out, c->dbg_prof.p, sizeof(long long) * rows * 8, cudaMemcpyDeviceToHost));
+    return rows;
 }
 
 extern "C" int rsr_debug_profile(rsr_ctx* c, int enable) {
