@@ -41,7 +41,10 @@ enum {
      * SPLIT_MID: two launches with l2 and the partial sums stored to HBM in between (6 launches per call).
      * Neither flag: the library default (the RSR_B200_FUSED=0|1 environment variable overrides it). */
     RSR_FLAG_FUSED_MID = 1,
-    RSR_FLAG_SPLIT_MID = 2
+    RSR_FLAG_SPLIT_MID = 2,
+    /* Run every conv launch on single CTAs (conv_strip.cuh) even where the library default uses CTA pairs
+     * (tcgen05 cta_group::2, conv_pair.cuh; RSR_B200_PAIR=<launch bit mask> overrides the default). */
+    RSR_FLAG_NO_PAIRS = 4
 };
 
 /* graph.num_params() of sr_net(factor, None): 130459 for factor 3 (main.rs:162; layout in

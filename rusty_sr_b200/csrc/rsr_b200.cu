@@ -20,6 +20,7 @@
 #include "../../include/rsr_b200.h"
 #include "conv_strip.cuh"
 #include "conv_fused.cuh"
+#include "conv_pair.cuh"
 
 using namespace rsr;
 
@@ -100,6 +101,9 @@ using Cfg2 = ConvCfg<3, 3, 128, 3, 2,  5, 2, 3, 2, 2, false, 8>;  // l1 -> conv5
 using Cfg3 = ConvCfg<3, 3, 128, 2, 2,  5, 2, 3, 3, 2, false>;  // l2 -> conv8 | conv9           (+ P3, E)
 using Cfg4 = ConvCfg<3, 3, 128, 1, 2,  6, 3, 3, 3, 2, true, 8>;  // l3 -> conv10 (+ E) + expand + bilinear skip
 
+#ifndef RSR_DEFAULT_PAIR_MASK
+#define RSR_DEFAULT_PAIR_MASK 4   // conv1|2|3 (launch index 2) on CTA pairs: -12..18 % on that launch, measured; the 3x3 launches are slower on pairs
+#endif
 #ifndef RSR_DEFAULT_FUSED_MID
 #define RSR_DEFAULT_FUSED_MID 0
 #endif
@@ -170,6 +174,7 @@ struct rsr_ctx {
     // workspace
     DevBuf xcol, xf4, actA, actB, partA, partB, partC, out_f32, out_u8, in_stage;
     bool fused_mid = false;     // conv5|6|7 + conv8|9 in one launch (conv_fused.cuh); RSR_FLAG_FUSED_MID
+    int pair_mask = 0;          // bit k: launch index k (1 = conv0 .. 5 = conv10) runs as CTA pairs (conv_pair.cuh)
     int fused_dbg = 0;          // test hook rsr_debug_fused: bit 0 skip S2 MMAs, bit 1 dump l2 / raw accumulators, bit 2 profile
     DevBuf dbg_l2, dbg_t3, dbg_prof;
     int* fault = nullptr;       // device alias of fault_host (mapped pinned memory: readable after a kernel trap)
@@ -355,6 +360,11 @@ static int create_impl(rsr_ctx* c, const float* params) {
     CUDA_TRY(cudaFuncSetAttribute(conv_strip_kernel<Cfg3>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg3::SMEM_BYTES));
     CUDA_TRY(cudaFuncSetAttribute(conv_strip_kernel<Cfg4>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg4::SMEM_BYTES));
     CUDA_TRY(cudaFuncSetAttribute(conv_fused_mid_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FusedCfg::SMEM_BYTES));
+    CUDA_TRY(cudaFuncSetAttribute(conv_pair_kernel<Cfg0>, cudaFuncAttributeMaxDynamicSharedMemorySize, PairCfg<Cfg0>::SMEM_BYTES));
+    CUDA_TRY(cudaFuncSetAttribute(conv_pair_kernel<Cfg1>, cudaFuncAttributeMaxDynamicSharedMemorySize, PairCfg<Cfg1>::SMEM_BYTES));
+    CUDA_TRY(cudaFuncSetAttribute(conv_pair_kernel<Cfg2>, cudaFuncAttributeMaxDynamicSharedMemorySize, PairCfg<Cfg2>::SMEM_BYTES));
+    CUDA_TRY(cudaFuncSetAttribute(conv_pair_kernel<Cfg3>, cudaFuncAttributeMaxDynamicSharedMemorySize, PairCfg<Cfg3>::SMEM_BYTES));
+    CUDA_TRY(cudaFuncSetAttribute(conv_pair_kernel<Cfg4>, cudaFuncAttributeMaxDynamicSharedMemorySize, PairCfg<Cfg4>::SMEM_BYTES));
     return 0;
 }
 
@@ -395,6 +405,10 @@ extern "C" rsr_ctx* rsr_create(const float* params, size_t n_params, int factor,
         if (flags & RSR_FLAG_FUSED_MID) fused = true;
         if (flags & RSR_FLAG_SPLIT_MID) fused = false;
         c->fused_mid = fused;
+        int pm = RSR_DEFAULT_PAIR_MASK;
+        if (const char* e = getenv("RSR_B200_PAIR")) pm = atoi(e);
+        if (flags & RSR_FLAG_NO_PAIRS) pm = 0;
+        c->pair_mask = pm;
     }
     if (create_impl(c, params) != 0) {
         const std::string keep = g_err;
@@ -468,8 +482,23 @@ static int make_map_w(rsr_ctx* c, CUtensorMap* m, const void* base, int elems, i
     return 0;
 }
 
+// CTA-pair variant (conv_pair.cuh): p.tmB must have been built with a box of NCOL / 2 rows (one CTA's half tap).
+template <class C>
+static int launch_conv_pair(rsr_ctx* c, ConvParams& p, int kindex) {
+    p.n_strips = (p.W + 127) / 128;
+    p.total_rowtiles = (long long)p.NIMG * p.n_strips * (p.row_end - p.row_begin);
+    const int ncl = (int)std::min<long long>(p.total_rowtiles, c->num_sms / 2);
+    p.prof = nullptr;
+    c->prof_grid[kindex] = 0;
+    conv_pair_kernel<C><<<2 * ncl, C::NTHREADS, PairCfg<C>::SMEM_BYTES, c->stream>>>(p);
+    CUDA_TRY(cudaGetLastError());
+    c->last_launches++;
+    return 0;
+}
+
 template <class C>
 static int launch_conv(rsr_ctx* c, ConvParams& p, int kindex) {
+    if (c->pair_mask >> kindex & 1) return launch_conv_pair<C>(c, p, kindex);
     p.n_strips = (p.W + 127) / 128;
     p.total_rowtiles = (long long)p.NIMG * p.n_strips * (p.row_end - p.row_begin);
     const int grid = (int)std::min<long long>(p.total_rowtiles, c->num_sms);
@@ -528,11 +557,12 @@ static int forward_device(rsr_ctx* c, const void* d_in, bool u8, int in_ch, int 
     p.xf4 = (const float4*)c->xf4.p;
     const EpiGroup none{EPI_NONE, 0, nullptr, nullptr, 0, 0};
     auto in_map = [&](CUtensorMap* m, const void* base, int boxw) { return make_map_act(c, m, base, 64, w, h, n, boxw); };
+    auto pair = [&](int kindex) { return (c->pair_mask >> kindex & 1) != 0; };
     auto part_map = [&](CUtensorMap* m, const void* base, int boxw) { return make_map_part(c, m, base, w, h, n, boxw); };
 
     // conv0: xcol -> f = BeLU(conv0(x) + f_bias)                       network.rs:33-35
     if (int rc = make_map_act(c, &p.tmA, xcol, 32, w, h, n, Cfg0::BOXW)) return rc;
-    if (int rc = make_map_w(c, &p.tmB, c->w0, 32, 5 * 32, Cfg0::TPS * 32)) return rc;
+    if (int rc = make_map_w(c, &p.tmB, c->w0, 32, 5 * 32, pair(1) ? 16 : Cfg0::TPS * 32)) return rc;
     if (int rc = in_map(&p.tmOut[0], f_act, 32)) return rc;
     p.grp[0] = EpiGroup{EPI_ACT, 0, f_bias, f_slope, 0, 0};
     p.grp[1] = none; p.grp[2] = none;
@@ -542,7 +572,7 @@ static int forward_device(rsr_ctx* c, const void* d_in, bool u8, int in_ch, int 
 
     // f -> l1 = BeLU(conv1(f) + l1_bias); P2 = conv2(f); P3 = conv3(f)  network.rs:60-62,50,54
     if (int rc = in_map(&p.tmA, f_act, Cfg1::BOXW)) return rc;
-    if (int rc = make_map_w(c, &p.tmB, c->w1, 64, 25 * 96, Cfg1::TPS * 96)) return rc;
+    if (int rc = make_map_w(c, &p.tmB, c->w1, 64, 25 * 96, pair(2) ? 48 : Cfg1::TPS * 96)) return rc;
     if (int rc = in_map(&p.tmOut[0], l1_act, 32)) return rc;
     if (int rc = part_map(&p.tmOut[1], P2, 32)) return rc;
     if (int rc = part_map(&p.tmOut[2], P3, 32)) return rc;
@@ -604,7 +634,7 @@ static int forward_device(rsr_ctx* c, const void* d_in, bool u8, int in_ch, int 
         // (l2 overwrites f, E overwrites P2: both are dead; a thread block only overwrites pixels whose
         //  partial tile it has already consumed — see DESIGN.md "aliasing")
         if (int rc = in_map(&p.tmA, l1_act, Cfg2::BOXW)) return rc;
-        if (int rc = make_map_w(c, &p.tmB, c->w2, 64, 9 * 96, Cfg2::TPS * 96)) return rc;
+        if (int rc = make_map_w(c, &p.tmB, c->w2, 64, 9 * 96, pair(3) ? 48 : Cfg2::TPS * 96)) return rc;
         if (int rc = part_map(&p.tmPin[0], P2, 128)) return rc;
         if (int rc = part_map(&p.tmPin[1], P3, 128)) return rc;
         if (int rc = in_map(&p.tmOut[0], l2_act, 32)) return rc;
@@ -619,7 +649,7 @@ static int forward_device(rsr_ctx* c, const void* d_in, bool u8, int in_ch, int 
 
         // l2 -> l3 = BeLU(P3 + conv8(l2) + l3_bias); E += conv9(l2)                  :69-70,52,56
         if (int rc = in_map(&p.tmA, l2_act, Cfg3::BOXW)) return rc;
-        if (int rc = make_map_w(c, &p.tmB, c->w3, 64, 9 * 64, Cfg3::TPS * 64)) return rc;
+        if (int rc = make_map_w(c, &p.tmB, c->w3, 64, 9 * 64, pair(4) ? 32 : Cfg3::TPS * 64)) return rc;
         if (int rc = part_map(&p.tmPin[0], P3, 128)) return rc;
         if (int rc = part_map(&p.tmPin[1], E, 128)) return rc;
         if (int rc = in_map(&p.tmOut[0], l3_act, 32)) return rc;
@@ -635,7 +665,7 @@ static int forward_device(rsr_ctx* c, const void* d_in, bool u8, int in_ch, int 
 
     // l3 -> output = Expand(E + conv10(l3) + expand_bias) + LinearInterp(x)          :72,38-39,27
     if (int rc = in_map(&p.tmA, l3_act, Cfg4::BOXW)) return rc;
-    if (int rc = make_map_w(c, &p.tmB, c->w4, 64, 9 * 32, Cfg4::TPS * 32)) return rc;
+    if (int rc = make_map_w(c, &p.tmB, c->w4, 64, 9 * 32, pair(5) ? 16 : Cfg4::TPS * 32)) return rc;
     if (int rc = part_map(&p.tmPin[0], E, 128)) return rc;
     p.grp[0] = EpiGroup{EPI_SHUFFLE, 1, e_bias, nullptr, 0, 0};
     p.grp[1] = none; p.grp[2] = none;
