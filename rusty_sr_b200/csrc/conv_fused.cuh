@@ -26,8 +26,15 @@
 // Warp roles (13 warps): 0 l1-row producer (TMA), 1 MMA issuer, 2 TMEM allocator + P2 producer, 3 weight
 // producer (one tap per stage, 5-stage ring), 4-7 E1, 8-11 E2, 12 P3 producer.  All hand-offs are mbarriers
 // and every wait is bounded (ptx.cuh mbar_wait).
+//
+// CTA-pair variant (template parameter PAIR; tcgen05 cta_group::2 as in conv_pair.cuh): the kernel is bound by the
+// shared-memory port — with one row per step every weight tap is re-streamed into shared memory and re-read by
+// the MMAs for every row — so a cluster of two CTAs shares the weights: each CTA holds half of every tap, the
+// leader's MMAs (M = 256) process the row of both CTAs at once.  The two CTAs take the upper / lower half of the
+// cluster's row range of one strip and run in lock step; l1 rows and weight halves signal the leader's barriers,
+// commits are multicast, the peer's E1 / E2 warps arrive remotely on the leader's l2_full / t_empty.
 #pragma once
-#include "conv_strip.cuh"
+#include "conv_pair.cuh"
 
 namespace rsr {
 
@@ -51,18 +58,37 @@ struct FusedParams {
     long long* prof;            // test hook: per-CTA wait-cycle counters of the MMA warp [gridDim.x][8]
 };
 
-struct FusedCfg {
+#ifndef RSR_FUSED_PAIR_TPS
+#define RSR_FUSED_PAIR_TPS 3
+#endif
+#ifndef RSR_FUSED_PAIR_NB
+#define RSR_FUSED_PAIR_NB 3
+#endif
+#ifndef RSR_FUSED_PAIR_NR1
+#define RSR_FUSED_PAIR_NR1 4
+#endif
+template <bool PAIR_>
+struct FusedCfgT {
+    static constexpr bool PAIR = PAIR_;
     static constexpr int STRIP = 124;          // output pixels per strip
     static constexpr int L2W = 126;            // valid l2 pixels per strip row
     static constexpr int SLOT = 128 * 128;     // one row slot: 128 pixels x 128 B
-    static constexpr int NR1 = 4;              // l1 ring (3-row window + 1 in flight)
+    static constexpr int NR1 = PAIR ? RSR_FUSED_PAIR_NR1 : 4;     // l1 ring (3-row window + rows in flight)
     static constexpr int NR2 = 3;              // l2 ring
-    static constexpr int NB = 5;               // weight stages (one tap each)
-    static constexpr int BST = 96 * 128;       // stage pitch (conv8|9 taps use 64 * 128 of it)
+    static constexpr int TPS = PAIR ? RSR_FUSED_PAIR_TPS : 1;     // taps per weight stage (each tcgen05.commit that
+                                               // releases a stage costs tensor-pipe time: fewer, larger stages)
+    static constexpr int NSTG = 9 / TPS;       // stages per S1 / S2
+    static constexpr int NB = PAIR ? RSR_FUSED_PAIR_NB : 5;       // weight stages in the ring
+    static constexpr int H1 = PAIR ? 48 : 96;  // weight rows per conv5|6|7 tap in this CTA
+    static constexpr int H2 = PAIR ? 32 : 64;  // weight rows per conv8|9 tap in this CTA
+    static constexpr int TAP1 = H1 * 128, TAP2 = H2 * 128;        // bytes of one tap in this CTA
+    static constexpr int BST = TPS * TAP1;     // stage pitch
+    static_assert(9 % TPS == 0, "taps per stage must divide 9");
     static constexpr int NT = 5;               // TMEM row slots of 96 columns
     static constexpr int TCOLS = 96;
     static constexpr int LOOKAHEAD = 4;        // S1 rows issued before the first S2 of a work item
     static constexpr int NTHREADS = 13 * 32;
+    static constexpr int NARR = PAIR ? 8 : 4;  // epilogue-warp arrivals on l2_full / t_empty (both CTAs of a pair)
     static constexpr int OFF_L2 = NR1 * SLOT;
     static constexpr int OFF_B = OFF_L2 + NR2 * SLOT;
     static constexpr int OFF_P2 = OFF_B + NB * BST;
@@ -76,19 +102,32 @@ struct FusedCfg {
     static_assert(OFF_BAR % 1024 == 0 && BST % 1024 == 0, "1024-byte swizzle atoms");
     static_assert(SMEM_BYTES <= 232448, "shared memory budget");
 };
+using FusedCfg = FusedCfgT<false>;
 
 struct FItem {
-    int img, x0, y_b, n;
+    int img, x0, y_b, n, y_e;   // rows y_b .. y_b+n-1 are computed, rows >= y_e are not stored
 };
-__device__ __forceinline__ bool fitem_next(const FusedParams& p, long long& cur, long long end, FItem& w) {
+// Cluster-level work item (strip, row range) -> this CTA's rows.  Single CTA: the whole range.  Pair: the leader
+// takes the upper half, the peer the lower half, both run `n` = ceil(range / 2) rows in lock step (y_e clips the
+// peer's stores when the range is odd or a single row).
+template <bool PAIR>
+__device__ __forceinline__ bool fitem_next(const FusedParams& p, long long& cur, long long end, uint32_t rank, FItem& w) {
     if (cur >= end) return false;
     const int col = (int)(cur / p.H);
     const int y0 = (int)(cur % p.H);
     const int n = (int)min((long long)(p.H - y0), end - cur);
     w.img = col / p.n_strips;
     w.x0 = (col % p.n_strips) * FusedCfg::STRIP;
-    w.y_b = y0;
-    w.n = n;
+    if (PAIR) {
+        const int l0 = (n + 1) / 2;
+        w.y_b = y0 + (rank ? l0 : 0);
+        w.n = l0;
+        w.y_e = y0 + n;
+    } else {
+        w.y_b = y0;
+        w.n = n;
+        w.y_e = y0 + n;
+    }
     cur += n;
     return true;
 }
@@ -97,7 +136,7 @@ __device__ __forceinline__ bool fitem_next(const FusedParams& p, long long& cur,
 // MMA-warp waits, charged to a counter when the profiling hook is on
 #define FWP(bar, par, tag, slot)                                   \
     do {                                                            \
-        if (p.prof) {                                               \
+        if (DBG && p.prof) {                                        \
             const long long t0__ = clock64();                       \
             mbar_wait(bar, par, p.fault, tag);                      \
             prof_acc[slot] += clock64() - t0__;                     \
@@ -106,8 +145,13 @@ __device__ __forceinline__ bool fitem_next(const FusedParams& p, long long& cur,
         }                                                           \
     } while (0)
 
+// DBG: compile the test hooks (dumps, S2 skip, wait profile) in — they cost ~25 % when merely present.
+// PAIR: CTA-pair variant; must be launched with cluster dimension 2.
+template <bool DBG, bool PAIR>
 __global__ void __launch_bounds__(FusedCfg::NTHREADS, 1) conv_fused_mid_kernel(const __grid_constant__ FusedParams p) {
-    using C = FusedCfg;
+    using C = FusedCfgT<PAIR>;
+    const uint32_t rank = PAIR ? cluster_ctarank() : 0u;
+    const bool leader = rank == 0;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* sA = smem;
@@ -139,8 +183,8 @@ __global__ void __launch_bounds__(FusedCfg::NTHREADS, 1) conv_fused_mid_kernel(c
         for (int i = 0; i < C::NB; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
         mbar_init(p2_full, 1); mbar_init(p2_empty, 4);
         mbar_init(p3_full, 1); mbar_init(p3_empty, 4);
-        for (int i = 0; i < C::NT; ++i) { mbar_init(&t1_full[i], 1); mbar_init(&t2_full[i], 1); mbar_init(&t_empty[i], 4); }
-        for (int i = 0; i < C::NR2; ++i) { mbar_init(&l2_full[i], 4); mbar_init(&l2_empty[i], 1); }
+        for (int i = 0; i < C::NT; ++i) { mbar_init(&t1_full[i], 1); mbar_init(&t2_full[i], 1); mbar_init(&t_empty[i], C::NARR); }
+        for (int i = 0; i < C::NR2; ++i) { mbar_init(&l2_full[i], C::NARR); mbar_init(&l2_empty[i], 1); }
         fence_mbar_init();
         tma_prefetch_desc(&p.tmA);
         tma_prefetch_desc(&p.tmB1);
@@ -148,15 +192,31 @@ __global__ void __launch_bounds__(FusedCfg::NTHREADS, 1) conv_fused_mid_kernel(c
         tma_prefetch_desc(&p.tmP2);
         tma_prefetch_desc(&p.tmP3);
     }
-    if (warp == 2) { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
+    if (warp == 2) {
+        if (PAIR) {
+            asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+        } else {
+            tmem_alloc(tmem_slot, 512);
+            tmem_relinquish();
+        }
+    }
     tc_fence_before();
     __syncthreads();
+    if (PAIR) cluster_sync_all();   // both CTAs' barriers exist before any cross-CTA signal
     tc_fence_after();
     const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
 
-    long long cur = p.total_rowtiles * (long long)blockIdx.x / gridDim.x;
-    const long long end = p.total_rowtiles * (long long)(blockIdx.x + 1) / gridDim.x;
+    // work ranges are per cluster (pair) or per CTA
+    const long long nrange = PAIR ? gridDim.x >> 1 : gridDim.x, irange = PAIR ? blockIdx.x >> 1 : blockIdx.x;
+    long long cur = p.total_rowtiles * irange / nrange;
+    const long long end = p.total_rowtiles * (irange + 1) / nrange;
     FItem w;
+    // barriers the MMA warp of the LEADER waits on, as seen from this CTA (pair: remote for the peer)
+    const uint32_t a_full0 = PAIR ? map_to_cta(smem_u32(a_full), 0) : smem_u32(a_full);
+    const uint32_t b_full0 = PAIR ? map_to_cta(smem_u32(b_full), 0) : smem_u32(b_full);
+    const uint32_t l2_full0 = PAIR ? map_to_cta(smem_u32(l2_full), 0) : smem_u32(l2_full);
+    const uint32_t t_empty0 = PAIR ? map_to_cta(smem_u32(t_empty), 0) : smem_u32(t_empty);
 
     // Counters shared by convention between the roles (each role keeps its own copy, advanced identically):
     //   c1 = number of S1 rows so far (all items): T slot c1 % NT, l2 slot c1 % NR2
@@ -166,13 +226,18 @@ __global__ void __launch_bounds__(FusedCfg::NTHREADS, 1) conv_fused_mid_kernel(c
     if (warp == 0) {
         // ===== l1 row producer: rows y_b-2 .. y_e+1 of the strip, pixels x0-2 .. x0+125 =====
         uint32_t a = 0;
-        while (fitem_next(p, cur, end, w)) {
+        while (fitem_next<PAIR>(p, cur, end, rank, w)) {
             for (int i = 0; i < w.n + 4; ++i, ++a) {
                 const uint32_t sl = a % C::NR1, par = ((a / C::NR1) & 1) ^ 1;
                 FW(&a_empty[sl], par, 21);
                 if (elect_one()) {
-                    mbar_arrive_expect_tx(&a_full[sl], C::SLOT);
-                    tma_load_4d(sA + sl * C::SLOT, &p.tmA, &a_full[sl], 0, w.x0 - 2, w.y_b - 2 + i, w.img);
+                    if (PAIR) {
+                        if (leader) mbar_arrive_expect_tx(&a_full[sl], 2 * C::SLOT);
+                        tma2_load_4d(smem_u32(sA + sl * C::SLOT), &p.tmA, a_full0 + sl * 8, 0, w.x0 - 2, w.y_b - 2 + i, w.img);
+                    } else {
+                        mbar_arrive_expect_tx(&a_full[sl], C::SLOT);
+                        tma_load_4d(sA + sl * C::SLOT, &p.tmA, &a_full[sl], 0, w.x0 - 2, w.y_b - 2 + i, w.img);
+                    }
                 }
                 __syncwarp();
             }
@@ -180,18 +245,28 @@ __global__ void __launch_bounds__(FusedCfg::NTHREADS, 1) conv_fused_mid_kernel(c
     } else if (warp == 3) {
         // ===== weight producer: one tap per stage, in the MMA warp's S1 / S2 order =====
         uint32_t st = 0, par = 1;
+        // ncol = output columns of the op (96 / 64); a pair CTA loads its half of the tap's rows
         auto taps = [&](const CUtensorMap* tm, int ncol) {
-            for (int t = 0; t < 9; ++t) {
+            const int tapb = (PAIR ? ncol / 2 : ncol) * 128;   // bytes of one tap in this CTA
+            for (int sp = 0; sp < C::NSTG; ++sp) {
                 FW(&b_empty[st], par, 22);
                 if (elect_one()) {
-                    mbar_arrive_expect_tx(&b_full[st], ncol * 128);
-                    tma_load_2d(sB + st * C::BST, tm, &b_full[st], 0, t * ncol);
+                    if (PAIR) {
+                        if (leader) mbar_arrive_expect_tx(&b_full[st], C::TPS * ncol * 128);   // both halves of every tap
+                        for (int tt = 0; tt < C::TPS; ++tt)
+                            tma2_load_2d(smem_u32(sB + st * C::BST + tt * tapb), tm, b_full0 + st * 8, 0,
+                                         (sp * C::TPS + tt) * ncol + (int)rank * (ncol / 2));
+                    } else {
+                        mbar_arrive_expect_tx(&b_full[st], C::TPS * ncol * 128);
+                        for (int tt = 0; tt < C::TPS; ++tt)
+                            tma_load_2d(sB + st * C::BST + tt * tapb, tm, &b_full[st], 0, (sp * C::TPS + tt) * ncol);
+                    }
                 }
                 __syncwarp();
                 if (++st == C::NB) { st = 0; par ^= 1; }
             }
         };
-        while (fitem_next(p, cur, end, w)) {
+        while (fitem_next<PAIR>(p, cur, end, rank, w)) {
             // op order of the MMA warp: S1 runs LOOKAHEAD rows ahead of S2
             const int ns1 = w.n + 2;
             for (int i1 = 0, r = 0; r < w.n;) {
@@ -203,7 +278,7 @@ __global__ void __launch_bounds__(FusedCfg::NTHREADS, 1) conv_fused_mid_kernel(c
     } else if (warp == 2) {
         // ===== P2 tile producer: one tile per S1 row (pixels x0-1 .. x0+126 of row y_b-1+q) =====
         uint32_t u = 0;
-        while (fitem_next(p, cur, end, w)) {
+        while (fitem_next<PAIR>(p, cur, end, rank, w)) {
             for (int q = 0; q < w.n + 2; ++q, ++u) {
                 FW(p2_empty, (u & 1) ^ 1, 23);
                 if (elect_one()) {
@@ -216,7 +291,7 @@ __global__ void __launch_bounds__(FusedCfg::NTHREADS, 1) conv_fused_mid_kernel(c
     } else if (warp == 12) {
         // ===== P3 tile producer: one tile per S2 row (pixels x0-1 .. x0+126 of row y_b+r: tile row = TMEM lane) =====
         uint32_t u = 0;
-        while (fitem_next(p, cur, end, w)) {
+        while (fitem_next<PAIR>(p, cur, end, rank, w)) {
             for (int r = 0; r < w.n; ++r, ++u) {
                 FW(p3_empty, (u & 1) ^ 1, 24);
                 if (elect_one()) {
@@ -227,10 +302,19 @@ __global__ void __launch_bounds__(FusedCfg::NTHREADS, 1) conv_fused_mid_kernel(c
             }
         }
     } else if (warp == 1) {
-        // ===== MMA issuer =====
+        // ===== MMA issuer (pair: the leader's, for both CTAs) =====
+        if (leader) {
         constexpr uint32_t HI = (uint32_t)make_sdesc_hi(1024, UMMA_SW_128B);
-        constexpr uint32_t IDESC1 = make_idesc_bf16(128, 96);
-        constexpr uint32_t IDESC2 = make_idesc_bf16(128, 64);
+        constexpr uint32_t IDESC1 = make_idesc_bf16(PAIR ? 256 : 128, 96);
+        constexpr uint32_t IDESC2 = make_idesc_bf16(PAIR ? 256 : 128, 64);
+        auto mma = [](uint32_t d, uint64_t a, uint64_t b, uint32_t idesc, uint32_t acc) {
+            if (PAIR) umma2_f16(d, a, b, idesc, acc); else umma_f16(d, a, b, idesc, acc);
+        };
+        auto commit = [](uint64_t* bar) { if (PAIR) umma2_commit(bar); else umma_commit(bar); };
+        // barriers that the epilogue warps of both CTAs arrive on need a cluster-scope acquire in the pair kernel
+        auto wait_epi = [&](uint64_t* bar, uint32_t par, int tag) {
+            if (PAIR) mbar_wait_cluster(bar, par, p.fault, tag); else mbar_wait(bar, par, p.fault, tag);
+        };
         constexpr uint32_t LBO = 1u << 16;
         constexpr uint32_t MID = 64 >> 4;   // encoded offset of the mid plane inside a pixel's 128 B
         const uint32_t sA_e = (smem_u32(sA) >> 4) | LBO, sL_e = (smem_u32(sL) >> 4) | LBO, sB_e = (smem_u32(sB) >> 4) | LBO;
@@ -241,13 +325,14 @@ __global__ void __launch_bounds__(FusedCfg::NTHREADS, 1) conv_fused_mid_kernel(c
         uint32_t bst = 0, bpar = 0;
         int n_item = 0;
         long long prof_acc[5] = {0, 0, 0, 0, 0};   // t_empty, a_full, b_full (S1), l2_full, b_full (S2)
-        const long long prof_t0 = p.prof ? clock64() : 0;
+        const long long prof_t0 = (DBG && p.prof) ? clock64() : 0;
 
         // S1(q): l1 rows q..q+2 of the item -> T slot of row q
         auto s1 = [&](int q) {
             const uint32_t c = c1_item + q;
             const uint32_t ts = c % C::NT;
-            FWP(&t_empty[ts], ((c / C::NT) & 1) ^ 1, 25, 0);
+            if (PAIR) wait_epi(&t_empty[ts], ((c / C::NT) & 1) ^ 1, 25);
+            else FWP(&t_empty[ts], ((c / C::NT) & 1) ^ 1, 25, 0);
             while (a_wait <= a_item + q + 2) {
                 FWP(&a_full[a_wait % C::NR1], (a_wait / C::NR1) & 1, 26, 1);
                 ++a_wait;
@@ -258,30 +343,34 @@ __global__ void __launch_bounds__(FusedCfg::NTHREADS, 1) conv_fused_mid_kernel(c
             for (int ta = 0; ta < 3; ++ta) arow[ta] = sA_e + ((a_item + q + ta) % C::NR1) * (C::SLOT >> 4);
             const uint32_t d = tmem_base + ts * C::TCOLS;
             #pragma unroll
-            for (int t = 0; t < 9; ++t) {
-                const int ta = t / 3, tb = t % 3;
+            for (int sp = 0; sp < C::NSTG; ++sp) {
                 FWP(&b_full[bst], bpar, 27, 2);
                 tc_fence_after();
                 if (elect_one()) {
-                    const uint32_t b_e = sB_e + bst * (C::BST >> 4);
-                    const uint32_t a_e = arow[ta] + tb * (128 >> 4);
                     #pragma unroll
-                    for (int k = 0; k < 2; ++k) {
-                        umma_f16(d, desc(HI, a_e + 2 * k), desc(HI, b_e + 2 * k), IDESC1, (t | k) != 0 ? 1u : 0u);
-                        umma_f16(d, desc(HI, a_e + MID + 2 * k), desc(HI, b_e + 2 * k), IDESC1, 1);
-                        umma_f16(d, desc(HI, a_e + 2 * k), desc(HI, b_e + MID + 2 * k), IDESC1, 1);
+                    for (int tt = 0; tt < C::TPS; ++tt) {
+                        const int t = sp * C::TPS + tt;
+                        const int ta = t / 3, tb = t % 3;
+                        const uint32_t b_e = sB_e + bst * (C::BST >> 4) + tt * (C::TAP1 >> 4);
+                        const uint32_t a_e = arow[ta] + tb * (128 >> 4);
+                        #pragma unroll
+                        for (int k = 0; k < 2; ++k) {
+                            mma(d, desc(HI, a_e + 2 * k), desc(HI, b_e + 2 * k), IDESC1, (t | k) != 0 ? 1u : 0u);
+                            mma(d, desc(HI, a_e + MID + 2 * k), desc(HI, b_e + 2 * k), IDESC1, 1);
+                            mma(d, desc(HI, a_e + 2 * k), desc(HI, b_e + MID + 2 * k), IDESC1, 1);
+                        }
+                        if (t == 2) commit(&a_empty[(a_item + q) % C::NR1]);   // top window row is dead
                     }
-                    if (t == 2) umma_commit(&a_empty[(a_item + q) % C::NR1]);   // top window row is dead
-                    umma_commit(&b_empty[bst]);
+                    commit(&b_empty[bst]);
                 }
                 __syncwarp();
                 if (++bst == C::NB) { bst = 0; bpar ^= 1; }
             }
             if (elect_one()) {
-                umma_commit(&t1_full[ts]);
+                commit(&t1_full[ts]);
                 if (q == n_item + 1) {   // last S1 of the item: the rest of its window is dead too
-                    umma_commit(&a_empty[(a_item + q + 1) % C::NR1]);
-                    umma_commit(&a_empty[(a_item + q + 2) % C::NR1]);
+                    commit(&a_empty[(a_item + q + 1) % C::NR1]);
+                    commit(&a_empty[(a_item + q + 2) % C::NR1]);
                 }
             }
             __syncwarp();
@@ -291,7 +380,8 @@ __global__ void __launch_bounds__(FusedCfg::NTHREADS, 1) conv_fused_mid_kernel(c
         auto s2 = [&](int r) {
             const uint32_t ts = (c1_item + r + 1) % C::NT;
             while (l2_wait <= c1_item + r + 2) {
-                FWP(&l2_full[l2_wait % C::NR2], (l2_wait / C::NR2) & 1, 28, 3);
+                if (PAIR) wait_epi(&l2_full[l2_wait % C::NR2], (l2_wait / C::NR2) & 1, 28);
+                else FWP(&l2_full[l2_wait % C::NR2], (l2_wait / C::NR2) & 1, 28, 3);
                 ++l2_wait;
             }
             tc_fence_after();
@@ -300,37 +390,41 @@ __global__ void __launch_bounds__(FusedCfg::NTHREADS, 1) conv_fused_mid_kernel(c
             for (int ta = 0; ta < 3; ++ta) lrow[ta] = sL_e + ((c1_item + r + ta) % C::NR2) * (C::SLOT >> 4);
             const uint32_t d = tmem_base + ts * C::TCOLS + 32;
             #pragma unroll
-            for (int t = 0; t < 9; ++t) {
-                const int ta = t / 3, tb = t % 3;
+            for (int sp = 0; sp < C::NSTG; ++sp) {
                 FWP(&b_full[bst], bpar, 29, 4);
                 tc_fence_after();
                 if (elect_one()) {
-                    const uint32_t b_e = sB_e + bst * (C::BST >> 4);
-                    const uint32_t a_e = lrow[ta] + (tb - 1) * (128 >> 4);   // lane m reads ring pixels m-1..m+1
                     #pragma unroll
-                    for (int k = 0; k < 2; ++k) {
-                        if (p.dbg_flags & 1) continue;
-                        umma_f16(d, desc(HI, a_e + 2 * k), desc(HI, b_e + 2 * k), IDESC2, 1);
-                        umma_f16(d, desc(HI, a_e + MID + 2 * k), desc(HI, b_e + 2 * k), IDESC2, 1);
-                        umma_f16(d, desc(HI, a_e + 2 * k), desc(HI, b_e + MID + 2 * k), IDESC2, 1);
+                    for (int tt = 0; tt < C::TPS; ++tt) {
+                        const int t = sp * C::TPS + tt;
+                        const int ta = t / 3, tb = t % 3;
+                        const uint32_t b_e = sB_e + bst * (C::BST >> 4) + tt * (C::TAP2 >> 4);
+                        const uint32_t a_e = lrow[ta] + (tb - 1) * (128 >> 4);   // lane m reads ring pixels m-1..m+1
+                        #pragma unroll
+                        for (int k = 0; k < 2; ++k) {
+                            if (DBG && (p.dbg_flags & 1)) continue;
+                            mma(d, desc(HI, a_e + 2 * k), desc(HI, b_e + 2 * k), IDESC2, 1);
+                            mma(d, desc(HI, a_e + MID + 2 * k), desc(HI, b_e + 2 * k), IDESC2, 1);
+                            mma(d, desc(HI, a_e + 2 * k), desc(HI, b_e + MID + 2 * k), IDESC2, 1);
+                        }
+                        if (t == 2) commit(&l2_empty[(c1_item + r) % C::NR2]);
                     }
-                    if (t == 2) umma_commit(&l2_empty[(c1_item + r) % C::NR2]);
-                    umma_commit(&b_empty[bst]);
+                    commit(&b_empty[bst]);
                 }
                 __syncwarp();
                 if (++bst == C::NB) { bst = 0; bpar ^= 1; }
             }
             if (elect_one()) {
-                umma_commit(&t2_full[c2 % C::NT]);
+                commit(&t2_full[c2 % C::NT]);
                 if (r == n_item - 1) {
-                    umma_commit(&l2_empty[(c1_item + r + 1) % C::NR2]);
-                    umma_commit(&l2_empty[(c1_item + r + 2) % C::NR2]);
+                    commit(&l2_empty[(c1_item + r + 1) % C::NR2]);
+                    commit(&l2_empty[(c1_item + r + 2) % C::NR2]);
                 }
             }
             __syncwarp();
             ++c2;
         };
-        while (fitem_next(p, cur, end, w)) {
+        while (fitem_next<PAIR>(p, cur, end, rank, w)) {
             n_item = w.n;
             // S1 runs LOOKAHEAD rows ahead of S2: S1(0..3) S2(0) S1(4) S2(1) ... ; all n+2 S1 rows precede S2(n-1)
             const int ns1 = w.n + 2;
@@ -341,18 +435,19 @@ __global__ void __launch_bounds__(FusedCfg::NTHREADS, 1) conv_fused_mid_kernel(c
             c1_item += ns1;
             a_item += w.n + 4;
         }
-        if (p.prof && lane == 0) {
+        if (DBG && p.prof && lane == 0) {
             long long* dst = p.prof + (size_t)blockIdx.x * 8;
             for (int i = 0; i < 5; ++i) dst[i] = prof_acc[i];
             dst[7] = clock64() - prof_t0;
         }
+        }  // leader
     } else if (warp >= 4 && warp < 8) {
         // ===== E1: l2pre (+ P2) -> l2 row in the shared-memory ring =====
         const int ew = warp - 4;
         const int m = ew * 32 + lane;            // MMA row = l2 ring pixel index
         const uint32_t sL_u = smem_u32(sL), sP2_u = smem_u32(sP2);
         uint32_t c = 0;
-        while (fitem_next(p, cur, end, w)) {
+        while (fitem_next<PAIR>(p, cur, end, rank, w)) {
             for (int q = 0; q < w.n + 2; ++q, ++c) {
                 const uint32_t ts = c % C::NT, ls = c % C::NR2;
                 const int y = w.y_b - 1 + q, px = w.x0 - 1 + m;
@@ -381,7 +476,7 @@ __global__ void __launch_bounds__(FusedCfg::NTHREADS, 1) conv_fused_mid_kernel(c
                 // Padding::Same of conv8 / conv9: l2 is ZERO outside the image (not BeLU(bias)); lanes past the
                 // strip's 126 valid l2 pixels hold garbage accumulators and are zeroed too
                 const bool valid = y >= 0 && y < p.H && px >= 0 && px < p.W && m < C::L2W;
-                if (p.dbg_l2 && valid) {
+                if (DBG && p.dbg_l2 && valid) {
                     float4* dst = reinterpret_cast<float4*>(p.dbg_l2 + (((size_t)w.img * p.H + y) * p.W + px) * 32);
                     #pragma unroll
                     for (int i = 0; i < 8; ++i) dst[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
@@ -405,9 +500,12 @@ __global__ void __launch_bounds__(FusedCfg::NTHREADS, 1) conv_fused_mid_kernel(c
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) {
-                    mbar_arrive(&l2_full[ls]);
+                    // (pair: both arrive on the leader's barriers; release at cluster scope)
+                    if (PAIR) mbar_arrive_cluster(l2_full0 + ls * 8); else mbar_arrive(&l2_full[ls]);
                     // halo rows have no S2 / E2: their T slot is released here
-                    if (q == 0 || q == w.n + 1) mbar_arrive(&t_empty[ts]);
+                    if (q == 0 || q == w.n + 1) {
+                        if (PAIR) mbar_arrive_cluster(t_empty0 + ts * 8); else mbar_arrive(&t_empty[ts]);
+                    }
                 }
             }
         }
@@ -421,13 +519,14 @@ __global__ void __launch_bounds__(FusedCfg::NTHREADS, 1) conv_fused_mid_kernel(c
         const int bx = ew == 0 ? 1 : ew == 3 ? 2 : 0;     // tensor maps with 32 / 31 / 29 pixel boxes
         const int srow = ew == 0 ? lane - 1 : lane;       // staging row of this lane (-1: not stored)
         uint32_t c1_item = 0, c2 = 0;
-        while (fitem_next(p, cur, end, w)) {
+        while (fitem_next<PAIR>(p, cur, end, rank, w)) {
             const int xl = w.x0 - 1 + ew * 32;
             const int xs = ew == 0 ? w.x0 : xl;            // first pixel this warp stores
-            const bool live = xs < p.W;   // warp-uniform
+            const bool live_x = xs < p.W;   // warp-uniform
             for (int r = 0; r < w.n; ++r, ++c2) {
                 const uint32_t ts = (c1_item + r + 1) % C::NT;
                 const int y = w.y_b + r;
+                const bool live = live_x && y < w.y_e;   // (pair: the peer's padding rows are computed, not stored)
                 FW(&t2_full[c2 % C::NT], (c2 / C::NT) & 1, 33);
                 tc_fence_after();
                 const uint32_t trow = tmem_base + ((uint32_t)(ew * 32) << 16) + ts * C::TCOLS;
@@ -438,7 +537,7 @@ __global__ void __launch_bounds__(FusedCfg::NTHREADS, 1) conv_fused_mid_kernel(c
                 tmem_ld_wait();
                 #pragma unroll
                 for (int k = 0; k < 32; ++k) v[k] = __uint_as_float(raw[k]);
-                if (p.dbg_t3 && live) {
+                if (DBG && p.dbg_t3 && live) {
                     const int m = ew * 32 + lane, px = xl + lane;
                     if (m >= 1 && m <= C::STRIP && px < p.W) {
                         float4* dst = reinterpret_cast<float4*>(p.dbg_t3 + (((size_t)w.img * p.H + y) * p.W + px) * 32);
@@ -485,7 +584,9 @@ __global__ void __launch_bounds__(FusedCfg::NTHREADS, 1) conv_fused_mid_kernel(c
                 }
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&t_empty[ts]);
+                if (lane == 0) {
+                    if (PAIR) mbar_arrive_cluster(t_empty0 + ts * 8); else mbar_arrive(&t_empty[ts]);
+                }
             }
             c1_item += w.n + 2;
         }
@@ -493,7 +594,13 @@ __global__ void __launch_bounds__(FusedCfg::NTHREADS, 1) conv_fused_mid_kernel(c
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 2) tmem_dealloc(tmem_base, 512);
+    if (PAIR) {
+        cluster_sync_all();   // the pair's MMAs and remote arrivals are over before either CTA leaves
+        if (warp == 2)
+            asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    } else if (warp == 2) {
+        tmem_dealloc(tmem_base, 512);
+    }
 }
 
 #undef FW

@@ -99,23 +99,6 @@ __device__ __forceinline__ void umma2_commit(uint64_t* bar) {
                  : "memory");
 }
 
-// Shared-memory plan of the pair kernel: as ConvCfg, with half a weight tap per CTA.
-template <class C_>
-struct PairCfg {
-    using C = C_;
-    static constexpr int HB = C::NCOL / 2;                       // weight rows per tap held by one CTA
-    static constexpr int TAP_BYTES_H = HB * C::RB;
-    static constexpr int BST = C::TPS * TAP_BYTES_H;             // bytes per weight stage per CTA
-    static constexpr int OFF_B = C::NR * C::SLOT;
-    static constexpr int OFF_P = OFF_B + C::NBS * BST;
-    static constexpr int OFF_O = OFF_P + C::NPIN * C::PIN_BYTES;
-    static constexpr int OFF_BAR = OFF_O + C::NEPI * C::NOUT * 4096;
-    static constexpr int SMEM_BYTES = 1024 + OFF_BAR + C::NBAR * 8 + 16;
-    static_assert(HB % 8 == 0, "half a tap must be whole 8-row core-matrix groups");
-    static_assert(TAP_BYTES_H % 1024 == 0, "half weight tap must keep 1024-byte alignment");
-    static_assert(SMEM_BYTES <= 232448, "shared memory budget");
-};
-
 struct PairIter {
     long long cur, end;
     int rows;
@@ -138,7 +121,8 @@ __device__ __forceinline__ bool pair_item_next(const ConvParams& p, PairIter& it
 
 template <class C>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(C::NTHREADS, 1) conv_pair_kernel(const __grid_constant__ ConvParams p) {
-    using P = PairCfg<C>;
+    static_assert(C::PAIR, "conv_pair_kernel needs a ConvCfg with PAIR = true (half weight taps)");
+    using P = C;   // shared-memory plan: ConvCfg computes it with half a weight tap per CTA
     extern __shared__ uint8_t smem_raw[];
     // (the dynamic shared-memory window starts at the same offset in both CTAs, so the aligned base does too)
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -225,9 +209,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(C::NTHREADS, 1) conv
                     if (elect_one()) {
                         const int t0 = sp * C::TPS;
                         const int nt = C::TAPS - t0 < C::TPS ? C::TAPS - t0 : C::TPS;   // taps really in this stage
-                        if (leader) mbar_arrive_expect_tx(&b_full[st], 2 * nt * P::TAP_BYTES_H);
+                        if (leader) mbar_arrive_expect_tx(&b_full[st], 2 * nt * P::TAP_BYTES);
                         for (int tt = 0; tt < nt; ++tt)
-                            tma2_load_2d(smem_u32(sB + st * P::BST + tt * P::TAP_BYTES_H), &p.tmB, b_full0 + st * 8, 0,
+                            tma2_load_2d(smem_u32(sB + st * P::BST + tt * P::TAP_BYTES), &p.tmB, b_full0 + st * 8, 0,
                                          (t0 + tt) * C::NCOL + (int)rank * P::HB);
                     }
                     __syncwarp();
@@ -298,7 +282,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(C::NTHREADS, 1) conv
                                 const int t = sp * C::TPS + tt;
                                 if (t < C::TAPS) {
                                     const int ta = t / C::KW, tb = t % C::KW;
-                                    const uint32_t b_e = b_st + tt * (P::TAP_BYTES_H >> 4);
+                                    const uint32_t b_e = b_st + tt * (P::TAP_BYTES >> 4);
                                     #pragma unroll
                                     for (int r = 0; r < C::R; ++r) {
                                         const uint32_t a_e = arow[r + ta] + tb * (C::RB >> 4);

@@ -100,8 +100,10 @@ struct ConvParams {
         }                                                                \
     } while (0)
 
-template <int KH_, int KW_, int RB_, int NG_, int R_, int NR_, int TPS_, int NBS_, int NPIN_, int NOUT_, bool SHUF_, int NEPI_ = 4>
+template <int KH_, int KW_, int RB_, int NG_, int R_, int NR_, int TPS_, int NBS_, int NPIN_, int NOUT_, bool SHUF_, int NEPI_ = 4,
+          bool PAIR_ = false>
 struct ConvCfg {
+    static constexpr bool PAIR = PAIR_;                                // CTA-pair kernel (conv_pair.cuh): half a weight tap per CTA
     static constexpr int KH = KH_, KW = KW_, RB = RB_, NG = NG_, R = R_;
     static constexpr int NEPI = NEPI_;                                 // epilogue warps (4 or 8)
     static_assert(NEPI == 4 || NEPI == 8, "4 or 8 epilogue warps");
@@ -117,7 +119,8 @@ struct ConvCfg {
     static constexpr int NR = NR_;                                     // input-row ring slots (>= R + 2*PH)
     static constexpr int TPS = TPS_;                                   // taps per weight stage
     static constexpr int NSTG = (TAPS + TPS - 1) / TPS;                // weight stages per pass
-    static constexpr int TAP_BYTES = NCOL * RB;                        // weight bytes of one tap
+    static constexpr int HB = PAIR ? NCOL / 2 : NCOL;                  // weight rows of one tap held by this CTA
+    static constexpr int TAP_BYTES = HB * RB;                          // weight bytes of one tap (in this CTA)
     static constexpr int BST = TPS * TAP_BYTES;                        // bytes per weight stage
     static constexpr int KC = RB / 64;                                 // 16-channel chunks per plane
     static constexpr int PIN_BYTES = 128 * 128;                        // one partial-sum tile
@@ -134,7 +137,8 @@ struct ConvCfg {
     static_assert(ACC_COLS <= 512, "accumulators exceed TMEM");
     static_assert(RB == 128 || RB == 64, "pixel row must be 128 or 64 bytes");
     static_assert(TAP_BYTES % 1024 == 0, "weight tap tile must keep 1024-byte alignment");
-    static_assert(TPS * NCOL <= 256, "weight stage exceeds the TMA box limit");
+    static_assert(PAIR || TPS * NCOL <= 256, "weight stage exceeds the TMA box limit");   // (pairs load tap by tap)
+    static_assert(HB % 8 == 0, "a CTA's share of a tap must be whole 8-row core-matrix groups");
     static_assert(NR >= R + 2 * PH, "row ring smaller than one pass window");
     static_assert(SMEM_BYTES <= 232448, "shared memory budget");
 };

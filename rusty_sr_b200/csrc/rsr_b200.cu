@@ -107,6 +107,32 @@ using Cfg4 = ConvCfg<3, 3, 128, 1, 2,  6, 3, 3, 3, 2, true, 8>;  // l3 -> conv10
 #ifndef RSR_DEFAULT_FUSED_MID
 #define RSR_DEFAULT_FUSED_MID 0
 #endif
+// CTA-pair variants (conv_pair.cuh): same geometry, half a weight tap per CTA, so the shared memory freed can go
+// into deeper weight rings
+#ifndef RSR_PCFG1_NR
+#define RSR_PCFG1_NR 7
+#endif
+#ifndef RSR_PCFG1_TPS
+#define RSR_PCFG1_TPS 2
+#endif
+#ifndef RSR_PCFG1_NBS
+#define RSR_PCFG1_NBS 3
+#endif
+#ifndef RSR_PCFG1_NEPI
+#define RSR_PCFG1_NEPI 4
+#endif
+using PCfg0 = ConvCfg<5, 1,  64, 1, 4, 12, 5, 2, 0, 2, false, 8, true>;
+using PCfg1 = ConvCfg<5, 5, 128, 3, 2, RSR_PCFG1_NR, RSR_PCFG1_TPS, RSR_PCFG1_NBS, 0, 2, false, RSR_PCFG1_NEPI, true>;
+using PCfg2 = ConvCfg<3, 3, 128, 3, 2,  5, 2, 3, 2, 2, false, 8, true>;
+using PCfg3 = ConvCfg<3, 3, 128, 2, 2,  5, 2, 3, 3, 2, false, 4, true>;
+using PCfg4 = ConvCfg<3, 3, 128, 1, 2,  6, 3, 3, 3, 2, true, 8, true>;
+template <class C> struct PairOf;
+template <> struct PairOf<Cfg0> { using type = PCfg0; };
+template <> struct PairOf<Cfg1> { using type = PCfg1; };
+template <> struct PairOf<Cfg2> { using type = PCfg2; };
+template <> struct PairOf<Cfg3> { using type = PCfg3; };
+template <> struct PairOf<Cfg4> { using type = PCfg4; };
+
 enum { K_PACK = 0, K_CONV0, K_F, K_L1, K_L2, K_L3, K_COUNT };
 static const char* kKernelNames[K_COUNT] = {"pack_input", "conv0", "conv1|2|3", "conv5|6|7", "conv8|9",
                                             "conv10+expand+skip"};
@@ -359,12 +385,14 @@ static int create_impl(rsr_ctx* c, const float* params) {
     CUDA_TRY(cudaFuncSetAttribute(conv_strip_kernel<Cfg2>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg2::SMEM_BYTES));
     CUDA_TRY(cudaFuncSetAttribute(conv_strip_kernel<Cfg3>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg3::SMEM_BYTES));
     CUDA_TRY(cudaFuncSetAttribute(conv_strip_kernel<Cfg4>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg4::SMEM_BYTES));
-    CUDA_TRY(cudaFuncSetAttribute(conv_fused_mid_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FusedCfg::SMEM_BYTES));
-    CUDA_TRY(cudaFuncSetAttribute(conv_pair_kernel<Cfg0>, cudaFuncAttributeMaxDynamicSharedMemorySize, PairCfg<Cfg0>::SMEM_BYTES));
-    CUDA_TRY(cudaFuncSetAttribute(conv_pair_kernel<Cfg1>, cudaFuncAttributeMaxDynamicSharedMemorySize, PairCfg<Cfg1>::SMEM_BYTES));
-    CUDA_TRY(cudaFuncSetAttribute(conv_pair_kernel<Cfg2>, cudaFuncAttributeMaxDynamicSharedMemorySize, PairCfg<Cfg2>::SMEM_BYTES));
-    CUDA_TRY(cudaFuncSetAttribute(conv_pair_kernel<Cfg3>, cudaFuncAttributeMaxDynamicSharedMemorySize, PairCfg<Cfg3>::SMEM_BYTES));
-    CUDA_TRY(cudaFuncSetAttribute(conv_pair_kernel<Cfg4>, cudaFuncAttributeMaxDynamicSharedMemorySize, PairCfg<Cfg4>::SMEM_BYTES));
+    CUDA_TRY(cudaFuncSetAttribute(conv_fused_mid_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FusedCfg::SMEM_BYTES));
+    CUDA_TRY(cudaFuncSetAttribute(conv_fused_mid_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FusedCfg::SMEM_BYTES));
+    CUDA_TRY(cudaFuncSetAttribute(conv_fused_mid_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FusedCfgT<true>::SMEM_BYTES));
+    CUDA_TRY(cudaFuncSetAttribute(conv_pair_kernel<PCfg0>, cudaFuncAttributeMaxDynamicSharedMemorySize, PCfg0::SMEM_BYTES));
+    CUDA_TRY(cudaFuncSetAttribute(conv_pair_kernel<PCfg1>, cudaFuncAttributeMaxDynamicSharedMemorySize, PCfg1::SMEM_BYTES));
+    CUDA_TRY(cudaFuncSetAttribute(conv_pair_kernel<PCfg2>, cudaFuncAttributeMaxDynamicSharedMemorySize, PCfg2::SMEM_BYTES));
+    CUDA_TRY(cudaFuncSetAttribute(conv_pair_kernel<PCfg3>, cudaFuncAttributeMaxDynamicSharedMemorySize, PCfg3::SMEM_BYTES));
+    CUDA_TRY(cudaFuncSetAttribute(conv_pair_kernel<PCfg4>, cudaFuncAttributeMaxDynamicSharedMemorySize, PCfg4::SMEM_BYTES));
     return 0;
 }
 
@@ -483,14 +511,15 @@ static int make_map_w(rsr_ctx* c, CUtensorMap* m, const void* base, int elems, i
 }
 
 // CTA-pair variant (conv_pair.cuh): p.tmB must have been built with a box of NCOL / 2 rows (one CTA's half tap).
-template <class C>
+template <class C0>
 static int launch_conv_pair(rsr_ctx* c, ConvParams& p, int kindex) {
+    using C = typename PairOf<C0>::type;
     p.n_strips = (p.W + 127) / 128;
     p.total_rowtiles = (long long)p.NIMG * p.n_strips * (p.row_end - p.row_begin);
     const int ncl = (int)std::min<long long>(p.total_rowtiles, c->num_sms / 2);
     p.prof = nullptr;
     c->prof_grid[kindex] = 0;
-    conv_pair_kernel<C><<<2 * ncl, C::NTHREADS, PairCfg<C>::SMEM_BYTES, c->stream>>>(p);
+    conv_pair_kernel<C><<<2 * ncl, C::NTHREADS, C::SMEM_BYTES, c->stream>>>(p);
     CUDA_TRY(cudaGetLastError());
     c->last_launches++;
     return 0;
@@ -595,8 +624,11 @@ static int forward_device(rsr_ctx* c, const void* d_in, bool u8, int in_ch, int 
         q.n_strips = (w + FusedCfg::STRIP - 1) / FusedCfg::STRIP;
         q.total_rowtiles = (long long)n * q.n_strips * h;
         if (int rc = in_map(&q.tmA, l1_act, 128)) return rc;
-        if (int rc = make_map_w(c, &q.tmB1, c->w2, 64, 9 * 96, 96)) return rc;
-        if (int rc = make_map_w(c, &q.tmB2, c->w3, 64, 9 * 64, 64)) return rc;
+        // the fused launch runs on CTA pairs when launch index 3 is in the pair mask (half-tap weight boxes);
+        // the debug hooks exist in the single-CTA debug instantiation only
+        const bool fpair = pair(3) && c->fused_dbg == 0;
+        if (int rc = make_map_w(c, &q.tmB1, c->w2, 64, 9 * 96, fpair ? 48 : 96)) return rc;
+        if (int rc = make_map_w(c, &q.tmB2, c->w3, 64, 9 * 64, fpair ? 32 : 64)) return rc;
         if (int rc = part_map(&q.tmP2, P2, 128)) return rc;
         if (int rc = part_map(&q.tmP3, P3, 128)) return rc;
         if (int rc = in_map(&q.tmL3[0], l3_act, 32)) return rc;
@@ -621,8 +653,24 @@ static int forward_device(rsr_ctx* c, const void* d_in, bool u8, int in_ch, int 
             CUDA_TRY(cudaMemsetAsync(c->dbg_prof.p, 0, 256 * 8 * sizeof(long long), c->stream));
             q.prof = (long long*)c->dbg_prof.p;
         }
-        const int grid = (int)std::min<long long>(q.total_rowtiles, c->num_sms);
-        conv_fused_mid_kernel<<<grid, FusedCfg::NTHREADS, FusedCfg::SMEM_BYTES, c->stream>>>(q);
+        if (fpair) {
+            const int ncl = (int)std::min<long long>(q.total_rowtiles, c->num_sms / 2);
+            cudaLaunchConfig_t cfg{};
+            cfg.gridDim = dim3(2 * ncl);
+            cfg.blockDim = dim3(FusedCfg::NTHREADS);
+            cfg.dynamicSmemBytes = FusedCfgT<true>::SMEM_BYTES;
+            cfg.stream = c->stream;
+            cudaLaunchAttribute at[1];
+            at[0].id = cudaLaunchAttributeClusterDimension;
+            at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+            cfg.attrs = at;
+            cfg.numAttrs = 1;
+            CUDA_TRY(cudaLaunchKernelEx(&cfg, conv_fused_mid_kernel<false, true>, q));
+        } else {
+            const int grid = (int)std::min<long long>(q.total_rowtiles, c->num_sms);
+            if (c->fused_dbg) conv_fused_mid_kernel<true, false><<<grid, FusedCfg::NTHREADS, FusedCfg::SMEM_BYTES, c->stream>>>(q);
+            else conv_fused_mid_kernel<false, false><<<grid, FusedCfg::NTHREADS, FusedCfg::SMEM_BYTES, c->stream>>>(q);
+        }
         CUDA_TRY(cudaGetLastError());
         c->last_launches++;
         // reported in the conv5|6|7 slot of rsr_last_kernel_times; the conv8|9 slot then reads ~0
