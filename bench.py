@@ -227,6 +227,7 @@ def run_ours(args):
         for k in kt_runs[0]:
             ktimes[k] = statistics.mean(r[k] for r in kt_runs)
         fused = up.last_launch_count() == 5      # conv5|6|7 and conv8|9 run as one launch (conv_fused.cuh)
+        plan = up.plan()
         if fused:
             ktimes["conv5|6|7+conv8|9 (fused)"] = ktimes.pop("conv5|6|7") + ktimes.pop("conv8|9")
 
@@ -308,11 +309,11 @@ def run_ours(args):
             "dtype": "bf16x3 split operands, f32 accumulate (fp32-equivalent)", "data": "synthetic",
             "config": {"workload": WORKLOAD, "factor": FACTOR, "weights": "imagenet.rsr",
                        "parallelism": f"image-batch sharding x{world}, no collective",
-                       "launch_plan": ("5 launches/frame: pack, conv0, conv1|2|3, conv5|6|7+conv8|9 fused, conv10+expand"
-                                       if fused else "6 launches/frame: pack, conv0, conv1|2|3, conv5|6|7, conv8|9, conv10+expand"),
+                       "launch_plan": plan,
                        "l2": f"working set ~1.3 GB/step >> 126 MB L2; input rotates over {N_ROTATE} distinct frames (149 MB)",
                        "io": "value: f32 in/out resident in HBM; e2e: u8 RGB host -> u8 RGBA host (pinned)"},
-            "roofline": {"kernel": "conv1|2|3 (conv_strip_kernel<5,5,128,3,2>)", "bound": "tensor",
+            "roofline": {"kernel": "conv1|2|3 (" + ("conv_pair_kernel, CTA pairs cta_group::2, M=256" if "conv1|2|3" in plan.split("CTA pairs")[-1]
+                                                    else "conv_strip_kernel, single CTA") + ", N=96, R=2)", "bound": "tensor",
                          "achieved": achieved_tf, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
                          "frac": achieved_tf / peaks["bf16_tflops"], "traffic": traffic,
                          "peak_source": peaks["source"],

@@ -136,6 +136,8 @@ int rsr_last_kernel_times(rsr_ctx* ctx, float* ms, int cap);
 const char* rsr_kernel_name(int index);
 /* Number of kernel launches issued by the most recent call. */
 int rsr_last_launch_count(rsr_ctx* ctx);
+/* Human-readable launch plan of this context (split / fused middle levels, which launches run on CTA pairs). */
+const char* rsr_plan(rsr_ctx* ctx);
 
 /* Test hooks (used by tests/ to localise a parity failure to one launch; not needed by a host
  * integration).  rsr_debug_stop_after(k): subsequent calls stop after launch index k (see

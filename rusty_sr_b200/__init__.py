@@ -212,6 +212,10 @@ class Upscaler:
             _lib.check(n)
         return out[:n]
 
+    def plan(self) -> str:
+        """Launch plan of this context: split / fused middle levels, which launches run on CTA pairs."""
+        return self._L.rsr_plan(self._h).decode()
+
     def last_launch_count(self) -> int:
         return int(self._L.rsr_last_launch_count(self._h))
 

@@ -22,7 +22,7 @@ EXPORTS = (
     "rsr_num_params", "rsr_create", "rsr_destroy", "rsr_upscale_f32", "rsr_upscale_u8",
     "rsr_upscale_batch_f32", "rsr_upscale_batch_u8", "rsr_upscale_device_f32",
     "rsr_upscale_device_u8", "rsr_synchronize", "rsr_submit_u8", "rsr_submit_f32", "rsr_wait", "rsr_wait_all", "rsr_upscale_band_f32", "rsr_set_stream",
-    "rsr_last_kernel_times", "rsr_kernel_name", "rsr_last_launch_count", "rsr_last_error",
+    "rsr_last_kernel_times", "rsr_kernel_name", "rsr_last_launch_count", "rsr_plan", "rsr_last_error",
     "rsr_last_error_code", "rsr_version", "rsr_debug_stop_after", "rsr_debug_read_node",
     "rsr_debug_profile", "rsr_debug_read_profile", "rsr_debug_fused", "rsr_debug_read_fused_profile",
     "rsr_bilinear_f32", "rsr_bilinear_u8", "rsr_downsample_f32", "rsr_downsample_u8", "rsr_conv2d_3x3_f32",
@@ -70,6 +70,8 @@ def load() -> ctypes.CDLL:
     L.rsr_kernel_name.restype = ctypes.c_char_p
     L.rsr_kernel_name.argtypes = [ci]
     L.rsr_last_launch_count.argtypes = [vp]
+    L.rsr_plan.argtypes = [vp]
+    L.rsr_plan.restype = ctypes.c_char_p
     L.rsr_last_error.restype = ctypes.c_char_p
     L.rsr_last_error_code.restype = ci
     L.rsr_version.restype = ctypes.c_char_p

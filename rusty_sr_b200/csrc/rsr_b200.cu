@@ -861,6 +861,18 @@ extern "C" int rsr_last_kernel_times(rsr_ctx* c, float* ms, int cap) {
     return nout;
 }
 extern "C" int rsr_last_launch_count(rsr_ctx* c) { return c ? c->last_launches : 0; }
+extern "C" const char* rsr_plan(rsr_ctx* c) {
+    static thread_local std::string s;
+    if (!c) return "";
+    s = c->fused_mid ? "5 launches: pack, conv0, conv1|2|3, conv5|6|7+conv8|9 fused, conv10+expand" 
+                     : "6 launches: pack, conv0, conv1|2|3, conv5|6|7, conv8|9, conv10+expand";
+    s += "; CTA pairs (cta_group::2):";
+    bool any = false;
+    for (int k = 1; k < K_COUNT; ++k)
+        if (c->pair_mask >> k & 1) { s += std::string(any ? "," : " ") + kKernelNames[k]; any = true; }
+    if (!any) s += " none";
+    return s.c_str();
+}
 
 // ------------------------------------------------------------------------------- test hooks
 extern "C" int rsr_debug_stop_after(rsr_ctx* c, int k) {
