@@ -152,8 +152,10 @@ int rsr_debug_read_node(rsr_ctx* ctx, int which, float* out, size_t n_pixels);
 /* Per-CTA wait-cycle counters of the conv launches (which mbarrier each warp role waited on, in SM
  * cycles): enable, run a call, then read [grid][16] rows for launch index 1..5; returns the grid. */
 /* Fused middle launch: flags bit 0 = skip the second-level MMAs, bit 1 = dump l2 (read_node which = 5) and the raw
- * accumulator columns conv6(l1)+conv8(l2) (which = 6) as f32 [n*h*w][32], bit 2 = MMA-warp wait-cycle counters,
- * read as [grid][8] rows (t_empty, a_full, b_full S1, l2_full, b_full S2, -, -, total cycles). */
+ * accumulator columns conv6(l1)+conv8(l2) (which = 6) as f32 [n*h*w][32]; bits 0-2 select the single-CTA debug
+ * kernel.  Bit 2 = wait-cycle counters of every warp role, read as [grid][32] rows (slot names: the FP_* enum of
+ * csrc/conv_fused.cuh); bit 3 = the same counters from the plan's own kernel (single CTA or CTA pair), which
+ * carries them only in a library built with -DRSR_FUSED_PROF=1 (all zero otherwise). */
 int rsr_debug_fused(rsr_ctx* ctx, int flags);
 int rsr_debug_read_fused_profile(rsr_ctx* ctx, long long* out, int cap_rows);
 int rsr_debug_profile(rsr_ctx* ctx, int enable);

@@ -206,7 +206,7 @@ class Upscaler:
         _lib.check(self._L.rsr_debug_fused(self._h, flags))
 
     def debug_read_fused_profile(self) -> np.ndarray:
-        out = np.zeros((256, 8), np.int64)
+        out = np.zeros((256, 32), np.int64)
         n = self._L.rsr_debug_read_fused_profile(self._h, _as_ptr(out), 256)
         if n < 0:
             _lib.check(n)

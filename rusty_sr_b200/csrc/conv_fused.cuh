@@ -55,7 +55,39 @@ struct FusedParams {
     float* dbg_l2;
     float* dbg_t3;
     int dbg_flags;
-    long long* prof;            // test hook: per-CTA wait-cycle counters of the MMA warp [gridDim.x][8]
+    long long* prof;            // test hook: per-CTA wait-cycle counters of every warp role [gridDim.x][FPROF_N] (slots: FP_*)
+};
+
+// Wait-cycle profile of the fused launch (rsr_debug_fused bit 2 / bit 3, tools/fused_debug.py --profile): every
+// role charges the cycles it spends blocked on each mbarrier to its own slot of the CTA's row.  Compiled into the
+// DBG instantiation, and into every instantiation (single CTA and CTA pair) when the library is built with
+// -DRSR_FUSED_PROF=1 (tools/ablate.sh builds that variant; the shipped library carries none of it).
+#ifndef RSR_FUSED_PROF
+#define RSR_FUSED_PROF 0
+#endif
+enum : int {
+    FP_A_EMPTY = 0,    // warp 0  l1 row producer: ring slot not yet released by the MMAs
+    FP_B_EMPTY,        // warp 3  weight producer: stage not yet released
+    FP_P2_EMPTY,       // warp 2  P2 producer: E1 still reading the tile
+    FP_P3_EMPTY,       // warp 12 P3 producer: E2 still reading the tile
+    FP_T_EMPTY,        // warp 1  MMA: accumulator slot not drained by E2 (or E1 for halo rows)
+    FP_A_FULL,         //         l1 row not landed
+    FP_B_FULL_S1,      //         weight stage not landed (S1)
+    FP_L2_FULL,        //         l2 ring row not written by E1
+    FP_B_FULL_S2,      //         weight stage not landed (S2)
+    FP_ISSUE_S1,       //         inside the issue blocks of S1 (MMA queue back-pressure included)
+    FP_ISSUE_S2,       //         same for S2
+    FP_MMA_TOTAL,      //         cycles of the whole role loop
+    FP_E1_T1_FULL,     // warp 4  E1: S1 accumulator not complete
+    FP_E1_P2_FULL,     //         P2 tile not landed
+    FP_E1_L2_EMPTY,    //         l2 ring slot still read by S2
+    FP_E1_TOTAL,
+    FP_E2_T2_FULL,     // warp 8  E2: S2 accumulation not complete
+    FP_E2_P3_FULL,     //         P3 tile not landed
+    FP_E2_STORE_READ,  //         staging tile still being read by the previous TMA store
+    FP_E2_TOTAL,
+    FP_ROWS,           // warp 1  S1 rows issued by this CTA
+    FPROF_N = 32
 };
 
 #ifndef RSR_FUSED_PAIR_TPS
@@ -133,16 +165,35 @@ __device__ __forceinline__ bool fitem_next(const FusedParams& p, long long& cur,
 }
 
 #define FW(bar, par, tag) mbar_wait(bar, par, p.fault, tag)
-// MMA-warp waits, charged to a counter when the profiling hook is on
+#define FPROF_ON ((DBG || RSR_FUSED_PROF) && p.prof)
+// waits charged to a profile slot of this CTA's row when the profiling hook is on (FWPC: cluster-scope acquire)
 #define FWP(bar, par, tag, slot)                                   \
     do {                                                            \
-        if (DBG && p.prof) {                                        \
+        if (FPROF_ON) {                                             \
             const long long t0__ = clock64();                       \
             mbar_wait(bar, par, p.fault, tag);                      \
             prof_acc[slot] += clock64() - t0__;                     \
         } else {                                                    \
             mbar_wait(bar, par, p.fault, tag);                      \
         }                                                           \
+    } while (0)
+#define FWPC(bar, par, tag, slot)                                  \
+    do {                                                            \
+        if (FPROF_ON) {                                             \
+            const long long t0__ = clock64();                       \
+            mbar_wait_cluster(bar, par, p.fault, tag);              \
+            prof_acc[slot] += clock64() - t0__;                     \
+        } else {                                                    \
+            mbar_wait_cluster(bar, par, p.fault, tag);              \
+        }                                                           \
+    } while (0)
+// end of a role: lane 0 adds the role's counters [first, first + n) to the CTA's row
+#define FPROF_FLUSH(first, n)                                                              \
+    do {                                                                                    \
+        if (FPROF_ON && lane == 0) {                                                        \
+            long long* dst__ = p.prof + (size_t)blockIdx.x * FPROF_N;                       \
+            for (int i__ = (first); i__ < (first) + (n); ++i__) dst__[i__] = prof_acc[i__]; \
+        }                                                                                   \
     } while (0)
 
 // DBG: compile the test hooks (dumps, S2 skip, wait profile) in — they cost ~25 % when merely present.
@@ -177,6 +228,7 @@ __global__ void __launch_bounds__(FusedCfg::NTHREADS, 1) conv_fused_mid_kernel(c
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
+    long long prof_acc[FPROF_N] = {};   // (dead code unless the profile is compiled in)
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < C::NR1; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
@@ -229,7 +281,7 @@ __global__ void __launch_bounds__(FusedCfg::NTHREADS, 1) conv_fused_mid_kernel(c
         while (fitem_next<PAIR>(p, cur, end, rank, w)) {
             for (int i = 0; i < w.n + 4; ++i, ++a) {
                 const uint32_t sl = a % C::NR1, par = ((a / C::NR1) & 1) ^ 1;
-                FW(&a_empty[sl], par, 21);
+                FWP(&a_empty[sl], par, 21, FP_A_EMPTY);
                 if (elect_one()) {
                     if (PAIR) {
                         if (leader) mbar_arrive_expect_tx(&a_full[sl], 2 * C::SLOT);
@@ -242,6 +294,7 @@ __global__ void __launch_bounds__(FusedCfg::NTHREADS, 1) conv_fused_mid_kernel(c
                 __syncwarp();
             }
         }
+        FPROF_FLUSH(FP_A_EMPTY, 1);
     } else if (warp == 3) {
         // ===== weight producer: one tap per stage, in the MMA warp's S1 / S2 order =====
         uint32_t st = 0, par = 1;
@@ -249,7 +302,7 @@ __global__ void __launch_bounds__(FusedCfg::NTHREADS, 1) conv_fused_mid_kernel(c
         auto taps = [&](const CUtensorMap* tm, int ncol) {
             const int tapb = (PAIR ? ncol / 2 : ncol) * 128;   // bytes of one tap in this CTA
             for (int sp = 0; sp < C::NSTG; ++sp) {
-                FW(&b_empty[st], par, 22);
+                FWP(&b_empty[st], par, 22, FP_B_EMPTY);
                 if (elect_one()) {
                     if (PAIR) {
                         if (leader) mbar_arrive_expect_tx(&b_full[st], C::TPS * ncol * 128);   // both halves of every tap
@@ -275,12 +328,13 @@ __global__ void __launch_bounds__(FusedCfg::NTHREADS, 1) conv_fused_mid_kernel(c
                 if (is_s1) ++i1; else ++r;
             }
         }
+        FPROF_FLUSH(FP_B_EMPTY, 1);
     } else if (warp == 2) {
         // ===== P2 tile producer: one tile per S1 row (pixels x0-1 .. x0+126 of row y_b-1+q) =====
         uint32_t u = 0;
         while (fitem_next<PAIR>(p, cur, end, rank, w)) {
             for (int q = 0; q < w.n + 2; ++q, ++u) {
-                FW(p2_empty, (u & 1) ^ 1, 23);
+                FWP(p2_empty, (u & 1) ^ 1, 23, FP_P2_EMPTY);
                 if (elect_one()) {
                     mbar_arrive_expect_tx(p2_full, C::SLOT);
                     tma_load_4d(sP2, &p.tmP2, p2_full, 0, w.x0 - 1, w.y_b - 1 + q, w.img);
@@ -288,12 +342,13 @@ __global__ void __launch_bounds__(FusedCfg::NTHREADS, 1) conv_fused_mid_kernel(c
                 __syncwarp();
             }
         }
+        FPROF_FLUSH(FP_P2_EMPTY, 1);
     } else if (warp == 12) {
         // ===== P3 tile producer: one tile per S2 row (pixels x0-1 .. x0+126 of row y_b+r: tile row = TMEM lane) =====
         uint32_t u = 0;
         while (fitem_next<PAIR>(p, cur, end, rank, w)) {
             for (int r = 0; r < w.n; ++r, ++u) {
-                FW(p3_empty, (u & 1) ^ 1, 24);
+                FWP(p3_empty, (u & 1) ^ 1, 24, FP_P3_EMPTY);
                 if (elect_one()) {
                     mbar_arrive_expect_tx(p3_full, C::SLOT);
                     tma_load_4d(sP3, &p.tmP3, p3_full, 0, w.x0 - 1, w.y_b + r, w.img);
@@ -301,6 +356,7 @@ __global__ void __launch_bounds__(FusedCfg::NTHREADS, 1) conv_fused_mid_kernel(c
                 __syncwarp();
             }
         }
+        FPROF_FLUSH(FP_P3_EMPTY, 1);
     } else if (warp == 1) {
         // ===== MMA issuer (pair: the leader's, for both CTAs) =====
         if (leader) {
@@ -311,10 +367,7 @@ __global__ void __launch_bounds__(FusedCfg::NTHREADS, 1) conv_fused_mid_kernel(c
             if (PAIR) umma2_f16(d, a, b, idesc, acc); else umma_f16(d, a, b, idesc, acc);
         };
         auto commit = [](uint64_t* bar) { if (PAIR) umma2_commit(bar); else umma_commit(bar); };
-        // barriers that the epilogue warps of both CTAs arrive on need a cluster-scope acquire in the pair kernel
-        auto wait_epi = [&](uint64_t* bar, uint32_t par, int tag) {
-            if (PAIR) mbar_wait_cluster(bar, par, p.fault, tag); else mbar_wait(bar, par, p.fault, tag);
-        };
+        // (barriers that the epilogue warps of both CTAs arrive on need a cluster-scope acquire in the pair kernel: FWPC)
         constexpr uint32_t LBO = 1u << 16;
         constexpr uint32_t MID = 64 >> 4;   // encoded offset of the mid plane inside a pixel's 128 B
         const uint32_t sA_e = (smem_u32(sA) >> 4) | LBO, sL_e = (smem_u32(sL) >> 4) | LBO, sB_e = (smem_u32(sB) >> 4) | LBO;
@@ -324,19 +377,19 @@ __global__ void __launch_bounds__(FusedCfg::NTHREADS, 1) conv_fused_mid_kernel(c
         uint32_t c2 = 0;                    // S2 rows so far
         uint32_t bst = 0, bpar = 0;
         int n_item = 0;
-        long long prof_acc[5] = {0, 0, 0, 0, 0};   // t_empty, a_full, b_full (S1), l2_full, b_full (S2)
-        const long long prof_t0 = (DBG && p.prof) ? clock64() : 0;
+        const long long prof_t0 = FPROF_ON ? clock64() : 0;
 
         // S1(q): l1 rows q..q+2 of the item -> T slot of row q
         auto s1 = [&](int q) {
             const uint32_t c = c1_item + q;
             const uint32_t ts = c % C::NT;
-            if (PAIR) wait_epi(&t_empty[ts], ((c / C::NT) & 1) ^ 1, 25);
-            else FWP(&t_empty[ts], ((c / C::NT) & 1) ^ 1, 25, 0);
+            if (PAIR) FWPC(&t_empty[ts], ((c / C::NT) & 1) ^ 1, 25, FP_T_EMPTY);
+            else FWP(&t_empty[ts], ((c / C::NT) & 1) ^ 1, 25, FP_T_EMPTY);
             while (a_wait <= a_item + q + 2) {
-                FWP(&a_full[a_wait % C::NR1], (a_wait / C::NR1) & 1, 26, 1);
+                FWP(&a_full[a_wait % C::NR1], (a_wait / C::NR1) & 1, 26, FP_A_FULL);
                 ++a_wait;
             }
+            if (FPROF_ON) ++prof_acc[FP_ROWS];
             tc_fence_after();
             uint32_t arow[3];
             #pragma unroll
@@ -344,8 +397,9 @@ __global__ void __launch_bounds__(FusedCfg::NTHREADS, 1) conv_fused_mid_kernel(c
             const uint32_t d = tmem_base + ts * C::TCOLS;
             #pragma unroll
             for (int sp = 0; sp < C::NSTG; ++sp) {
-                FWP(&b_full[bst], bpar, 27, 2);
+                FWP(&b_full[bst], bpar, 27, FP_B_FULL_S1);
                 tc_fence_after();
+                const long long ti0 = FPROF_ON ? clock64() : 0;
                 if (elect_one()) {
                     #pragma unroll
                     for (int tt = 0; tt < C::TPS; ++tt) {
@@ -364,6 +418,7 @@ __global__ void __launch_bounds__(FusedCfg::NTHREADS, 1) conv_fused_mid_kernel(c
                     commit(&b_empty[bst]);
                 }
                 __syncwarp();
+                if (FPROF_ON) prof_acc[FP_ISSUE_S1] += clock64() - ti0;
                 if (++bst == C::NB) { bst = 0; bpar ^= 1; }
             }
             if (elect_one()) {
@@ -380,8 +435,8 @@ __global__ void __launch_bounds__(FusedCfg::NTHREADS, 1) conv_fused_mid_kernel(c
         auto s2 = [&](int r) {
             const uint32_t ts = (c1_item + r + 1) % C::NT;
             while (l2_wait <= c1_item + r + 2) {
-                if (PAIR) wait_epi(&l2_full[l2_wait % C::NR2], (l2_wait / C::NR2) & 1, 28);
-                else FWP(&l2_full[l2_wait % C::NR2], (l2_wait / C::NR2) & 1, 28, 3);
+                if (PAIR) FWPC(&l2_full[l2_wait % C::NR2], (l2_wait / C::NR2) & 1, 28, FP_L2_FULL);
+                else FWP(&l2_full[l2_wait % C::NR2], (l2_wait / C::NR2) & 1, 28, FP_L2_FULL);
                 ++l2_wait;
             }
             tc_fence_after();
@@ -391,8 +446,9 @@ __global__ void __launch_bounds__(FusedCfg::NTHREADS, 1) conv_fused_mid_kernel(c
             const uint32_t d = tmem_base + ts * C::TCOLS + 32;
             #pragma unroll
             for (int sp = 0; sp < C::NSTG; ++sp) {
-                FWP(&b_full[bst], bpar, 29, 4);
+                FWP(&b_full[bst], bpar, 29, FP_B_FULL_S2);
                 tc_fence_after();
+                const long long ti0 = FPROF_ON ? clock64() : 0;
                 if (elect_one()) {
                     #pragma unroll
                     for (int tt = 0; tt < C::TPS; ++tt) {
@@ -412,6 +468,7 @@ __global__ void __launch_bounds__(FusedCfg::NTHREADS, 1) conv_fused_mid_kernel(c
                     commit(&b_empty[bst]);
                 }
                 __syncwarp();
+                if (FPROF_ON) prof_acc[FP_ISSUE_S2] += clock64() - ti0;
                 if (++bst == C::NB) { bst = 0; bpar ^= 1; }
             }
             if (elect_one()) {
@@ -435,11 +492,9 @@ __global__ void __launch_bounds__(FusedCfg::NTHREADS, 1) conv_fused_mid_kernel(c
             c1_item += ns1;
             a_item += w.n + 4;
         }
-        if (DBG && p.prof && lane == 0) {
-            long long* dst = p.prof + (size_t)blockIdx.x * 8;
-            for (int i = 0; i < 5; ++i) dst[i] = prof_acc[i];
-            dst[7] = clock64() - prof_t0;
-        }
+        if (FPROF_ON) prof_acc[FP_MMA_TOTAL] = clock64() - prof_t0;
+        FPROF_FLUSH(FP_T_EMPTY, FP_MMA_TOTAL - FP_T_EMPTY + 1);
+        FPROF_FLUSH(FP_ROWS, 1);
         }  // leader
     } else if (warp >= 4 && warp < 8) {
         // ===== E1: l2pre (+ P2) -> l2 row in the shared-memory ring =====
@@ -447,11 +502,12 @@ __global__ void __launch_bounds__(FusedCfg::NTHREADS, 1) conv_fused_mid_kernel(c
         const int m = ew * 32 + lane;            // MMA row = l2 ring pixel index
         const uint32_t sL_u = smem_u32(sL), sP2_u = smem_u32(sP2);
         uint32_t c = 0;
+        const long long prof_t0 = FPROF_ON ? clock64() : 0;
         while (fitem_next<PAIR>(p, cur, end, rank, w)) {
             for (int q = 0; q < w.n + 2; ++q, ++c) {
                 const uint32_t ts = c % C::NT, ls = c % C::NR2;
                 const int y = w.y_b - 1 + q, px = w.x0 - 1 + m;
-                FW(&t1_full[ts], (c / C::NT) & 1, 30);
+                FWP(&t1_full[ts], (c / C::NT) & 1, 30, FP_E1_T1_FULL);
                 tc_fence_after();
                 uint32_t raw[32];
                 tmem_ld_32x32(tmem_base + ((uint32_t)(ew * 32) << 16) + ts * C::TCOLS, raw);
@@ -459,7 +515,7 @@ __global__ void __launch_bounds__(FusedCfg::NTHREADS, 1) conv_fused_mid_kernel(c
                 float v[32];
                 #pragma unroll
                 for (int k = 0; k < 32; ++k) v[k] = __uint_as_float(raw[k]);
-                FW(p2_full, c & 1, 31);
+                FWP(p2_full, c & 1, 31, FP_E1_P2_FULL);
                 epi_add_partial_tile(v, sP2_u, m);
                 __syncwarp();
                 if (lane == 0) mbar_arrive(p2_empty);
@@ -488,7 +544,7 @@ __global__ void __launch_bounds__(FusedCfg::NTHREADS, 1) conv_fused_mid_kernel(c
                     if (!valid) { hi[i] = 0u; mid[i] = 0u; }
                 }
                 // the MMAs that read the previous occupant of this ring slot must have completed
-                FW(&l2_empty[ls], ((c / C::NR2) & 1) ^ 1, 32);
+                FWP(&l2_empty[ls], ((c / C::NR2) & 1) ^ 1, 32, FP_E1_L2_EMPTY);
                 const uint32_t row = sL_u + ls * C::SLOT + m * 128;
                 const uint32_t sw = m & 7;
                 #pragma unroll
@@ -509,6 +565,8 @@ __global__ void __launch_bounds__(FusedCfg::NTHREADS, 1) conv_fused_mid_kernel(c
                 }
             }
         }
+        if (FPROF_ON) prof_acc[FP_E1_TOTAL] = clock64() - prof_t0;
+        if (warp == 4) FPROF_FLUSH(FP_E1_T1_FULL, 4);
     } else if (warp >= 8 && warp < 12) {
         // ===== E2: T[32:64] (+ P3) -> l3;  T[64:96] -> E =====
         // This warp's lanes are pixels xl .. xl+31 with xl = x0-1+32*ew; the strip's outputs are lanes 1..124, so
@@ -519,6 +577,7 @@ __global__ void __launch_bounds__(FusedCfg::NTHREADS, 1) conv_fused_mid_kernel(c
         const int bx = ew == 0 ? 1 : ew == 3 ? 2 : 0;     // tensor maps with 32 / 31 / 29 pixel boxes
         const int srow = ew == 0 ? lane - 1 : lane;       // staging row of this lane (-1: not stored)
         uint32_t c1_item = 0, c2 = 0;
+        const long long prof_t0 = FPROF_ON ? clock64() : 0;
         while (fitem_next<PAIR>(p, cur, end, rank, w)) {
             const int xl = w.x0 - 1 + ew * 32;
             const int xs = ew == 0 ? w.x0 : xl;            // first pixel this warp stores
@@ -527,7 +586,7 @@ __global__ void __launch_bounds__(FusedCfg::NTHREADS, 1) conv_fused_mid_kernel(c
                 const uint32_t ts = (c1_item + r + 1) % C::NT;
                 const int y = w.y_b + r;
                 const bool live = live_x && y < w.y_e;   // (pair: the peer's padding rows are computed, not stored)
-                FW(&t2_full[c2 % C::NT], (c2 / C::NT) & 1, 33);
+                FWP(&t2_full[c2 % C::NT], (c2 / C::NT) & 1, 33, FP_E2_T2_FULL);
                 tc_fence_after();
                 const uint32_t trow = tmem_base + ((uint32_t)(ew * 32) << 16) + ts * C::TCOLS;
                 uint32_t raw[32];
@@ -545,13 +604,17 @@ __global__ void __launch_bounds__(FusedCfg::NTHREADS, 1) conv_fused_mid_kernel(c
                         for (int i = 0; i < 8; ++i) dst[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
                     }
                 }
-                FW(p3_full, c2 & 1, 34);
+                FWP(p3_full, c2 & 1, 34, FP_E2_P3_FULL);
                 epi_add_partial_tile(v, sP3_u, ew * 32 + lane);
                 __syncwarp();
                 if (lane == 0) mbar_arrive(p3_empty);
                 if (live) {
-                    if (elect_one()) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-                    __syncwarp();
+                    {
+                        const long long t0s = FPROF_ON ? clock64() : 0;
+                        if (elect_one()) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                        __syncwarp();
+                        if (FPROF_ON) prof_acc[FP_E2_STORE_READ] += clock64() - t0s;
+                    }
                     if (srow >= 0) epi_split_to_stage(p.g_l3, v, stage, srow);
                     fence_proxy_async_smem();
                     __syncwarp();
@@ -569,8 +632,12 @@ __global__ void __launch_bounds__(FusedCfg::NTHREADS, 1) conv_fused_mid_kernel(c
                 #pragma unroll
                 for (int k = 0; k < 32; ++k) v[k] = __uint_as_float(raw[k]);
                 if (live) {
-                    if (elect_one()) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-                    __syncwarp();
+                    {
+                        const long long t0s = FPROF_ON ? clock64() : 0;
+                        if (elect_one()) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                        __syncwarp();
+                        if (FPROF_ON) prof_acc[FP_E2_STORE_READ] += clock64() - t0s;
+                    }
                     if (srow >= 0) epi_raw_to_stage(v, stage, srow);
                     fence_proxy_async_smem();
                     __syncwarp();
@@ -590,6 +657,8 @@ __global__ void __launch_bounds__(FusedCfg::NTHREADS, 1) conv_fused_mid_kernel(c
             }
             c1_item += w.n + 2;
         }
+        if (FPROF_ON) prof_acc[FP_E2_TOTAL] = clock64() - prof_t0;
+        if (warp == 8) FPROF_FLUSH(FP_E2_T2_FULL, 4);
         if (elect_one()) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     }
     tc_fence_before();
@@ -605,5 +674,7 @@ __global__ void __launch_bounds__(FusedCfg::NTHREADS, 1) conv_fused_mid_kernel(c
 
 #undef FW
 #undef FWP
+#undef FWPC
+#undef FPROF_FLUSH
 
 }  // namespace rsr

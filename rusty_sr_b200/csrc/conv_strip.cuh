@@ -702,13 +702,13 @@ __global__ void __launch_bounds__(C::NTHREADS, 1) conv_strip_kernel(const __grid
     }
     if (RSR_PROF_ON && lane == 0 && (warp < 5)) {
         // row per CTA: [warp0: a_empty] [warp1: t_empty a_full b_full p_full] [warp2: p_empty] [warp3: b_empty]
-        //              [warp4: t_full store_read] [15: total cycles]
+        //              [warp4: t_full store_read] [9: MMA issue blocks] [10: epilogue busy] [11: warp4 p_full] [15: total cycles]
         long long* dst = p.prof + (size_t)blockIdx.x * 16;
         const int base = warp == 0 ? 0 : warp == 1 ? 1 : warp == 2 ? 5 : warp == 3 ? 6 : 7;
         const int n = warp == 1 ? 4 : warp == 4 ? 2 : 1;
         for (int i = 0; i < n; ++i) dst[base + i] = prof_acc[i];
         if (warp == 1) { dst[9] = prof_acc[4]; dst[15] = clock64() - prof_t0; }
-        if (warp == 4) dst[10] = prof_acc[2];
+        if (warp == 4) { dst[10] = prof_acc[2]; dst[11] = prof_acc[3]; }
     }
     tc_fence_before();
     __syncthreads();

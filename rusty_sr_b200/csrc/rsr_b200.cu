@@ -83,7 +83,13 @@ static Layout make_layout(int factor) {
 
 // --------------------------------------------------------------------------- kernel configs
 //                      KH KW  RB NG R NR TPS NBS NPIN NOUT SHUF NEPI
-using Cfg0 = ConvCfg<5, 1,  64, 1, 4, 12, 5, 2, 0, 2, false, 8>;  // conv0 on the x-im2col'd input (K = 5 taps x 16)
+#ifndef RSR_CFG0_R
+#define RSR_CFG0_R 4
+#endif
+#ifndef RSR_CFG0_NR
+#define RSR_CFG0_NR 12
+#endif
+using Cfg0 = ConvCfg<5, 1,  64, 1, RSR_CFG0_R, RSR_CFG0_NR, 5, 2, 0, 2, false, 8>;  // conv0 on the x-im2col'd input (K = 5 taps x 16)
 #ifndef RSR_CFG1_NR
 #define RSR_CFG1_NR 7
 #endif
@@ -97,9 +103,63 @@ using Cfg0 = ConvCfg<5, 1,  64, 1, 4, 12, 5, 2, 0, 2, false, 8>;  // conv0 on th
 #define RSR_L2PROMO CU_TENSOR_MAP_L2_PROMOTION_L2_256B
 #endif
 using Cfg1 = ConvCfg<5, 5, 128, 3, 2, RSR_CFG1_NR, RSR_CFG1_TPS, RSR_CFG1_NBS, 0, 2, false>;  // f  -> conv1 | conv2 | conv3
-using Cfg2 = ConvCfg<3, 3, 128, 3, 2,  5, 2, 3, 2, 2, false, 8>;  // l1 -> conv5 | conv6 | conv7   (+ P2, P3)
-using Cfg3 = ConvCfg<3, 3, 128, 2, 2,  5, 2, 3, 3, 2, false>;  // l2 -> conv8 | conv9           (+ P3, E)
-using Cfg4 = ConvCfg<3, 3, 128, 1, 2,  6, 3, 3, 3, 2, true, 8>;  // l3 -> conv10 (+ E) + expand + bilinear skip
+// Ring geometry of the 3x3 launches, overridable at build time for same-box A/B runs (tools/ab_build.sh, tools/ab.sh):
+// rows per pass R, input-row slots NR, taps per weight stage TPS, weight stages NBS, partial-sum tile slots NPIN.
+#ifndef RSR_CFG2_R
+#define RSR_CFG2_R 2
+#endif
+#ifndef RSR_CFG2_NR
+#define RSR_CFG2_NR 5
+#endif
+#ifndef RSR_CFG2_TPS
+#define RSR_CFG2_TPS 2
+#endif
+#ifndef RSR_CFG2_NBS
+#define RSR_CFG2_NBS 3
+#endif
+#ifndef RSR_CFG2_NPIN
+#define RSR_CFG2_NPIN 2
+#endif
+#define RSR_CFG2_GEOM RSR_CFG2_R, RSR_CFG2_NR, RSR_CFG2_TPS, RSR_CFG2_NBS, RSR_CFG2_NPIN
+#ifndef RSR_CFG3_R
+#define RSR_CFG3_R 2
+#endif
+#ifndef RSR_CFG3_NR
+#define RSR_CFG3_NR 5
+#endif
+#ifndef RSR_CFG3_TPS
+#define RSR_CFG3_TPS 2
+#endif
+#ifndef RSR_CFG3_NBS
+#define RSR_CFG3_NBS 3
+#endif
+#ifndef RSR_CFG3_NPIN
+#define RSR_CFG3_NPIN 3
+#endif
+#define RSR_CFG3_GEOM RSR_CFG3_R, RSR_CFG3_NR, RSR_CFG3_TPS, RSR_CFG3_NBS, RSR_CFG3_NPIN
+#ifndef RSR_CFG4_R
+#define RSR_CFG4_R 2
+#endif
+#ifndef RSR_CFG4_NR
+#define RSR_CFG4_NR 6
+#endif
+#ifndef RSR_CFG4_TPS
+#define RSR_CFG4_TPS 3
+#endif
+#ifndef RSR_CFG4_NBS
+#define RSR_CFG4_NBS 3
+#endif
+#ifndef RSR_CFG4_NPIN
+#define RSR_CFG4_NPIN 3
+#endif
+#define RSR_CFG4_GEOM RSR_CFG4_R, RSR_CFG4_NR, RSR_CFG4_TPS, RSR_CFG4_NBS, RSR_CFG4_NPIN
+#ifndef RSR_CFG3_NEPI
+#define RSR_CFG3_NEPI 4
+#endif
+//                                   R NR TPS NBS NPIN
+using Cfg2 = ConvCfg<3, 3, 128, 3, RSR_CFG2_GEOM, 2, false, 8>;  // l1 -> conv5 | conv6 | conv7   (+ P2, P3)
+using Cfg3 = ConvCfg<3, 3, 128, 2, RSR_CFG3_GEOM, 2, false, RSR_CFG3_NEPI>;  // l2 -> conv8 | conv9           (+ P3, E)
+using Cfg4 = ConvCfg<3, 3, 128, 1, RSR_CFG4_GEOM, 2, true, 8>;  // l3 -> conv10 (+ E) + expand + bilinear skip
 
 #ifndef RSR_DEFAULT_PAIR_MASK
 #define RSR_DEFAULT_PAIR_MASK 4   // conv1|2|3 (launch index 2) on CTA pairs: -12..18 % on that launch, measured; the 3x3 launches are slower on pairs
@@ -201,7 +261,8 @@ struct rsr_ctx {
     DevBuf xcol, xf4, actA, actB, partA, partB, partC, out_f32, out_u8, in_stage;
     bool fused_mid = false;     // conv5|6|7 + conv8|9 in one launch (conv_fused.cuh); RSR_FLAG_FUSED_MID
     int pair_mask = 0;          // bit k: launch index k (1 = conv0 .. 5 = conv10) runs as CTA pairs (conv_pair.cuh)
-    int fused_dbg = 0;          // test hook rsr_debug_fused: bit 0 skip S2 MMAs, bit 1 dump l2 / raw accumulators, bit 2 profile
+    int fused_dbg = 0;          // test hook rsr_debug_fused: bit 0 skip S2 MMAs, bit 1 dump l2 / raw accumulators, bit 2 profile (debug kernel),
+                                // bit 3 profile of the plan's own kernel (single CTA or pair; needs a -DRSR_FUSED_PROF=1 build)
     DevBuf dbg_l2, dbg_t3, dbg_prof;
     int* fault = nullptr;       // device alias of fault_host (mapped pinned memory: readable after a kernel trap)
     int* fault_host = nullptr;  // [0] = code, [4 + 4*warp ..] = which barrier each warp role was stuck on
@@ -626,7 +687,7 @@ static int forward_device(rsr_ctx* c, const void* d_in, bool u8, int in_ch, int 
         if (int rc = in_map(&q.tmA, l1_act, 128)) return rc;
         // the fused launch runs on CTA pairs when launch index 3 is in the pair mask (half-tap weight boxes);
         // the debug hooks exist in the single-CTA debug instantiation only
-        const bool fpair = pair(3) && c->fused_dbg == 0;
+        const bool fpair = pair(3) && (c->fused_dbg & 7) == 0;
         if (int rc = make_map_w(c, &q.tmB1, c->w2, 64, 9 * 96, fpair ? 48 : 96)) return rc;
         if (int rc = make_map_w(c, &q.tmB2, c->w3, 64, 9 * 64, fpair ? 32 : 64)) return rc;
         if (int rc = part_map(&q.tmP2, P2, 128)) return rc;
@@ -648,9 +709,9 @@ static int forward_device(rsr_ctx* c, const void* d_in, bool u8, int in_ch, int 
             q.dbg_l2 = (float*)c->dbg_l2.p;
             q.dbg_t3 = (float*)c->dbg_t3.p;
         }
-        if (c->fused_dbg & 4) {
-            if (int rc = ensure(c->dbg_prof, 256 * 8 * sizeof(long long))) return rc;
-            CUDA_TRY(cudaMemsetAsync(c->dbg_prof.p, 0, 256 * 8 * sizeof(long long), c->stream));
+        if (c->fused_dbg & (4 | 8)) {
+            if (int rc = ensure(c->dbg_prof, 256 * FPROF_N * sizeof(long long))) return rc;
+            CUDA_TRY(cudaMemsetAsync(c->dbg_prof.p, 0, 256 * FPROF_N * sizeof(long long), c->stream));
             q.prof = (long long*)c->dbg_prof.p;
         }
         if (fpair) {
@@ -668,7 +729,7 @@ static int forward_device(rsr_ctx* c, const void* d_in, bool u8, int in_ch, int 
             CUDA_TRY(cudaLaunchKernelEx(&cfg, conv_fused_mid_kernel<false, true>, q));
         } else {
             const int grid = (int)std::min<long long>(q.total_rowtiles, c->num_sms);
-            if (c->fused_dbg) conv_fused_mid_kernel<true, false><<<grid, FusedCfg::NTHREADS, FusedCfg::SMEM_BYTES, c->stream>>>(q);
+            if (c->fused_dbg & 7) conv_fused_mid_kernel<true, false><<<grid, FusedCfg::NTHREADS, FusedCfg::SMEM_BYTES, c->stream>>>(q);
             else conv_fused_mid_kernel<false, false><<<grid, FusedCfg::NTHREADS, FusedCfg::SMEM_BYTES, c->stream>>>(q);
         }
         CUDA_TRY(cudaGetLastError());
@@ -903,12 +964,12 @@ extern "C" int rsr_debug_fused(rsr_ctx* c, int flags) {
     c->fused_dbg = flags;
     return 0;
 }
-// [grid][8] wait-cycle counters of the fused launch's MMA warp (t_empty, a_full, b_full S1, l2_full, b_full S2, -, -, total)
+// [grid][32] wait-cycle counters of every warp role of the fused launch (slot names: FP_* in conv_fused.cuh)
 extern "C" int rsr_debug_read_fused_profile(rsr_ctx* c, long long* out, int cap_rows) {
     if (!c || !out || !c->dbg_prof.p) return fail(RSR_E_BAD_ARG, "fused profile not enabled");
     if (int rc = rsr_synchronize(c)) return rc;
     const int rows = cap_rows < 256 ? cap_rows : 256;
-    CUDA_TRY(cudaMemcpy(out, c->dbg_prof.p, sizeof(long long) * rows * 8, cudaMemcpyDeviceToHost));
+    CUDA_TRY(cudaMemcpy(out, c->dbg_prof.p, sizeof(long long) * rows * FPROF_N, cudaMemcpyDeviceToHost));
     return rows;
 }
 

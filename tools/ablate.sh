@@ -9,7 +9,7 @@ if [ "$1" = "build" ]; then
   for v in $VARIANTS; do
     $NV -DRSR_ABL=$v -o build/abl/librsr_b200_abl$v.so rusty_sr_b200/csrc/rsr_b200.cu -lcudart &
   done
-  $NV -DRSR_PROFILE=1 -o build/abl/librsr_b200_prof.so rusty_sr_b200/csrc/rsr_b200.cu -lcudart &
+  $NV -DRSR_PROFILE=1 -DRSR_FUSED_PROF=1 -o build/abl/librsr_b200_prof.so rusty_sr_b200/csrc/rsr_b200.cu -lcudart &
   wait; ls build/abl
 else
   for v in $VARIANTS; do

@@ -1,5 +1,5 @@
 """GPU diagnostic for the fused middle launch: compares its l2 ring rows and raw accumulators with the oracle
-(test hooks rsr_debug_fused / rsr_debug_read_node 5, 6) and prints the MMA warp's wait-cycle profile."""
+(test hooks rsr_debug_fused / rsr_debug_read_node 5, 6) and prints the wait-cycle profile of every warp role (--profile / --profile-plan / --profile-only)."""
 import os
 import sys
 
@@ -64,25 +64,48 @@ def check(params, x, label):
     up.close()
 
 
-def profile():
+FP_NAMES = ["a_empty(l1 producer)", "b_empty(weight producer)", "p2_empty(P2 producer)", "p3_empty(P3 producer)",
+            "t_empty(mma)", "a_full(mma)", "b_full S1(mma)", "l2_full(mma)", "b_full S2(mma)", "ISSUE S1(mma)",
+            "ISSUE S2(mma)", "TOTAL(mma)", "t1_full(E1)", "p2_full(E1)", "l2_empty(E1)", "TOTAL(E1)", "t2_full(E2)",
+            "p3_full(E2)", "store_read(E2)", "TOTAL(E2)", "S1 rows"]
+
+
+def profile(mode=4):
+    """mode 4: the single-CTA debug kernel (any build).  mode 8: the plan's own kernel, single CTA or CTA pair
+    (RSR_B200_PAIR bit 3), in a library built with -DRSR_FUSED_PROF=1 (tools/ablate.sh; RSR_B200_LIB selects it)."""
     up = R.Upscaler(parameters="imagenet", flags=R.RSR_FLAG_FUSED_MID)
     x = noise_image(1080, 1920, 1234)
     up.forward(x)
-    up.debug_fused(4)
+    up.debug_fused(mode)
     up.forward(x)
-    pr = up.debug_read_fused_profile()[:148].astype(np.float64)
-    names = ["t_empty", "a_full", "b_full(S1)", "l2_full", "b_full(S2)"]
-    tot = pr[:, 7].mean()
-    print("fused MMA-warp wait profile (mean cycles per CTA, % of total):", f"total {tot:.0f}")
-    for i, n in enumerate(names):
-        print(f"   {n:12s} {pr[:, i].mean():10.0f}  {100 * pr[:, i].mean() / tot:5.1f} %")
+    pr = up.debug_read_fused_profile().astype(np.float64)
+    # pair plan: only the leader CTA of a cluster runs the MMA role; every CTA runs the others
+    mma_rows = pr[pr[:, 11] > 0]
+    all_rows = pr[pr[:, 15] > 0]
+    if not len(mma_rows):
+        print("fused profile: no counters (library built without -DRSR_FUSED_PROF=1?)", up.plan())
+        up.close()
+        return
+    tot = mma_rows[:, 11].mean()
+    rows = mma_rows[:, 20].mean()
+    print(f"fused wait profile, mode {mode}, plan: {up.plan()}")
+    print(f"  CTAs {len(all_rows)} (MMA role in {len(mma_rows)}); MMA-role cycles/CTA {tot:.0f}; S1 rows/CTA {rows:.1f};"
+          f" cycles per S1 row {tot / rows:.0f}")
+    for i, n in enumerate(FP_NAMES[:20]):
+        src = mma_rows if 4 <= i <= 11 else all_rows
+        print(f"   {n:26s} {src[:, i].mean():10.0f}  {100 * src[:, i].mean() / tot:5.1f} %   (max CTA {src[:, i].max():10.0f})")
     print("   kernel ms:", up.last_kernel_times_ms())
     up.close()
 
 
 if __name__ == "__main__":
+    if "--profile-only" in sys.argv:
+        profile(8)
+        sys.exit(0)
     P = {k: R.load_builtin_params(k) for k in R.BUILTIN_PARAMETERS}
     check(P["anime"], O.img_to_data(load_png("cartoon_lr")), "cartoon 84x120")
     check(P["imagenet"], noise_image(40, 300, 5), "noise 300x40")
     if "--profile" in sys.argv:
-        profile()
+        profile(4)
+    if "--profile-plan" in sys.argv:
+        profile(8)
