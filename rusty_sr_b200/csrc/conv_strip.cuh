@@ -44,7 +44,20 @@
 #define ABL_NO_EPI_OUT (RSR_ABL & 16)   // epilogue: TMEM load only, no math / staging / store
 #define ABL_NO_PIN_MMA (RSR_ABL & 32)   // partial-sum fold MMAs skipped
 
+// EPI_SHUFFLE output: 1 = the three 1152-byte (f32) / 384-byte (RGBA u8) output-row segments of a 32-pixel tile leave
+// the staging tile as bulk async copies (cp.async.bulk.global.shared::cta) issued by one lane; 0 = float4 / u32 stores
+// by the whole warp.  Build-time A/B switch (tools/ab_build.sh).
+#ifndef RSR_SHUF_BULK
+#define RSR_SHUF_BULK 0
+#endif
+
 namespace rsr {
+
+// shared memory -> global memory bulk copy (16-byte aligned, size a multiple of 16), tracked by the bulk async-group
+__device__ __forceinline__ void bulk_store(void* gdst, uint32_t ssrc, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(reinterpret_cast<uint64_t>(gdst)), "r"(ssrc), "r"(bytes)
+                 : "memory");
+}
 
 // What happens to one 32-column group of the accumulator.
 enum EpiKind : int {
@@ -325,7 +338,7 @@ __global__ void __launch_bounds__(C::NTHREADS, 1) conv_strip_kernel(const __grid
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
-    long long prof_acc[6] = {0, 0, 0, 0, 0, 0};
+    long long prof_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     const long long prof_t0 = RSR_PROF_ON ? clock64() : 0;
 
     // which groups fold a partial sum (uniform per launch)
@@ -589,8 +602,10 @@ __global__ void __launch_bounds__(C::NTHREADS, 1) conv_strip_kernel(const __grid
                             continue;
                         }
                         uint32_t raw[32];
+                        const long long tl0 = RSR_PROF_ON ? clock64() : 0;
                         tmem_ld_32x32(tmem_base + ((uint32_t)(ew * 32) << 16) + buf * (C::R * C::NCOL) + r * C::NCOL + g * 32, raw);
                         tmem_ld_wait();
+                        if (RSR_PROF_ON) prof_acc[5] += clock64() - tl0;
                         float v[32];
                         #pragma unroll
                         for (int k = 0; k < 32; ++k) v[k] = __uint_as_float(raw[k]);
@@ -602,6 +617,7 @@ __global__ void __launch_bounds__(C::NTHREADS, 1) conv_strip_kernel(const __grid
                             if (++pst == NPB) { pst = 0; ppar ^= 1; }
                         }
                         if (ABL_NO_EPI_OUT) { if (v[0] == 123.456f && p.out_f32) p.out_f32[0] = v[1]; ++oc; continue; }
+                        const long long to0 = RSR_PROF_ON ? clock64() : 0;
                         const uint32_t stage = stage0 + (oc % C::NOUT) * 4096;
                         // the staging tile used NOUT stores ago must have been read out by the TMA engine
                         {
@@ -652,8 +668,18 @@ __global__ void __launch_bounds__(C::NTHREADS, 1) conv_strip_kernel(const __grid
                                 for (int dy = 0; dy < 3; ++dy)
                                     #pragma unroll
                                     for (int k = 0; k < 9; ++k) sf[dy * 288 + lane * 9 + k] = o[dy][k];
-                                __syncwarp();
                                 const int nfl = npx_valid * 9;
+                                if (RSR_SHUF_BULK && npx_valid == 32 && p.out_vec_ok) {
+                                    fence_proxy_async_smem();
+                                    __syncwarp();
+                                    if (elect_one()) {
+                                        #pragma unroll
+                                        for (int dy = 0; dy < 3; ++dy)
+                                            bulk_store(p.out_f32 + (orow0 + (size_t)dy * W3) * 3, smem_u32(sf + dy * 288), 1152);
+                                        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                                    }
+                                } else {
+                                __syncwarp();
                                 #pragma unroll
                                 for (int dy = 0; dy < 3; ++dy) {
                                     float* dst = p.out_f32 + (orow0 + (size_t)dy * W3) * 3;
@@ -663,6 +689,7 @@ __global__ void __launch_bounds__(C::NTHREADS, 1) conv_strip_kernel(const __grid
                                     } else {
                                         for (int i = lane; i < nfl; i += 32) dst[i] = sf[dy * 288 + i];
                                     }
+                                }
                                 }
                             }
                             if (p.out_u8) {
@@ -678,16 +705,28 @@ __global__ void __launch_bounds__(C::NTHREADS, 1) conv_strip_kernel(const __grid
                                         const uint32_t b8 = (uint32_t)(fminf(fmaxf(o[dy][dx * 3 + 2], 0.f), 1.f) * 255.0f + 0.5f);
                                         sq[dy * 96 + lane * 3 + dx] = r8 | (g8 << 8) | (b8 << 16) | 0xFF000000u;
                                     }
-                                __syncwarp();
                                 const int nu = npx_valid * 3;
-                                #pragma unroll
-                                for (int dy = 0; dy < 3; ++dy) {
-                                    uint32_t* dst = reinterpret_cast<uint32_t*>(p.out_u8) + orow0 + (size_t)dy * W3;
-                                    for (int i = lane; i < nu; i += 32) dst[i] = sq[dy * 96 + i];
+                                if (RSR_SHUF_BULK && npx_valid == 32 && (p.W & 3) == 0 && (reinterpret_cast<uintptr_t>(p.out_u8) & 15) == 0) {
+                                    fence_proxy_async_smem();
+                                    __syncwarp();
+                                    if (elect_one()) {
+                                        #pragma unroll
+                                        for (int dy = 0; dy < 3; ++dy)
+                                            bulk_store(reinterpret_cast<uint32_t*>(p.out_u8) + orow0 + (size_t)dy * W3, smem_u32(sq + dy * 96), 384);
+                                        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                                    }
+                                } else {
+                                    __syncwarp();
+                                    #pragma unroll
+                                    for (int dy = 0; dy < 3; ++dy) {
+                                        uint32_t* dst = reinterpret_cast<uint32_t*>(p.out_u8) + orow0 + (size_t)dy * W3;
+                                        for (int i = lane; i < nu; i += 32) dst[i] = sq[dy * 96 + i];
+                                    }
                                 }
                             }
                             __syncwarp();
                         }
+                        if (RSR_PROF_ON) prof_acc[6] += clock64() - to0;
                         ++oc;
                     }
                 }
@@ -702,13 +741,14 @@ __global__ void __launch_bounds__(C::NTHREADS, 1) conv_strip_kernel(const __grid
     }
     if (RSR_PROF_ON && lane == 0 && (warp < 5)) {
         // row per CTA: [warp0: a_empty] [warp1: t_empty a_full b_full p_full] [warp2: p_empty] [warp3: b_empty]
-        //              [warp4: t_full store_read] [9: MMA issue blocks] [10: epilogue busy] [11: warp4 p_full] [15: total cycles]
+        //              [warp4: t_full store_read] [9: MMA issue blocks] [10: epilogue busy] [11: warp4 p_full] [12: warp4 tcgen05.ld + wait]
+        //              [13: warp4 output path: math, staging, store issue (store_read wait included)] [15: total cycles]
         long long* dst = p.prof + (size_t)blockIdx.x * 16;
         const int base = warp == 0 ? 0 : warp == 1 ? 1 : warp == 2 ? 5 : warp == 3 ? 6 : 7;
         const int n = warp == 1 ? 4 : warp == 4 ? 2 : 1;
         for (int i = 0; i < n; ++i) dst[base + i] = prof_acc[i];
         if (warp == 1) { dst[9] = prof_acc[4]; dst[15] = clock64() - prof_t0; }
-        if (warp == 4) { dst[10] = prof_acc[2]; dst[11] = prof_acc[3]; }
+        if (warp == 4) { dst[10] = prof_acc[2]; dst[11] = prof_acc[3]; dst[12] = prof_acc[5]; dst[13] = prof_acc[6]; }
     }
     tc_fence_before();
     __syncthreads();

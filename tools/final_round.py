@@ -23,6 +23,12 @@ def left():
     return BUDGET - (time.time() - T0)
 
 
+def save():
+    summary["elapsed_s"] = round(time.time() - T0, 1)
+    with open(os.path.join(OUT, "final_round_summary.json"), "w") as f:
+        json.dump(summary, f, indent=1)
+
+
 def run(name, cmd, timeout, env=None, out=None):
     """Runs cmd (list) with a timeout clipped to the remaining budget; returns (rc, stdout)."""
     t = min(timeout, left() - 5)
@@ -51,6 +57,7 @@ def run(name, cmd, timeout, env=None, out=None):
                 f.write(se)
     summary["stages"][name] = {"rc": rc, "s": round(time.time() - t1, 1)}
     print(f"[{name}] rc={rc} {time.time() - t1:.1f}s (left {left():.0f}s)", flush=True)
+    save()
     return rc, so
 
 
@@ -105,11 +112,11 @@ def main():
     libs = sorted(f for f in os.listdir(ABL) if f.endswith(".so") and f[:2] in LAUNCH_OF) if os.path.isdir(ABL) else []
     base_lib = os.path.join(ABL, "base.so")
     times = {n: [] for n in ["base.so"] + libs}
-    for rnd in range(3):
-        if left() < 150 and rnd > 0:   # keep time for the combined-library check
+    for rnd in range(2):
+        if left() < 200 and rnd > 0:   # keep time for the combined-library check
             break
         for n in ["base.so"] + libs:
-            if left() < 130:
+            if left() < 150:
                 break
             us = ab_step(os.path.join(ABL, n))
             if us:
@@ -127,10 +134,11 @@ def main():
             gain = 1.0 - v / bmean[launch]
             ab[n] = {"launch": launch, "us": round(v, 1), "base_us": round(bmean[launch], 1), "gain": round(gain, 4), "runs": len(times[n])}
             print(f"    {n:14s} {launch:20s} {v:7.1f} us vs {bmean[launch]:7.1f}  gain {100 * gain:+.1f} %  ({len(times[n])} runs)", flush=True)
-            if gain > 0.015 and (n[:2] not in winners or gain > winners[n[:2]][1]):
+            if gain > 0.02 and (n[:2] not in winners or gain > winners[n[:2]][1]):
                 winners[n[:2]] = (n, gain)
     summary["ab"] = ab
     summary["winners"] = {k: v[0] for k, v in winners.items()}
+    save()
     # 5. winners combined into one library: must pass the GPU suite and beat the shipped library in bench.py
     if winners and left() > 120:
         flags = []
@@ -156,9 +164,7 @@ def main():
                 if bs and cs:
                     summary["combo_vs_shipped"] = {"shipped_ms": bs, "combo_ms": cs, "gain": round(1 - (sum(cs) / len(cs)) / (sum(bs) / len(bs)), 4)}
                     print("    combo vs shipped:", summary["combo_vs_shipped"], flush=True)
-    summary["elapsed_s"] = round(time.time() - T0, 1)
-    with open(os.path.join(OUT, "final_round_summary.json"), "w") as f:
-        json.dump(summary, f, indent=1)
+    save()
     print(json.dumps(summary), flush=True)
 
 

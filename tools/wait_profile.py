@@ -17,7 +17,7 @@ up.forward(x)
 up.debug_profile(True)
 up.forward(x)
 names = ["a_empty(rowprod)", "t_empty(mma)", "a_full(mma)", "b_full(mma)", "p_full(mma)", "p_empty(pinprod)",
-         "b_empty(wprod)", "t_full(epi)", "store_read(epi)", "MMA_ISSUE_BLOCK(mma)", "EPI_BUSY(epi)", "p_full(epi, inside EPI_BUSY)"]
+         "b_empty(wprod)", "t_full(epi)", "store_read(epi)", "MMA_ISSUE_BLOCK(mma)", "EPI_BUSY(epi)", "p_full(epi, inside EPI_BUSY)", "tmem_ld(epi)", "out_path(epi: math+stage+store issue)"]
 kt = up.last_kernel_times_ms()
 for k, kname in enumerate(list(kt)[1:], start=1):
     prof = up.debug_read_profile(k).astype(np.float64)
