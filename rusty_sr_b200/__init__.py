@@ -15,12 +15,12 @@ from typing import Optional
 import numpy as np
 
 from . import _lib
-from ._lib import RsrError, RSR_FLAG_FUSED_MID, RSR_FLAG_SPLIT_MID
+from ._lib import RsrError, RSR_FLAG_FUSED_MID, RSR_FLAG_SPLIT_MID, RSR_FLAG_NO_PAIRS
 from .network import FACTOR, num_params, param_layout
 from .rsr_format import decode_rsr, encode_rsr
 
 __all__ = ["Upscaler", "upscale", "bilinear", "downsample", "conv2d_3x3", "load_builtin_params", "decode_rsr", "encode_rsr", "RsrError",
-           "num_params", "param_layout", "FACTOR", "BUILTIN_PARAMETERS", "RSR_FLAG_FUSED_MID", "RSR_FLAG_SPLIT_MID"]
+           "num_params", "param_layout", "FACTOR", "BUILTIN_PARAMETERS", "RSR_FLAG_FUSED_MID", "RSR_FLAG_SPLIT_MID", "RSR_FLAG_NO_PAIRS"]
 
 _RES = os.path.join(os.path.dirname(os.path.abspath(__file__)), "res")
 

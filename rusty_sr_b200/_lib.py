@@ -16,6 +16,7 @@ RSR_E_OOM = -4
 RSR_E_UNSUPPORTED = -5
 RSR_FLAG_FUSED_MID = 1   # rsr_create flags (include/rsr_b200.h)
 RSR_FLAG_SPLIT_MID = 2
+RSR_FLAG_NO_PAIRS = 4    # every launch on single CTAs (no cta_group::2 kernels)
 
 # every symbol include/rsr_b200.h declares (checked by tests/test_abi.py)
 EXPORTS = (

@@ -84,10 +84,10 @@ static Layout make_layout(int factor) {
 // --------------------------------------------------------------------------- kernel configs
 //                      KH KW  RB NG R NR TPS NBS NPIN NOUT SHUF NEPI
 #ifndef RSR_CFG0_R
-#define RSR_CFG0_R 4
+#define RSR_CFG0_R 8   // 8 rows per pass: conv0's MMAs are tiny (15 per row), so the per-pass hand-offs dominate; 4 -> 8: -20 % (same-box A/B, r01j)
 #endif
 #ifndef RSR_CFG0_NR
-#define RSR_CFG0_NR 12
+#define RSR_CFG0_NR 16
 #endif
 using Cfg0 = ConvCfg<5, 1,  64, 1, RSR_CFG0_R, RSR_CFG0_NR, 5, 2, 0, 2, false, 8>;  // conv0 on the x-im2col'd input (K = 5 taps x 16)
 #ifndef RSR_CFG1_NR
@@ -241,6 +241,50 @@ __global__ void __launch_bounds__(256) pack_input_kernel(const void* __restrict_
         dst[2] = make_uint4(mid[0], mid[1], mid[2], mid[3]);
         dst[3] = make_uint4(mid[4], mid[5], mid[6], mid[7]);
         xf4[i] = make_float4(v[6], v[7], v[8], 0.f);  // d = 2 is the pixel itself
+    }
+}
+
+// Same result, four threads per pixel: thread part p writes 16-byte chunk p of the pixel's 64-byte xcol row (hi k 0..7,
+// hi k 8..15, mid k 0..7, mid k 8..15), so that one warp store instruction covers 512 contiguous bytes instead of 32
+// 16-byte pieces at a 64-byte stride.  Build-time A/B switch RSR_PACK_V2 (tools/ab_build.sh).
+#ifndef RSR_PACK_V2
+#define RSR_PACK_V2 0
+#endif
+template <bool U8>
+__global__ void __launch_bounds__(256) pack_input_kernel_v2(const void* __restrict__ in, int in_ch, int W, int H,
+                                                             int NIMG, __nv_bfloat16* __restrict__ xcol,
+                                                             float4* __restrict__ xf4) {
+    const size_t nq = (size_t)NIMG * H * W * 4;
+    for (size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x; q < nq; q += (size_t)gridDim.x * blockDim.x) {
+        const size_t i = q >> 2;
+        const int part = (int)(q & 3), half = part & 1;
+        const int x = (int)(i % W);
+        const size_t rowbase = i - x;  // (img*H + y) * W
+        auto load = [&](int xx, int c) -> float {   // channel c of pixel xx of this row, 0 outside the image
+            if (xx < 0 || xx >= W) return 0.f;
+            if (U8) return (float)reinterpret_cast<const uint8_t*>(in)[(rowbase + xx) * in_ch + c] / 255.0f;
+            return reinterpret_cast<const float*>(in)[(rowbase + xx) * 3 + c];
+        };
+        float v[8];
+        #pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int k = 8 * half + j;        // k = d * 3 + c, d = horizontal neighbour 0..4 (k = 15: padding)
+            const int d = (k * 11) >> 5;       // k / 3 for k < 16
+            v[j] = k < 15 ? load(x + d - 2, k - 3 * d) : 0.f;
+        }
+        uint32_t w[4];
+        #pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const __nv_bfloat16 h0 = __float2bfloat16_rn(v[2 * k]), h1 = __float2bfloat16_rn(v[2 * k + 1]);
+            if (part < 2) {
+                w[k] = pack_bf16x2(h0, h1);
+            } else {
+                w[k] = pack_bf16x2(__float2bfloat16_rn(v[2 * k] - __bfloat162float(h0)),
+                                   __float2bfloat16_rn(v[2 * k + 1] - __bfloat162float(h1)));
+            }
+        }
+        reinterpret_cast<uint4*>(xcol)[q] = make_uint4(w[0], w[1], w[2], w[3]);   // chunk order = part order: hi lo, hi hi, mid lo, mid hi
+        if (part == 0) xf4[i] = make_float4(v[6], v[7], load(x, 2), 0.f);        // d = 2 is the pixel itself: k = 6, 7, 8
     }
 }
 
@@ -632,9 +676,15 @@ static int forward_device(rsr_ctx* c, const void* d_in, bool u8, int in_ch, int 
     c->last_launches = 0;
     CUDA_TRY(cudaEventRecord(c->ev[0], c->stream));
     {
+#if RSR_PACK_V2
+        const int blocks = (int)std::min<size_t>((npx * 4 + 255) / 256, (size_t)c->num_sms * 32);
+        if (u8) pack_input_kernel_v2<true><<<blocks, 256, 0, c->stream>>>(d_in, in_ch, w, h, n, xcol, (float4*)c->xf4.p);
+        else    pack_input_kernel_v2<false><<<blocks, 256, 0, c->stream>>>(d_in, 3, w, h, n, xcol, (float4*)c->xf4.p);
+#else
         const int blocks = (int)std::min<size_t>((npx + 255) / 256, (size_t)c->num_sms * 16);
         if (u8) pack_input_kernel<true><<<blocks, 256, 0, c->stream>>>(d_in, in_ch, w, h, n, xcol, (float4*)c->xf4.p);
         else    pack_input_kernel<false><<<blocks, 256, 0, c->stream>>>(d_in, 3, w, h, n, xcol, (float4*)c->xf4.p);
+#endif
         CUDA_TRY(cudaGetLastError());
         c->last_launches++;
     }
