@@ -44,20 +44,7 @@
 #define ABL_NO_EPI_OUT (RSR_ABL & 16)   // epilogue: TMEM load only, no math / staging / store
 #define ABL_NO_PIN_MMA (RSR_ABL & 32)   // partial-sum fold MMAs skipped
 
-// EPI_SHUFFLE output: 1 = the three 1152-byte (f32) / 384-byte (RGBA u8) output-row segments of a 32-pixel tile leave
-// the staging tile as bulk async copies (cp.async.bulk.global.shared::cta) issued by one lane; 0 = float4 / u32 stores
-// by the whole warp.  Build-time A/B switch (tools/ab_build.sh).
-#ifndef RSR_SHUF_BULK
-#define RSR_SHUF_BULK 0
-#endif
-
 namespace rsr {
-
-// shared memory -> global memory bulk copy (16-byte aligned, size a multiple of 16), tracked by the bulk async-group
-__device__ __forceinline__ void bulk_store(void* gdst, uint32_t ssrc, uint32_t bytes) {
-    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(reinterpret_cast<uint64_t>(gdst)), "r"(ssrc), "r"(bytes)
-                 : "memory");
-}
 
 // What happens to one 32-column group of the accumulator.
 enum EpiKind : int {
@@ -668,18 +655,8 @@ __global__ void __launch_bounds__(C::NTHREADS, 1) conv_strip_kernel(const __grid
                                 for (int dy = 0; dy < 3; ++dy)
                                     #pragma unroll
                                     for (int k = 0; k < 9; ++k) sf[dy * 288 + lane * 9 + k] = o[dy][k];
-                                const int nfl = npx_valid * 9;
-                                if (RSR_SHUF_BULK && npx_valid == 32 && p.out_vec_ok) {
-                                    fence_proxy_async_smem();
-                                    __syncwarp();
-                                    if (elect_one()) {
-                                        #pragma unroll
-                                        for (int dy = 0; dy < 3; ++dy)
-                                            bulk_store(p.out_f32 + (orow0 + (size_t)dy * W3) * 3, smem_u32(sf + dy * 288), 1152);
-                                        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-                                    }
-                                } else {
                                 __syncwarp();
+                                const int nfl = npx_valid * 9;
                                 #pragma unroll
                                 for (int dy = 0; dy < 3; ++dy) {
                                     float* dst = p.out_f32 + (orow0 + (size_t)dy * W3) * 3;
@@ -689,7 +666,6 @@ __global__ void __launch_bounds__(C::NTHREADS, 1) conv_strip_kernel(const __grid
                                     } else {
                                         for (int i = lane; i < nfl; i += 32) dst[i] = sf[dy * 288 + i];
                                     }
-                                }
                                 }
                             }
                             if (p.out_u8) {
@@ -705,23 +681,12 @@ __global__ void __launch_bounds__(C::NTHREADS, 1) conv_strip_kernel(const __grid
                                         const uint32_t b8 = (uint32_t)(fminf(fmaxf(o[dy][dx * 3 + 2], 0.f), 1.f) * 255.0f + 0.5f);
                                         sq[dy * 96 + lane * 3 + dx] = r8 | (g8 << 8) | (b8 << 16) | 0xFF000000u;
                                     }
+                                __syncwarp();
                                 const int nu = npx_valid * 3;
-                                if (RSR_SHUF_BULK && npx_valid == 32 && (p.W & 3) == 0 && (reinterpret_cast<uintptr_t>(p.out_u8) & 15) == 0) {
-                                    fence_proxy_async_smem();
-                                    __syncwarp();
-                                    if (elect_one()) {
-                                        #pragma unroll
-                                        for (int dy = 0; dy < 3; ++dy)
-                                            bulk_store(reinterpret_cast<uint32_t*>(p.out_u8) + orow0 + (size_t)dy * W3, smem_u32(sq + dy * 96), 384);
-                                        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-                                    }
-                                } else {
-                                    __syncwarp();
-                                    #pragma unroll
-                                    for (int dy = 0; dy < 3; ++dy) {
-                                        uint32_t* dst = reinterpret_cast<uint32_t*>(p.out_u8) + orow0 + (size_t)dy * W3;
-                                        for (int i = lane; i < nu; i += 32) dst[i] = sq[dy * 96 + i];
-                                    }
+                                #pragma unroll
+                                for (int dy = 0; dy < 3; ++dy) {
+                                    uint32_t* dst = reinterpret_cast<uint32_t*>(p.out_u8) + orow0 + (size_t)dy * W3;
+                                    for (int i = lane; i < nu; i += 32) dst[i] = sq[dy * 96 + i];
                                 }
                             }
                             __syncwarp();

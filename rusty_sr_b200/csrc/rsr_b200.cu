@@ -122,16 +122,16 @@ using Cfg1 = ConvCfg<5, 5, 128, 3, 2, RSR_CFG1_NR, RSR_CFG1_TPS, RSR_CFG1_NBS, 0
 #endif
 #define RSR_CFG2_GEOM RSR_CFG2_R, RSR_CFG2_NR, RSR_CFG2_TPS, RSR_CFG2_NBS, RSR_CFG2_NPIN
 #ifndef RSR_CFG3_R
-#define RSR_CFG3_R 2
+#define RSR_CFG3_R 3   // (split plan only) 3 rows per pass, 2 weight stages: -2 % on conv8|9, same-box A/B r01j
 #endif
 #ifndef RSR_CFG3_NR
-#define RSR_CFG3_NR 5
+#define RSR_CFG3_NR 6
 #endif
 #ifndef RSR_CFG3_TPS
 #define RSR_CFG3_TPS 2
 #endif
 #ifndef RSR_CFG3_NBS
-#define RSR_CFG3_NBS 3
+#define RSR_CFG3_NBS 2
 #endif
 #ifndef RSR_CFG3_NPIN
 #define RSR_CFG3_NPIN 3
@@ -161,11 +161,17 @@ using Cfg2 = ConvCfg<3, 3, 128, 3, RSR_CFG2_GEOM, 2, false, 8>;  // l1 -> conv5 
 using Cfg3 = ConvCfg<3, 3, 128, 2, RSR_CFG3_GEOM, 2, false, RSR_CFG3_NEPI>;  // l2 -> conv8 | conv9           (+ P3, E)
 using Cfg4 = ConvCfg<3, 3, 128, 1, RSR_CFG4_GEOM, 2, true, 8>;  // l3 -> conv10 (+ E) + expand + bilinear skip
 
+// Launches that run on CTA pairs (bit = launch index) when neither RSR_B200_PAIR nor RSR_FLAG_NO_PAIRS says otherwise:
+// conv1|2|3 (index 2: -12..18 % on pairs) and, in the fused plan, the fused middle launch (index 3: 455 vs 605 us).  The
+// separate 3x3 launches, conv0 and conv10 are slower on pairs (measured, profiles/README.md), so the split plan keeps bit 2 only.
 #ifndef RSR_DEFAULT_PAIR_MASK
-#define RSR_DEFAULT_PAIR_MASK 4   // conv1|2|3 (launch index 2) on CTA pairs: -12..18 % on that launch, measured; the 3x3 launches are slower on pairs
+#define RSR_DEFAULT_PAIR_MASK 12
+#endif
+#ifndef RSR_DEFAULT_PAIR_MASK_SPLIT
+#define RSR_DEFAULT_PAIR_MASK_SPLIT 4
 #endif
 #ifndef RSR_DEFAULT_FUSED_MID
-#define RSR_DEFAULT_FUSED_MID 0
+#define RSR_DEFAULT_FUSED_MID 1   // conv5|6|7 + conv8|9 as one launch on CTA pairs: 455 vs 583 us, frame 1.495 -> 1.368 ms (same-box bench A/B, r01j)
 #endif
 // CTA-pair variants (conv_pair.cuh): same geometry, half a weight tap per CTA, so the shared memory freed can go
 // into deeper weight rings
@@ -241,50 +247,6 @@ __global__ void __launch_bounds__(256) pack_input_kernel(const void* __restrict_
         dst[2] = make_uint4(mid[0], mid[1], mid[2], mid[3]);
         dst[3] = make_uint4(mid[4], mid[5], mid[6], mid[7]);
         xf4[i] = make_float4(v[6], v[7], v[8], 0.f);  // d = 2 is the pixel itself
-    }
-}
-
-// Same result, four threads per pixel: thread part p writes 16-byte chunk p of the pixel's 64-byte xcol row (hi k 0..7,
-// hi k 8..15, mid k 0..7, mid k 8..15), so that one warp store instruction covers 512 contiguous bytes instead of 32
-// 16-byte pieces at a 64-byte stride.  Build-time A/B switch RSR_PACK_V2 (tools/ab_build.sh).
-#ifndef RSR_PACK_V2
-#define RSR_PACK_V2 0
-#endif
-template <bool U8>
-__global__ void __launch_bounds__(256) pack_input_kernel_v2(const void* __restrict__ in, int in_ch, int W, int H,
-                                                             int NIMG, __nv_bfloat16* __restrict__ xcol,
-                                                             float4* __restrict__ xf4) {
-    const size_t nq = (size_t)NIMG * H * W * 4;
-    for (size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x; q < nq; q += (size_t)gridDim.x * blockDim.x) {
-        const size_t i = q >> 2;
-        const int part = (int)(q & 3), half = part & 1;
-        const int x = (int)(i % W);
-        const size_t rowbase = i - x;  // (img*H + y) * W
-        auto load = [&](int xx, int c) -> float {   // channel c of pixel xx of this row, 0 outside the image
-            if (xx < 0 || xx >= W) return 0.f;
-            if (U8) return (float)reinterpret_cast<const uint8_t*>(in)[(rowbase + xx) * in_ch + c] / 255.0f;
-            return reinterpret_cast<const float*>(in)[(rowbase + xx) * 3 + c];
-        };
-        float v[8];
-        #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            const int k = 8 * half + j;        // k = d * 3 + c, d = horizontal neighbour 0..4 (k = 15: padding)
-            const int d = (k * 11) >> 5;       // k / 3 for k < 16
-            v[j] = k < 15 ? load(x + d - 2, k - 3 * d) : 0.f;
-        }
-        uint32_t w[4];
-        #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const __nv_bfloat16 h0 = __float2bfloat16_rn(v[2 * k]), h1 = __float2bfloat16_rn(v[2 * k + 1]);
-            if (part < 2) {
-                w[k] = pack_bf16x2(h0, h1);
-            } else {
-                w[k] = pack_bf16x2(__float2bfloat16_rn(v[2 * k] - __bfloat162float(h0)),
-                                   __float2bfloat16_rn(v[2 * k + 1] - __bfloat162float(h1)));
-            }
-        }
-        reinterpret_cast<uint4*>(xcol)[q] = make_uint4(w[0], w[1], w[2], w[3]);   // chunk order = part order: hi lo, hi hi, mid lo, mid hi
-        if (part == 0) xf4[i] = make_float4(v[6], v[7], load(x, 2), 0.f);        // d = 2 is the pixel itself: k = 6, 7, 8
     }
 }
 
@@ -538,7 +500,7 @@ extern "C" rsr_ctx* rsr_create(const float* params, size_t n_params, int factor,
         if (flags & RSR_FLAG_FUSED_MID) fused = true;
         if (flags & RSR_FLAG_SPLIT_MID) fused = false;
         c->fused_mid = fused;
-        int pm = RSR_DEFAULT_PAIR_MASK;
+        int pm = fused ? RSR_DEFAULT_PAIR_MASK : RSR_DEFAULT_PAIR_MASK_SPLIT;
         if (const char* e = getenv("RSR_B200_PAIR")) pm = atoi(e);
         if (flags & RSR_FLAG_NO_PAIRS) pm = 0;
         c->pair_mask = pm;
@@ -676,15 +638,9 @@ static int forward_device(rsr_ctx* c, const void* d_in, bool u8, int in_ch, int 
     c->last_launches = 0;
     CUDA_TRY(cudaEventRecord(c->ev[0], c->stream));
     {
-#if RSR_PACK_V2
-        const int blocks = (int)std::min<size_t>((npx * 4 + 255) / 256, (size_t)c->num_sms * 32);
-        if (u8) pack_input_kernel_v2<true><<<blocks, 256, 0, c->stream>>>(d_in, in_ch, w, h, n, xcol, (float4*)c->xf4.p);
-        else    pack_input_kernel_v2<false><<<blocks, 256, 0, c->stream>>>(d_in, 3, w, h, n, xcol, (float4*)c->xf4.p);
-#else
         const int blocks = (int)std::min<size_t>((npx + 255) / 256, (size_t)c->num_sms * 16);
         if (u8) pack_input_kernel<true><<<blocks, 256, 0, c->stream>>>(d_in, in_ch, w, h, n, xcol, (float4*)c->xf4.p);
         else    pack_input_kernel<false><<<blocks, 256, 0, c->stream>>>(d_in, 3, w, h, n, xcol, (float4*)c->xf4.p);
-#endif
         CUDA_TRY(cudaGetLastError());
         c->last_launches++;
     }
@@ -980,7 +936,10 @@ extern "C" const char* rsr_plan(rsr_ctx* c) {
     s += "; CTA pairs (cta_group::2):";
     bool any = false;
     for (int k = 1; k < K_COUNT; ++k)
-        if (c->pair_mask >> k & 1) { s += std::string(any ? "," : " ") + kKernelNames[k]; any = true; }
+        if ((c->pair_mask >> k & 1) && !(c->fused_mid && k == K_L2)) {   // (the fused plan has no launch of its own for conv8|9)
+            s += std::string(any ? "," : " ") + (c->fused_mid && k == K_L1 ? "conv5|6|7+conv8|9 fused" : kKernelNames[k]);
+            any = true;
+        }
     if (!any) s += " none";
     return s.c_str();
 }

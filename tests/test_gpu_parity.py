@@ -21,9 +21,12 @@ def R():
     return R
 
 
-@pytest.fixture(scope="module")
-def ups(R, weights):
-    d = {k: R.Upscaler(weights[k]) for k in weights}
+# Every test runs on the library's default launch plan (fused middle launch on CTA pairs) and on the split plan
+# (RSR_FLAG_SPLIT_MID: conv5|6|7 and conv8|9 as separate launches), which stays selectable through the C ABI.
+@pytest.fixture(scope="module", params=["default", "split"])
+def ups(request, R, weights):
+    flags = 0 if request.param == "default" else R.RSR_FLAG_SPLIT_MID
+    d = {k: R.Upscaler(weights[k], flags=flags) for k in weights}
     yield d
     for u in d.values():
         u.close()
