@@ -40,6 +40,18 @@ W_LR, H_LR, FACTOR = 1920, 1080, 3
 OUT_MPIX = W_LR * H_LR * FACTOR * FACTOR / 1e6          # 18.6624 Mpix per frame
 FLOPS_PER_LR_PX = 260352                                # SURVEY.md 8(a), whole net
 FLOPS_CONV123_PER_LR_PX = 3 * 51200                     # conv1 + conv2 + conv3 (network.rs:60-62)
+# Per launch: (useful FLOP per LR pixel, algorithmic HBM bytes per LR pixel) — DESIGN.md §5 table; every tensor read once + written
+# once in its stored layout, padding lanes not counted as useful FLOPs.  The fused middle launch moves 640 B/px (l1, P2, P3 in;
+# l3, E out) where conv5|6|7 + conv8|9 move 768 + 640.
+LAUNCH_WORK = {
+    "pack_input": (0, 12 + 80),
+    "conv0": (4800, 64 + 128),
+    "conv1|2|3": (153600, 128 + 384),
+    "conv5|6|7": (18432 * 2 + 15552, 384 + 384),
+    "conv8|9": (18432 + 15552, 384 + 256),
+    "conv5|6|7+conv8|9 (fused)": (18432 * 3 + 15552 * 2, 384 + 256),
+    "conv10+expand+skip": (15552, 256 + 16 + 108),
+}
 WORKLOAD = f"{W_LR}x{H_LR} RGB -> {W_LR*FACTOR}x{H_LR*FACTOR} (factor 3, bundled imagenet weights), 1 frame/GPU/step"
 N_ROTATE = 6   # distinct input frames cycled through so the input is never L2 resident
 
@@ -54,6 +66,25 @@ def load_peaks():
                 "hbm_gbs": float(d.get("hbm_gbs", 6650.0)), "source": "measured (MEASURED_PEAKS.json, sustained)"}
     return {"bf16_tflops": 1400.0, "bf16_tflops_burst": 1590.0, "hbm_gbs": 6650.0,
             "source": "fallback (B200_PROFILING.md)"}
+
+
+def per_launch_roofline(ktimes, npx, peaks):
+    """Every launch against min(tensor, HBM): roofline_ms = max(useful FLOPs / measured sustained dense-bf16 peak, algorithmic
+    bytes / measured copy bandwidth), frac = roofline_ms / measured ms.  *_bf16x3: the same with the FLOPs the BF16x3 split
+    actually executes (3 x useful) against the measured burst peak — the ceiling of this formulation."""
+    per_launch = {}
+    for k, ms in ktimes.items():
+        if k not in LAUNCH_WORK or not ms or ms != ms:
+            continue
+        fl, by = LAUNCH_WORK[k]
+        t_tensor = fl * npx / (peaks["bf16_tflops"] * 1e12) * 1e3
+        t_hbm = by * npx / (peaks["hbm_gbs"] * 1e9) * 1e3
+        t_x3 = 3 * fl * npx / (peaks["bf16_tflops_burst"] * 1e12) * 1e3   # the three split products, at the burst peak
+        per_launch[k] = {"ms": ms, "useful_tflops": fl * npx / (ms * 1e-3) / 1e12, "hbm_gbs": by * npx / (ms * 1e-3) / 1e9,
+                         "bound": "tensor" if t_tensor > t_hbm else "hbm", "roofline_ms": max(t_tensor, t_hbm),
+                         "frac": max(t_tensor, t_hbm) / ms,
+                         "roofline_ms_bf16x3": max(t_x3, t_hbm), "frac_bf16x3": max(t_x3, t_hbm) / ms}
+    return per_launch
 
 
 class ClockSampler:
@@ -302,6 +333,7 @@ def run_ours(args):
                    "sample": f"2 x ({W_LR}x{rows} slab of the same frame), img_to_data+forward(fp32)+data_to_img",
                    "note": "CPU restatement of rusty_sr/alumina path (Rust toolchain unavailable)"}
         total_k = sum(ktimes.values())
+        per_launch = per_launch_roofline(ktimes, npx, peaks)
         line = {
             "metric": "output Mpix/s (3x upscale, sr_net forward)", "value": value, "unit": "Mpix/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
@@ -321,6 +353,7 @@ def run_ours(args):
                                  "tensor pipe executes 3x that (BF16x3 split), so the ceiling of this formulation is 1/3",
                          "executed_frac": 3 * achieved_tf / peaks["bf16_tflops"]},
             "kernel_ms": ktimes,
+            "per_launch_roofline": per_launch,
             "whole_net_tflops_useful": FLOPS_PER_LR_PX * npx / (total_k * 1e-3) / 1e12 if total_k else None,
             "cpu_baseline": cpu,
             "e2e": {"value": e2e_value, "unit": "Mpix/s", "ms_per_step": e2e_ms_step,

@@ -39,3 +39,22 @@ def test_our_arm_fails_loudly_without_a_gpu():
         return
     r = run_bench("--steps", "1", "--warmup", "1")
     assert r.returncode != 0 and "no CUDA device" in r.stdout
+
+
+def test_per_launch_roofline_table():
+    """The per-launch roofline of the bench line, on the launch times of a recorded run (profiles/r01j_bench.json)."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(ROOT, "bench.py"))
+    b = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(b)
+    rec = json.load(open(os.path.join(ROOT, "profiles", "r01j_bench.json")))
+    peaks = {"bf16_tflops": 1361.8, "bf16_tflops_burst": 1621.1, "hbm_gbs": 6550.4}
+    t = b.per_launch_roofline(rec["kernel_ms"], 1920 * 1080, peaks)
+    assert set(t) == set(rec["kernel_ms"])
+    # whole-net useful FLOPs and bytes of the launch table agree with SURVEY.md 8(a) / DESIGN.md (fused plan: 768 B/px less)
+    fused = [k for k in b.LAUNCH_WORK if k not in ("conv5|6|7", "conv8|9")]
+    assert sum(b.LAUNCH_WORK[k][0] for k in fused) == b.FLOPS_PER_LR_PX
+    assert sum(b.LAUNCH_WORK[k][1] for k in b.LAUNCH_WORK if "fused" not in k) == 2584
+    assert t["conv1|2|3"]["bound"] == "tensor" and 0.3 < t["conv1|2|3"]["frac"] < 0.5
+    assert t["pack_input"]["bound"] == "hbm" and all(0 < v["frac"] <= 1.0 for v in t.values())
+    assert b.per_launch_roofline({"conv0": float("nan"), "unknown": 1.0}, 10, peaks) == {}

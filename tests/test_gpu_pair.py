@@ -1,6 +1,8 @@
 """CTA-pair kernels (rusty_sr_b200/csrc/conv_pair.cuh: tcgen05 cta_group::2, two SMs per MMA): every conv launch
 can run on pairs (RSR_B200_PAIR=<launch bit mask>, read when a context is created); the library default uses them
-for conv1|2|3.  All plans must meet the same parity bar and agree with each other."""
+for conv1|2|3 and for the fused middle launch.  All plans must meet the same parity bar and agree with each other.
+Masks are tried on the default launch plan (fused middle launch: bit 3 = that launch) and on the split plan
+(RSR_FLAG_SPLIT_MID: bits 3 and 4 = conv5|6|7 and conv8|9 as separate pair launches)."""
 import os
 
 import numpy as np
@@ -30,6 +32,8 @@ def plans(weights):
     import rusty_sr_b200 as R
     d = {m: make(R, weights["imagenet"], m) for m in (0, 4, 62)}
     d["nopairs-flag"] = make(R, weights["imagenet"], 62, flags=R.RSR_FLAG_NO_PAIRS)
+    d["split-0"] = make(R, weights["imagenet"], 0, flags=R.RSR_FLAG_SPLIT_MID)
+    d["split-62"] = make(R, weights["imagenet"], 62, flags=R.RSR_FLAG_SPLIT_MID)
     yield d
     for u in d.values():
         u.close()
@@ -49,11 +53,16 @@ def test_pair_plans_parity_and_agreement(plans, weights, shape):
     for m in (4, 62):
         assert np.abs(outs[m] - outs[0]).max() < 2e-5
     assert np.array_equal(outs["nopairs-flag"], outs[0])
+    assert np.abs(outs["split-62"] - outs["split-0"]).max() < 2e-5
 
 
 def test_pair_plan_partition_independence(plans):
     """Batches and 7-row-halo bands reproduce the single frame bit for bit on pairs too."""
-    u = plans[62]
+    for key in (62, "split-62"):
+        _partition_independence(plans[key])
+
+
+def _partition_independence(u):
     xs = np.stack([noise_image(40, 140, 50 + i) for i in range(3)])
     outs = u.forward(xs)
     for i in range(3):
