@@ -25,6 +25,12 @@
 // TMEM -> registers (+ partial from smem) -> bias / BeLU / split -> swizzled staging -> TMA store.  R output rows are accumulated per pass in TMEM, double
 // buffered, so the epilogue of pass j overlaps the MMAs of pass j + 1.
 //
+// Row folding (ConvCfg::FOLD, experimental): at N <= 64 an MMA is bound by the shared-memory read of its 4 KB A tile
+// (tests/cuda/umma_bench.cu: max(N/2, 32 + N/4) cycles).  Input row i of a pass window contributes to the output rows
+// r = i - ta, ta = 0..KH-1; with the accumulators of the R rows of a pass adjacent in TMEM and the KH weight taps of one tap
+// column stored bottom tap first, those contributions are ONE MMA with N = (rows hit) x NCOL: same tensor work, KH times
+// fewer A reads (conv10: 54 N=32 MMAs per row -> 36 MMAs of N = 32..96 per two rows).
+//
 // Warp roles: warp 0 = input-row producer, warp 3 = weight producer, warp 2 = TMEM allocator +
 // partial-sum producer, warp 1 = MMA issuer (one lane), warps 4.. = epilogue (4 or 8 warps per config;
 // with 8, two warps per TMEM lane quarter take alternate (row, group) tiles of a pass, which hides the
@@ -101,9 +107,12 @@ struct ConvParams {
     } while (0)
 
 template <int KH_, int KW_, int RB_, int NG_, int R_, int NR_, int TPS_, int NBS_, int NPIN_, int NOUT_, bool SHUF_, int NEPI_ = 4,
-          bool PAIR_ = false>
+          bool PAIR_ = false, bool FOLD_ = false>
 struct ConvCfg {
     static constexpr bool PAIR = PAIR_;                                // CTA-pair kernel (conv_pair.cuh): half a weight tap per CTA
+    // Row-folded MMAs (experimental, off in every shipped launch; see the MMA role): the KH vertical taps of one tap column
+    // become ONE MMA per input row whose N spans the up to KH output rows that row contributes to.
+    static constexpr bool FOLD = FOLD_;
     static constexpr int KH = KH_, KW = KW_, RB = RB_, NG = NG_, R = R_;
     static constexpr int NEPI = NEPI_;                                 // epilogue warps (4 or 8)
     static_assert(NEPI == 4 || NEPI == 8, "4 or 8 epilogue warps");
@@ -141,6 +150,7 @@ struct ConvCfg {
     static_assert(HB % 8 == 0, "a CTA's share of a tap must be whole 8-row core-matrix groups");
     static_assert(NR >= R + 2 * PH, "row ring smaller than one pass window");
     static_assert(SMEM_BYTES <= 232448, "shared memory budget");
+    static_assert(!FOLD || (!PAIR && TPS == KH && KH * NCOL <= 256), "row folding: one weight stage = the KH taps of one tap column");
 };
 
 struct WorkItem {
@@ -439,7 +449,8 @@ __global__ void __launch_bounds__(C::NTHREADS, 1) conv_strip_kernel(const __grid
         constexpr uint32_t LBO = 1u << 16;
         constexpr uint32_t MID = (C::RB / 2) >> 4;   // encoded offset of the mid plane
         constexpr int WIN = C::R + 2 * C::PH;        // input rows one pass reads
-        constexpr int NEARLY = C::R < C::KH ? C::R : C::KH;   // rows retired during the pass
+        constexpr int NEARLY = C::FOLD ? 0 : (C::R < C::KH ? C::R : C::KH);   // rows retired during the pass (folded: every
+                                                                               // stage reads the whole window)
         const uint32_t sA_e = (smem_u32(sA) >> 4) | LBO, sB_e = (smem_u32(sB) >> 4) | LBO;
         auto desc = [](uint32_t hi, uint32_t lo) { return ((uint64_t)hi << 32) | lo; };
         uint32_t slot0 = 0;              // ring slot of the first window row of the current pass
@@ -472,6 +483,49 @@ __global__ void __launch_bounds__(C::NTHREADS, 1) conv_strip_kernel(const __grid
                     }
                 }
                 const uint32_t d_pass = tmem_base + buf * (C::R * C::NCOL);
+                if constexpr (C::FOLD) {
+                    // stage sp = tap column tb: weight rows [j][n], j = KH-1-ta (bottom tap first), so the taps that input row i
+                    // feeds into output rows r_lo..r_hi (ta = i-r_lo down to i-r_hi) are one contiguous block of rows
+                    #pragma unroll
+                    for (int sp = 0; sp < C::NSTG; ++sp) {
+                        RSR_WAIT(&b_full[bst], bpar, 5, 2);
+                        tc_fence_after();
+                        const uint32_t b_st = sB_e + bst * (C::BST >> 4);
+                        const long long ti0 = RSR_PROF_ON ? clock64() : 0;
+                        if (elect_one()) {
+                            #pragma unroll
+                            for (int i = 0; i < WIN; ++i) {
+                                const int r_lo = i - (C::KH - 1) > 0 ? i - (C::KH - 1) : 0;
+                                const int r_hi = i < C::R - 1 ? i : C::R - 1;
+                                const int n = r_hi - r_lo + 1;                       // output rows this input row feeds
+                                const uint32_t a_e = arow[i] + sp * (C::RB >> 4);
+                                const uint32_t b_e = b_st + (C::KH - 1 - (i - r_lo)) * (C::TAP_BYTES >> 4);
+                                const uint32_t d = d_pass + r_lo * C::NCOL;
+                                const uint32_t idesc_n = make_idesc_bf16(128, n * C::NCOL);
+                                #pragma unroll
+                                for (int c = 0; c < C::KC; ++c) {
+                                    if (ABL_NO_MMA) continue;
+                                    if (sp == 0 && c == 0 && i < C::R) {
+                                        // the first product that reaches output row i (= r_hi) overwrites its accumulator; the
+                                        // rows above it in the same block already hold sums: two MMAs instead of one
+                                        if (n > 1)
+                                            umma_f16(d, desc(HI, a_e), desc(HI, b_e), make_idesc_bf16(128, (n - 1) * C::NCOL), 1);
+                                        umma_f16(d + (n - 1) * C::NCOL, desc(HI, a_e), desc(HI, b_e + (n - 1) * (C::TAP_BYTES >> 4)),
+                                                 make_idesc_bf16(128, C::NCOL), 0);
+                                    } else {
+                                        umma_f16(d, desc(HI, a_e + 2 * c), desc(HI, b_e + 2 * c), idesc_n, 1);
+                                    }
+                                    umma_f16(d, desc(HI, a_e + MID + 2 * c), desc(HI, b_e + 2 * c), idesc_n, 1);
+                                    umma_f16(d, desc(HI, a_e + 2 * c), desc(HI, b_e + MID + 2 * c), idesc_n, 1);
+                                }
+                            }
+                            umma_commit(&b_empty[bst]);
+                        }
+                        __syncwarp();
+                        if (RSR_PROF_ON) prof_acc[4] += clock64() - ti0;
+                        if (++bst == C::NBS) { bst = 0; bpar ^= 1; }
+                    }
+                } else {
                 #pragma unroll
                 for (int sp = 0; sp < C::NSTG; ++sp) {
                     RSR_WAIT(&b_full[bst], bpar, 5, 2);
@@ -511,6 +565,7 @@ __global__ void __launch_bounds__(C::NTHREADS, 1) conv_strip_kernel(const __grid
                     if (RSR_PROF_ON) prof_acc[4] += clock64() - ti0;
                     if (++bst == C::NBS) { bst = 0; bpar ^= 1; }
                 }
+                }  // !FOLD
                 const bool last = j == w.npass - 1 || p.n_cb > 1;
                 const int n_retire = last ? WIN : C::R;
                 if (elect_one()) {

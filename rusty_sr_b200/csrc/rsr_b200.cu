@@ -15,6 +15,7 @@
 #include <cstring>
 #include <new>
 #include <string>
+#include <type_traits>
 #include <vector>
 
 #include "../../include/rsr_b200.h"
@@ -192,6 +193,13 @@ using PCfg1 = ConvCfg<5, 5, 128, 3, 2, RSR_PCFG1_NR, RSR_PCFG1_TPS, RSR_PCFG1_NB
 using PCfg2 = ConvCfg<3, 3, 128, 3, 2,  5, 2, 3, 2, 2, false, 8, true>;
 using PCfg3 = ConvCfg<3, 3, 128, 2, 2,  5, 2, 3, 3, 2, false, 4, true>;
 using PCfg4 = ConvCfg<3, 3, 128, 1, 2,  6, 3, 3, 3, 2, true, 8, true>;
+// Row-folded variants (ConvCfg::FOLD, conv_strip.cuh; EXPERIMENTAL: selected only by RSR_B200_FOLD=<launch bit mask>, off by
+// default and not yet timed on hardware): conv0 and conv10, the two N = 32 launches whose MMAs are bound by the A-tile read.
+using FCfg0 = ConvCfg<5, 1,  64, 1, RSR_CFG0_R, RSR_CFG0_NR, 5, 2, 0, 2, false, 8, false, true>;
+using FCfg4 = ConvCfg<3, 3, 128, 1, RSR_CFG4_R, RSR_CFG4_NR, 3, RSR_CFG4_NBS, RSR_CFG4_NPIN, 2, true, 8, false, true>;
+template <class C> struct FoldOf { using type = void; };
+template <> struct FoldOf<Cfg0> { using type = FCfg0; };
+template <> struct FoldOf<Cfg4> { using type = FCfg4; };
 template <class C> struct PairOf;
 template <> struct PairOf<Cfg0> { using type = PCfg0; };
 template <> struct PairOf<Cfg1> { using type = PCfg1; };
@@ -267,6 +275,8 @@ struct rsr_ctx {
     DevBuf xcol, xf4, actA, actB, partA, partB, partC, out_f32, out_u8, in_stage;
     bool fused_mid = false;     // conv5|6|7 + conv8|9 in one launch (conv_fused.cuh); RSR_FLAG_FUSED_MID
     int pair_mask = 0;          // bit k: launch index k (1 = conv0 .. 5 = conv10) runs as CTA pairs (conv_pair.cuh)
+    int fold_mask = 0;          // bit k: launch index k (1 = conv0, 5 = conv10) runs with row-folded MMAs (experimental)
+    __nv_bfloat16 *w0f = nullptr, *w4f = nullptr;   // the same weights, taps of a tap column stored bottom tap first
     int fused_dbg = 0;          // test hook rsr_debug_fused: bit 0 skip S2 MMAs, bit 1 dump l2 / raw accumulators, bit 2 profile (debug kernel),
                                 // bit 3 profile of the plan's own kernel (single CTA or pair; needs a -DRSR_FUSED_PROF=1 build)
     DevBuf dbg_l2, dbg_t3, dbg_prof;
@@ -347,7 +357,7 @@ extern "C" void rsr_destroy(rsr_ctx* c) {
     if (!c) return;
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
-    cudaFree(c->w0); cudaFree(c->w1); cudaFree(c->w2); cudaFree(c->w3); cudaFree(c->w4);
+    cudaFree(c->w0); cudaFree(c->w1); cudaFree(c->w2); cudaFree(c->w3); cudaFree(c->w4); cudaFree(c->w0f); cudaFree(c->w4f);
     cudaFree(c->vecs); cudaFree(c->prof);
     if (c->fault_host) cudaFreeHost(c->fault_host);
     release(c->xcol); release(c->xf4); release(c->actA); release(c->actB); release(c->partA);
@@ -414,6 +424,11 @@ static int create_impl(rsr_ctx* c, const float* params) {
                         w[row + 16 + b * 3 + ch] = m;
                     }
         if (int rc = upload(&c->w0, w.data(), w.size() * 2)) return rc;
+        // row-folded order: tap row a stored at block 4 - a
+        std::vector<__nv_bfloat16> wf(w.size());
+        for (int a = 0; a < 5; ++a)
+            memcpy(&wf[(size_t)(4 - a) * 32 * 32], &w[(size_t)a * 32 * 32], sizeof(__nv_bfloat16) * 32 * 32);
+        if (int rc = upload(&c->w0f, wf.data(), wf.size() * 2)) return rc;
     }
     std::vector<__nv_bfloat16> w;
     {
@@ -439,6 +454,12 @@ static int create_impl(rsr_ctx* c, const float* params) {
         const int co[1] = {L.ce};
         pack_group(params, offs, co, 1, 3, w);
         if (int rc = upload(&c->w4, w.data(), w.size() * 2)) return rc;
+        // row-folded order: tap (ta, tb) stored at block tb * 3 + (2 - ta)   (blocks of 32 rows x 64 bf16)
+        std::vector<__nv_bfloat16> wf(w.size());
+        for (int ta = 0; ta < 3; ++ta)
+            for (int tb = 0; tb < 3; ++tb)
+                memcpy(&wf[(size_t)(tb * 3 + (2 - ta)) * 32 * 64], &w[(size_t)(ta * 3 + tb) * 32 * 64], sizeof(__nv_bfloat16) * 32 * 64);
+        if (int rc = upload(&c->w4f, wf.data(), wf.size() * 2)) return rc;
     }
     {
         std::vector<float> v(9 * 32, 0.f);
@@ -452,6 +473,8 @@ static int create_impl(rsr_ctx* c, const float* params) {
     CUDA_TRY(cudaFuncSetAttribute(conv_strip_kernel<Cfg2>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg2::SMEM_BYTES));
     CUDA_TRY(cudaFuncSetAttribute(conv_strip_kernel<Cfg3>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg3::SMEM_BYTES));
     CUDA_TRY(cudaFuncSetAttribute(conv_strip_kernel<Cfg4>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg4::SMEM_BYTES));
+    CUDA_TRY(cudaFuncSetAttribute(conv_strip_kernel<FCfg0>, cudaFuncAttributeMaxDynamicSharedMemorySize, FCfg0::SMEM_BYTES));
+    CUDA_TRY(cudaFuncSetAttribute(conv_strip_kernel<FCfg4>, cudaFuncAttributeMaxDynamicSharedMemorySize, FCfg4::SMEM_BYTES));
     CUDA_TRY(cudaFuncSetAttribute(conv_fused_mid_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FusedCfg::SMEM_BYTES));
     CUDA_TRY(cudaFuncSetAttribute(conv_fused_mid_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FusedCfg::SMEM_BYTES));
     CUDA_TRY(cudaFuncSetAttribute(conv_fused_mid_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FusedCfgT<true>::SMEM_BYTES));
@@ -504,6 +527,7 @@ extern "C" rsr_ctx* rsr_create(const float* params, size_t n_params, int factor,
         if (const char* e = getenv("RSR_B200_PAIR")) pm = atoi(e);
         if (flags & RSR_FLAG_NO_PAIRS) pm = 0;
         c->pair_mask = pm;
+        if (const char* e = getenv("RSR_B200_FOLD")) c->fold_mask = atoi(e) & ((1 << K_CONV0) | (1 << K_L3)) & ~pm;
     }
     if (create_impl(c, params) != 0) {
         const std::string keep = g_err;
@@ -600,6 +624,15 @@ static int launch_conv(rsr_ctx* c, ConvParams& p, int kindex) {
     const int grid = (int)std::min<long long>(p.total_rowtiles, c->num_sms);
     p.prof = (c->prof && grid <= 256) ? c->prof + (size_t)kindex * 256 * 16 : nullptr;
     c->prof_grid[kindex] = grid;
+    using F = typename FoldOf<C>::type;
+    if constexpr (!std::is_void<F>::value) {
+        if (c->fold_mask >> kindex & 1) {   // p.tmB must then map the fold-ordered weight copy (same box)
+            conv_strip_kernel<F><<<grid, F::NTHREADS, F::SMEM_BYTES, c->stream>>>(p);
+            CUDA_TRY(cudaGetLastError());
+            c->last_launches++;
+            return 0;
+        }
+    }
     conv_strip_kernel<C><<<grid, C::NTHREADS, C::SMEM_BYTES, c->stream>>>(p);
     CUDA_TRY(cudaGetLastError());
     c->last_launches++;
@@ -658,7 +691,8 @@ static int forward_device(rsr_ctx* c, const void* d_in, bool u8, int in_ch, int 
 
     // conv0: xcol -> f = BeLU(conv0(x) + f_bias)                       network.rs:33-35
     if (int rc = make_map_act(c, &p.tmA, xcol, 32, w, h, n, Cfg0::BOXW)) return rc;
-    if (int rc = make_map_w(c, &p.tmB, c->w0, 32, 5 * 32, pair(1) ? 16 : Cfg0::TPS * 32)) return rc;
+    auto fold = [&](int kindex) { return (c->fold_mask >> kindex & 1) != 0; };
+    if (int rc = make_map_w(c, &p.tmB, fold(1) ? c->w0f : c->w0, 32, 5 * 32, pair(1) ? 16 : Cfg0::TPS * 32)) return rc;
     if (int rc = in_map(&p.tmOut[0], f_act, 32)) return rc;
     p.grp[0] = EpiGroup{EPI_ACT, 0, f_bias, f_slope, 0, 0};
     p.grp[1] = none; p.grp[2] = none;
@@ -780,7 +814,7 @@ static int forward_device(rsr_ctx* c, const void* d_in, bool u8, int in_ch, int 
 
     // l3 -> output = Expand(E + conv10(l3) + expand_bias) + LinearInterp(x)          :72,38-39,27
     if (int rc = in_map(&p.tmA, l3_act, Cfg4::BOXW)) return rc;
-    if (int rc = make_map_w(c, &p.tmB, c->w4, 64, 9 * 32, pair(5) ? 16 : Cfg4::TPS * 32)) return rc;
+    if (int rc = make_map_w(c, &p.tmB, fold(5) ? c->w4f : c->w4, 64, 9 * 32, pair(5) ? 16 : Cfg4::TPS * 32)) return rc;
     if (int rc = part_map(&p.tmPin[0], E, 128)) return rc;
     p.grp[0] = EpiGroup{EPI_SHUFFLE, 1, e_bias, nullptr, 0, 0};
     p.grp[1] = none; p.grp[2] = none;
