@@ -104,7 +104,7 @@ using Cfg0 = ConvCfg<5, 1,  64, 1, RSR_CFG0_R, RSR_CFG0_NR, 5, 2, 0, 2, false, 8
 #define RSR_L2PROMO CU_TENSOR_MAP_L2_PROMOTION_L2_256B
 #endif
 using Cfg1 = ConvCfg<5, 5, 128, 3, 2, RSR_CFG1_NR, RSR_CFG1_TPS, RSR_CFG1_NBS, 0, 2, false>;  // f  -> conv1 | conv2 | conv3
-// Ring geometry of the 3x3 launches, overridable at build time for same-box A/B runs (tools/ab_build.sh, tools/ab.sh):
+// Ring geometry of the 3x3 launches, overridable at build time for same-box A/B runs (tools/ab_session.py):
 // rows per pass R, input-row slots NR, taps per weight stage TPS, weight stages NBS, partial-sum tile slots NPIN.
 #ifndef RSR_CFG2_R
 #define RSR_CFG2_R 2

@@ -1,7 +1,15 @@
-"""Second GPU session of the round (run under gpurun, hard time budget): the whole GPU suite on the shipped library and
-on the previous default (fallback), bench, the TMEM-operand probe, a same-box A/B of library variants and launch
-plans, a combined library of the winners (GPU suite + bench), then the ncu launch list and one full capture.
-Everything lands in gpurun_out/.  usage: python tools/final_round2.py [budget_seconds]   (DRY=1: control flow only)"""
+"""One GPU session under a hard time budget, driven by a JSON spec (tools/specs/*.json): the whole GPU suite on the shipped
+library, bench, hardware probes, an interleaved same-box A/B of library variants (build flags) and launch plans
+(environment), a combined library of the winners that must pass the GPU suite and is benched against the shipped one,
+then the ncu launch list and one full capture.  Everything lands in gpurun_out/; nothing here changes the shipped library.
+
+  python tools/ab_session.py SPEC --build            here (no GPU): compile the spec's variants into build/abl/
+  gpurun -- python tools/ab_session.py SPEC BUDGET   on the GPU box     (DRY=1: control flow only, no GPU commands)
+
+Spec: {"entries": {name: {"flags": "<nvcc -D flags>" | "lib": "<file in build/abl>", "env": {...}, "launches": [...],
+       "group": "<variants of one group compete; the best one above `min_gain` joins the combined library>"}},
+       "probes": [...tests/cuda binaries], "pytest_env": {...}, "ncu_kernel": "regex", "ncu_skip": n, "min_gain": 0.02}
+The entry "base" (no flags) is the reference of every comparison."""
 import json
 import os
 import subprocess
@@ -11,28 +19,40 @@ import time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 OUT = os.path.join(ROOT, "gpurun_out")
 ABL = os.path.join(ROOT, "build", "abl")
-BUDGET = float(sys.argv[1]) if len(sys.argv) > 1 else 330.0
+SPEC = json.load(open(sys.argv[1]))
+BUILD_ONLY = "--build" in sys.argv[2:]
+BUDGET = float(sys.argv[2]) if len(sys.argv) > 2 and not BUILD_ONLY else 330.0
 T0 = time.time()
 DRY = os.environ.get("DRY") == "1"
-summary = {"stages": {}}
-MID = ("conv5|6|7", "conv8|9")
-# name -> (library file in build/abl, extra environment, launches whose summed time is compared with `base`)
-ENTRIES = {
-    "base": ("base.so", {}, None),
-    "c0_r4n12": ("c0_r4n12.so", {}, ("conv0",)),
-    "c0_r8n12": ("c0_r8n12.so", {}, ("conv0",)),
-    "c0_r8n20": ("c0_r8n20.so", {}, ("conv0",)),
-    "c0_r6n14": ("c0_r6n14.so", {}, ("conv0",)),
-    "c3_r3": ("c3_r3.so", {}, ("conv8|9",)),
-    "c3_r3b": ("c3_r3b.so", {}, ("conv8|9",)),
-    "pk_v2": ("pk_v2.so", {}, ("pack_input",)),
-    "f_single": ("base.so", {"RSR_B200_FUSED": "1", "RSR_B200_PAIR": "4"}, MID),
-    "f_pair": ("base.so", {"RSR_B200_FUSED": "1", "RSR_B200_PAIR": "12"}, MID),
-    "f_pair_prof": ("librsr_b200_prof.so", {"RSR_B200_FUSED": "1", "RSR_B200_PAIR": "12"}, MID),
-    "fp_t1n9": ("fp_t1n9.so", {"RSR_B200_FUSED": "1", "RSR_B200_PAIR": "12"}, MID),
-    "fp_nr5": ("fp_nr5.so", {"RSR_B200_FUSED": "1", "RSR_B200_PAIR": "12"}, MID),
-}
-COMBINABLE = ("c0", "c3", "pk")   # build-flag variants (the f_* entries are launch plans of the same library)
+summary = {"stages": {}, "spec": os.path.basename(sys.argv[1])}
+NVCC = ["/usr/local/cuda/bin/nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC",
+        "-shared"]
+# name -> (library file in build/abl, extra environment, launches whose summed time is compared with `base`, group)
+ENTRIES = {"base": ("base.so", {}, None, None)}
+for _n, _e in SPEC["entries"].items():
+    ENTRIES[_n] = (_e.get("lib", _n + ".so"), _e.get("env", {}), tuple(_e["launches"]) if _e.get("launches") else None, _e.get("group"))
+MIN_GAIN = float(SPEC.get("min_gain", 0.02))
+
+
+def build_variants():
+    """Compiles base.so and every entry that has build flags (parallel nvcc; no GPU needed)."""
+    os.makedirs(ABL, exist_ok=True)
+    jobs = {"base": ""}
+    jobs.update({n: e["flags"] for n, e in SPEC["entries"].items() if "flags" in e})
+    procs = {}
+    for n, flags in jobs.items():
+        with open(os.path.join(ABL, n + ".flags"), "w") as f:
+            f.write(flags)
+        procs[n] = subprocess.Popen([*NVCC, *flags.split(), "-o", os.path.join(ABL, n + ".so"), "rusty_sr_b200/csrc/rsr_b200.cu", "-lcudart"],
+                                    cwd=ROOT, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    ok = True
+    for n, p in procs.items():
+        out, _ = p.communicate()
+        print(f"build {n:16s} rc={p.returncode}", flush=True)
+        if p.returncode != 0:
+            ok = False
+            print(out[-2000:])
+    return ok
 
 
 def left():
@@ -41,7 +61,7 @@ def left():
 
 def save():
     summary["elapsed_s"] = round(time.time() - T0, 1)
-    with open(os.path.join(OUT, "final_round2_summary.json"), "w") as f:
+    with open(os.path.join(OUT, "ab_session_summary.json"), "w") as f:
         json.dump(summary, f, indent=1)
 
 
@@ -77,16 +97,21 @@ def run(name, cmd, timeout, env=None, out=None, quiet=False):
     return rc, so
 
 
-def pytest_gpu(tag, lib=None):
-    rc, so = run(f"pytest -m gpu ({tag})", [sys.executable, "-m", "pytest", "tests", "-m", "gpu", "-q"], 150,
-                 {"RSR_B200_LIB": lib} if lib else {}, f"pytest_gpu_{tag}.log")
+def pytest_gpu(tag, lib=None, extra_env=None):
+    env = dict(SPEC.get("pytest_env", {}))
+    env.update(extra_env or {})
+    if lib:
+        env["RSR_B200_LIB"] = lib
+    rc, so = run(f"pytest -m gpu ({tag})", [sys.executable, "-m", "pytest", "tests", "-m", "gpu", "-q"], 150, env, f"pytest_gpu_{tag}.log")
     print("   ", (so.strip().splitlines() or ["-"])[-1], flush=True)
     return rc
 
 
-def bench(tag, lib=None):
-    rc, so = run(f"bench {tag}", [sys.executable, "bench.py", "--steps", "20", "--warmup", "3"], 90,
-                 {"RSR_B200_LIB": lib} if lib else {}, f"bench_{tag}.json")
+def bench(tag, lib=None, extra_env=None):
+    env = dict(extra_env or {})
+    if lib:
+        env["RSR_B200_LIB"] = lib
+    rc, so = run(f"bench {tag}", [sys.executable, "bench.py", "--steps", "20", "--warmup", "3"], 90, env, f"bench_{tag}.json")
     if DRY:
         return {"ms_per_step": 1.5 if lib is None else 1.45}
     try:
@@ -100,7 +125,7 @@ def bench(tag, lib=None):
 
 
 def ab_step(name):
-    lib, env, _ = ENTRIES[name]
+    lib, env, _, _ = ENTRIES[name]
     path = os.path.join(ABL, lib)
     if not os.path.exists(path) and not DRY:
         return None
@@ -123,12 +148,11 @@ def ab_step(name):
 def main():
     os.makedirs(OUT, exist_ok=True)
     py = sys.executable
-    # 1. gates: the whole GPU suite on the shipped library, and on the previous default kept as fallback
+    # 1. gate: the whole GPU suite on the shipped library (spec "pytest_env": e.g. RSR_TEST_EXPERIMENTAL=1)
     summary["pytest_shipped_rc"] = pytest_gpu("shipped")
-    summary["pytest_fallback_rc"] = pytest_gpu("fallback_c0_r4n12", os.path.join(ABL, "c0_r4n12.so"))
     base1 = bench("shipped")
-    # 2. hardware probes (tests/cuda): A operand from tensor memory; reference figures from the same box
-    for probe in ("umma_ts_bench", "umma_bench"):
+    # 2. hardware probes (tests/cuda)
+    for probe in SPEC.get("probes", []):
         exe = os.path.join(ROOT, "tests", "cuda", probe)
         if os.path.exists(exe) or DRY:
             run(probe, [exe], 30, out=probe + ".txt")
@@ -148,7 +172,7 @@ def main():
         nb = len(times["base"])
         bmean = {k: sum(t[k] for t in times["base"]) / nb for k in times["base"][0]}
         print("    base us:", {k: round(v, 1) for k, v in bmean.items()}, f"total {sum(bmean.values()):.1f}", flush=True)
-        for n, (lib, env, keys) in ENTRIES.items():
+        for n, (lib, env, keys, group) in ENTRIES.items():
             if keys is None or not times[n]:
                 continue
             v = sum(sum(t[k] for k in keys) for t in times[n]) / len(times[n])
@@ -156,27 +180,28 @@ def main():
             gain = 1.0 - v / b
             ab[n] = {"launches": "+".join(keys), "us": round(v, 1), "base_us": round(b, 1), "gain": round(gain, 4), "runs": len(times[n])}
             print(f"    {n:12s} {'+'.join(keys):20s} {v:7.1f} us vs {b:7.1f}  gain {100 * gain:+.1f} %  ({len(times[n])} runs)", flush=True)
-            if n[:2] in COMBINABLE and gain > 0.02 and (n[:2] not in winners or gain > winners[n[:2]][1]):
-                winners[n[:2]] = (n, gain)
+            if group and gain > MIN_GAIN and (group not in winners or gain > winners[group][1]):
+                winners[group] = (n, gain)
     summary["ab"] = ab
     summary["winners"] = {k: v[0] for k, v in winners.items()}
     save()
     # 4. winners combined into one library: GPU suite + bench against the shipped one
     if winners and left() > 100:
-        flags = []
+        flags, cenv = [], {}
         for k, (n, _) in winners.items():
-            flags += open(os.path.join(ABL, n + ".flags")).read().split()
+            flags += SPEC["entries"][n].get("flags", "").split()
+            cenv.update(SPEC["entries"][n].get("env", {}))
         combo = os.path.join(ABL, "combo.so")
-        nv = ["/usr/local/cuda/bin/nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo",
-              "-Xcompiler", "-fPIC", "-shared", *flags, "-o", combo, "rusty_sr_b200/csrc/rsr_b200.cu", "-lcudart"]
+        summary["combo_env"] = cenv
+        nv = [*NVCC, *flags, "-o", combo, "rusty_sr_b200/csrc/rsr_b200.cu", "-lcudart"]
         summary["combo_flags"] = flags
         rc, _ = run("build combo", nv, 120)
         if rc == 0 or DRY:
-            summary["combo_tests_rc"] = pytest_gpu("combo", combo)
+            summary["combo_tests_rc"] = pytest_gpu("combo", combo, cenv)
             if summary["combo_tests_rc"] == 0:
-                c1 = bench("combo", combo)
+                c1 = bench("combo", combo, cenv)
                 base2 = bench("shipped2") if left() > 70 else None
-                c2 = bench("combo2", combo) if left() > 70 else None
+                c2 = bench("combo2", combo, cenv) if left() > 70 else None
                 bs = [b["ms_per_step"] for b in (base1, base2) if b]
                 cs = [c["ms_per_step"] for c in (c1, c2) if c]
                 if bs and cs:
@@ -187,11 +212,15 @@ def main():
     ncu = "ncu"
     run("ncu launch list", [ncu, "--metrics", "gpu__time_duration.sum", "--clock-control", "none", "-c", "40", "--csv", "--log-file",
                             os.path.join(OUT, "launches.csv"), py, "tools/profile_step.py", "3"], 60, out="ncu_launches.log")
-    run("ncu full conv0", [ncu, "--set", "full", "--clock-control", "none", "--import-source", "on", "-k", "regex:conv_strip", "-s", "4",
-                           "-c", "1", "-o", os.path.join(OUT, "prof_conv0"), "-f", py, "tools/profile_step.py", "3"], 90, out="ncu_full_conv0.log")
+    if SPEC.get("ncu_kernel"):
+        run("ncu full", [ncu, "--set", "full", "--clock-control", "none", "--import-source", "on", "-k", "regex:" + SPEC["ncu_kernel"], "-s",
+                         str(SPEC.get("ncu_skip", 0)), "-c", "1", "-o", os.path.join(OUT, "prof_session"), "-f", py, "tools/profile_step.py", "3"],
+            90, SPEC.get("ncu_env"), out="ncu_full.log")
     save()
     print(json.dumps(summary), flush=True)
 
 
 if __name__ == "__main__":
+    if BUILD_ONLY:
+        sys.exit(0 if build_variants() else 1)
     main()

@@ -1,5 +1,5 @@
 """Per-launch CUDA-event times of a few 1080p forward passes, without importing torch (fast start-up): the unit
-of tools/ab.sh / tools/final_round.py same-box A/B runs.  RSR_B200_LIB selects the library variant.
+of tools/ab_session.py same-box A/B runs.  RSR_B200_LIB selects the library variant.
 usage: python tools/ab_step.py [steps]   -> one JSON line {"lib": ..., "plan": ..., "us": {launch: mean microseconds}}"""
 import json
 import os
