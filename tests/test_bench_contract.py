@@ -58,3 +58,21 @@ def test_per_launch_roofline_table():
     assert t["conv1|2|3"]["bound"] == "tensor" and 0.3 < t["conv1|2|3"]["frac"] < 0.5
     assert t["pack_input"]["bound"] == "hbm" and all(0 < v["frac"] <= 1.0 for v in t.values())
     assert b.per_launch_roofline({"conv0": float("nan"), "unknown": 1.0}, 10, peaks) == {}
+
+
+def test_recorded_bench_line_has_the_contract_keys_and_matches_the_docs():
+    """profiles/r01j_bench.json (the recorded line of the shipped default plan) carries every key the driver and the judge read,
+    and the headline numbers quoted in README.md / DESIGN.md are the ones in that file."""
+    rec = json.load(open(os.path.join(ROOT, "profiles", "r01j_bench.json")))
+    for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline",
+              "dtype", "data", "config", "roofline", "cpu_baseline", "e2e", "gpu_launches", "clocks"):
+        assert k in rec, k
+    assert set(("bound", "achieved", "peak", "unit", "frac", "traffic")) <= set(rec["roofline"])
+    assert set(("value", "unit", "cores", "kind", "sample")) <= set(rec["cpu_baseline"])
+    assert set(("value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step")) <= set(rec["e2e"])
+    assert rec["gpu_launches"] == 5 * rec["steps"] and rec["config"]["workload"].startswith("1920x1080")
+    assert abs(rec["value"] - 18.6624 / rec["ms_per_step"] * 1e3) < 1.0          # Mpix/s = output Mpix per frame / s per frame
+    assert not {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"} & set(rec["clocks"]["reasons"])
+    ms = f"{rec['ms_per_step']:.3f}"
+    for doc in ("DESIGN.md", os.path.join("profiles", "README.md")):
+        assert ms in open(os.path.join(ROOT, doc)).read(), (doc, ms)
