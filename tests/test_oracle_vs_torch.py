@@ -44,3 +44,23 @@ def test_c_oracle_equals_torch_restatement(weights, wname, case):
     assert got.shape == ref.shape == (x.shape[0] * 3, x.shape[1] * 3, 3)
     assert np.abs(got - ref).max() < 1e-11
     assert np.abs(O.forward(weights[wname], x, 3, np.float32).astype(np.float64) - ref).max() < 5e-5
+
+
+def _srgb_to_linear(t):
+    return torch.where(t <= 0.04045, t / 12.92, ((t + 0.055) / 1.055) ** 2.4)
+
+
+def _linear_to_srgb(t):
+    return torch.where(t <= 0.0031308, t * 12.92, 1.055 * t ** (1.0 / 2.4) - 0.055)
+
+
+@pytest.mark.parametrize("shape", [(12, 15), (1, 1), (7, 5), (40, 31)])
+def test_parameter_free_modes_equal_torch_restatement(shape):
+    """bilinear_net / downsample_net (network.rs:111-138): SrgbToLinear -> LinearInterp | Pooling -> LinearToSrgb.  (Internal
+    consistency of two restatements; the reference commits no output of these modes, so they stay "parity unpinned".)"""
+    x = noise_image(shape[0], shape[1], 17)
+    t = torch.from_numpy(x.astype(np.float64)).permute(2, 0, 1)[None]
+    up = _linear_to_srgb(F.interpolate(_srgb_to_linear(t), scale_factor=3, mode="bilinear", align_corners=False))
+    assert np.abs(O.bilinear(x, 3) - up[0].permute(1, 2, 0).numpy()).max() < 1e-12
+    dn = _linear_to_srgb(F.avg_pool2d(_srgb_to_linear(t), 3, ceil_mode=True, count_include_pad=False))
+    assert np.abs(O.downsample(x, 3) - dn[0].permute(1, 2, 0).numpy()).max() < 1e-12
