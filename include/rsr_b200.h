@@ -102,6 +102,28 @@ int rsr_wait_all(rsr_ctx* ctx);
 int rsr_upscale_band_f32(rsr_ctx* ctx, const float* in_rows, int w, int rows_in, int top_halo,
                          int bottom_halo, float* out_rows);
 
+/* Same for the u8 image form (RGB / RGBA rows in, RGBA rows out). */
+int rsr_upscale_band_u8(rsr_ctx* ctx, const uint8_t* in_rows, int w, int rows_in, int top_halo, int bottom_halo,
+                        int in_channels, uint8_t* out_rows_rgba);
+
+/* Several GPUs from ONE host process — what a single-process host such as the reference CLI (main.rs:33-178) binds
+ * to use a whole box (SURVEY.md 8(b) "multi-GPU variants", 8(e)).  One context per listed device (a device may be
+ * listed more than once), one host thread per context inside each call, no collective:
+ *   rsr_multi_upscale_batch_*: image i of the batch runs on context i mod G (independent units);
+ *   rsr_multi_upscale_frame_*: ONE frame split into G horizontal bands with 7-row input halos (overlap-recompute);
+ *                              the result is bit-identical to rsr_upscale_* of the whole frame on one GPU.
+ * devices == NULL: all visible devices (at most n_devices of them if n_devices > 0).  Errors: as rsr_create /
+ * rsr_upscale_*; the message names the failing device.  Not thread-safe per multi context. */
+typedef struct rsr_multi rsr_multi;
+rsr_multi* rsr_create_multi(const float* params, size_t n_params, int factor, const int* devices, int n_devices, int flags);
+void rsr_destroy_multi(rsr_multi* m);
+int rsr_multi_size(rsr_multi* m);               /* number of contexts G */
+rsr_ctx* rsr_multi_ctx(rsr_multi* m, int i);    /* borrowed: context i (timing / plan queries) */
+int rsr_multi_upscale_batch_f32(rsr_multi* m, const float* in, int n, int w, int h, float* out);
+int rsr_multi_upscale_batch_u8(rsr_multi* m, const uint8_t* in, int n, int w, int h, int in_channels, uint8_t* out_rgba);
+int rsr_multi_upscale_frame_f32(rsr_multi* m, const float* in_hwc3, int w, int h, float* out_hwc3);
+int rsr_multi_upscale_frame_u8(rsr_multi* m, const uint8_t* in, int w, int h, int in_channels, uint8_t* out_rgba);
+
 /* The two parameter-free modes of the reference CLI (no conv net, no rsr_ctx):
  *   rsr_bilinear_*   = bilinear_net(factor)   (network.rs:111-123; `-p bilinear`, main.rs:153-155):
  *                      sRGB -> linear, LinearInterp x factor (half-pixel centres, edge clamp), linear -> sRGB

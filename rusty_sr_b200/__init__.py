@@ -10,7 +10,7 @@ from __future__ import annotations
 
 import ctypes
 import os
-from typing import Optional
+from typing import Optional, Sequence
 
 import numpy as np
 
@@ -19,7 +19,7 @@ from ._lib import RsrError, RSR_FLAG_FUSED_MID, RSR_FLAG_SPLIT_MID, RSR_FLAG_NO_
 from .network import FACTOR, num_params, param_layout
 from .rsr_format import decode_rsr, encode_rsr
 
-__all__ = ["Upscaler", "upscale", "bilinear", "downsample", "conv2d_3x3", "load_builtin_params", "decode_rsr", "encode_rsr", "RsrError",
+__all__ = ["Upscaler", "MultiUpscaler", "upscale", "bilinear", "downsample", "conv2d_3x3", "load_builtin_params", "decode_rsr", "encode_rsr", "RsrError",
            "num_params", "param_layout", "FACTOR", "BUILTIN_PARAMETERS", "RSR_FLAG_FUSED_MID", "RSR_FLAG_SPLIT_MID", "RSR_FLAG_NO_PAIRS"]
 
 _RES = os.path.join(os.path.dirname(os.path.abspath(__file__)), "res")
@@ -267,6 +267,89 @@ def conv2d_3x3(x: np.ndarray, weights: np.ndarray, device: int = 0, iters: int =
     ms = ctypes.c_float(0.0)
     _lib.check(L.rsr_conv2d_3x3_f32(device, _as_ptr(x), _as_ptr(wt), W, H, ci, co, _as_ptr(out), iters, ctypes.byref(ms)))
     return out, float(ms.value)
+
+
+
+class MultiUpscaler:
+    """Several GPUs from one host process (rsr_create_multi, include/rsr_b200.h): one context per listed device, one host
+    thread per context inside each call, no collective.  `devices=None`: every visible device."""
+
+    def __init__(self, params: Optional[np.ndarray] = None, parameters: str = "imagenet", factor: int = FACTOR,
+                 devices: Optional[Sequence[int]] = None, flags: int = 0):
+        if params is None:
+            params = load_builtin_params(parameters)
+        params = np.ascontiguousarray(params, dtype=np.float32).ravel()
+        self._L = _lib.load()
+        self.factor = factor
+        dev = None if devices is None else (ctypes.c_int * len(devices))(*[int(d) for d in devices])
+        h = self._L.rsr_create_multi(params.ctypes.data_as(ctypes.POINTER(ctypes.c_float)), params.size, factor,
+                                     dev, 0 if devices is None else len(devices), int(flags))
+        if not h:
+            code = self._L.rsr_last_error_code()
+            msg = self._L.rsr_last_error().decode("utf-8", "replace")
+            if code == _lib.RSR_E_PARAM_COUNT:
+                raise ValueError(msg)
+            raise RsrError(code, msg)
+        self._h = ctypes.c_void_p(h)
+
+    def close(self) -> None:
+        if getattr(self, "_h", None):
+            self._L.rsr_destroy_multi(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def size(self) -> int:
+        return int(self._L.rsr_multi_size(self._h))
+
+    def forward_batch(self, x_nhwc3: np.ndarray) -> np.ndarray:
+        """Image batch, image i on context i mod G.  f32 [N][H][W][3] -> f32 [N][fH][fW][3]."""
+        x = np.ascontiguousarray(x_nhwc3, dtype=np.float32)
+        if x.ndim != 4 or x.shape[3] != 3:
+            raise ValueError("expected [N][H][W][3]")
+        N, H, W = x.shape[:3]
+        out = np.empty((N, H * self.factor, W * self.factor, 3), np.float32)
+        _lib.check(self._L.rsr_multi_upscale_batch_f32(self._h, _as_ptr(x), N, W, H, _as_ptr(out)))
+        return out
+
+    def forward_batch_u8(self, imgs: np.ndarray) -> np.ndarray:
+        """u8 [N][H][W][3|4] -> RGBA u8 [N][fH][fW][4]."""
+        x = np.ascontiguousarray(imgs, dtype=np.uint8)
+        if x.ndim != 4 or x.shape[3] not in (3, 4):
+            raise ValueError("expected [N][H][W][3|4]")
+        N, H, W, C = x.shape
+        out = np.empty((N, H * self.factor, W * self.factor, 4), np.uint8)
+        _lib.check(self._L.rsr_multi_upscale_batch_u8(self._h, _as_ptr(x), N, W, H, C, _as_ptr(out)))
+        return out
+
+    def forward_frame(self, x_hwc3: np.ndarray) -> np.ndarray:
+        """ONE frame as G horizontal bands with 7-row input halos; bit-identical to Upscaler.forward of the frame."""
+        x = np.ascontiguousarray(x_hwc3, dtype=np.float32)
+        if x.ndim != 3 or x.shape[2] != 3:
+            raise ValueError("expected [H][W][3]")
+        H, W = x.shape[:2]
+        out = np.empty((H * self.factor, W * self.factor, 3), np.float32)
+        _lib.check(self._L.rsr_multi_upscale_frame_f32(self._h, _as_ptr(x), W, H, _as_ptr(out)))
+        return out
+
+    def forward_frame_u8(self, img: np.ndarray) -> np.ndarray:
+        x = np.ascontiguousarray(img, dtype=np.uint8)
+        if x.ndim != 3 or x.shape[2] not in (3, 4):
+            raise ValueError("expected [H][W][3|4]")
+        H, W, C = x.shape
+        out = np.empty((H * self.factor, W * self.factor, 4), np.uint8)
+        _lib.check(self._L.rsr_multi_upscale_frame_u8(self._h, _as_ptr(x), W, H, C, _as_ptr(out)))
+        return out
 
 
 def upscale(input_image: np.ndarray, parameters: str = "imagenet", custom: Optional[str] = None,

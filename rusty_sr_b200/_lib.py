@@ -22,7 +22,9 @@ RSR_FLAG_NO_PAIRS = 4    # every launch on single CTAs (no cta_group::2 kernels)
 EXPORTS = (
     "rsr_num_params", "rsr_create", "rsr_destroy", "rsr_upscale_f32", "rsr_upscale_u8",
     "rsr_upscale_batch_f32", "rsr_upscale_batch_u8", "rsr_upscale_device_f32",
-    "rsr_upscale_device_u8", "rsr_synchronize", "rsr_submit_u8", "rsr_submit_f32", "rsr_wait", "rsr_wait_all", "rsr_upscale_band_f32", "rsr_set_stream",
+    "rsr_upscale_device_u8", "rsr_synchronize", "rsr_submit_u8", "rsr_submit_f32", "rsr_wait", "rsr_wait_all", "rsr_upscale_band_f32", "rsr_upscale_band_u8", "rsr_set_stream",
+    "rsr_create_multi", "rsr_destroy_multi", "rsr_multi_size", "rsr_multi_ctx", "rsr_multi_upscale_batch_f32",
+    "rsr_multi_upscale_batch_u8", "rsr_multi_upscale_frame_f32", "rsr_multi_upscale_frame_u8",
     "rsr_last_kernel_times", "rsr_kernel_name", "rsr_last_launch_count", "rsr_plan", "rsr_last_error",
     "rsr_last_error_code", "rsr_version", "rsr_debug_stop_after", "rsr_debug_read_node",
     "rsr_debug_profile", "rsr_debug_read_profile", "rsr_debug_fused", "rsr_debug_read_fused_profile",
@@ -66,6 +68,18 @@ def load() -> ctypes.CDLL:
     L.rsr_wait.argtypes = [vp, ci]
     L.rsr_wait_all.argtypes = [vp]
     L.rsr_upscale_band_f32.argtypes = [vp, vp, ci, ci, ci, ci, vp]
+    L.rsr_upscale_band_u8.argtypes = [vp, vp, ci, ci, ci, ci, ci, vp]
+    L.rsr_create_multi.restype = vp
+    L.rsr_create_multi.argtypes = [vp, ctypes.c_size_t, ci, vp, ci, ci]
+    L.rsr_destroy_multi.argtypes = [vp]
+    L.rsr_destroy_multi.restype = None
+    L.rsr_multi_size.argtypes = [vp]
+    L.rsr_multi_ctx.argtypes = [vp, ci]
+    L.rsr_multi_ctx.restype = vp
+    L.rsr_multi_upscale_batch_f32.argtypes = [vp, vp, ci, ci, ci, vp]
+    L.rsr_multi_upscale_batch_u8.argtypes = [vp, vp, ci, ci, ci, ci, vp]
+    L.rsr_multi_upscale_frame_f32.argtypes = [vp, vp, ci, ci, vp]
+    L.rsr_multi_upscale_frame_u8.argtypes = [vp, vp, ci, ci, ci, vp]
     L.rsr_set_stream.argtypes = [vp, vp]
     L.rsr_last_kernel_times.argtypes = [vp, fp, ci]
     L.rsr_kernel_name.restype = ctypes.c_char_p

@@ -15,6 +15,7 @@
 #include <cstring>
 #include <new>
 #include <string>
+#include <thread>
 #include <type_traits>
 #include <vector>
 
@@ -953,6 +954,15 @@ extern "C" int rsr_upscale_band_f32(rsr_ctx* c, const float* in_rows, int w, int
                         (rows_in - top_halo - bottom_halo) * F);
 }
 
+extern "C" int rsr_upscale_band_u8(rsr_ctx* c, const uint8_t* in_rows, int w, int rows_in, int top_halo, int bottom_halo,
+                                   int in_channels, uint8_t* out_rows_rgba) {
+    if (top_halo < 0 || bottom_halo < 0 || rows_in - top_halo - bottom_halo < 1)
+        return fail(RSR_E_BAD_ARG, "bad band: rows_in=%d top_halo=%d bottom_halo=%d", rows_in, top_halo, bottom_halo);
+    const int F = c ? c->factor : 3;
+    return upscale_host(c, in_rows, true, in_channels, 1, w, rows_in, nullptr, out_rows_rgba, top_halo * F,
+                        (rows_in - top_halo - bottom_halo) * F);
+}
+
 extern "C" int rsr_last_kernel_times(rsr_ctx* c, float* ms, int cap) {
     if (!c || !ms) return fail(RSR_E_BAD_ARG, "null argument");
     if (!c->timed) return 0;
@@ -1342,4 +1352,131 @@ extern "C" int rsr_conv2d_3x3_f32(int device, const float* x, const float* weigh
 #undef CV_TRY
     cleanup();
     return 0;
+}
+
+// ------------------------------------------------------------------ several GPUs from ONE host process
+// The reference CLI is a single process (main.rs:33-178); these entry points let such a host use every GPU of the box
+// (SURVEY.md 8(b) "multi-GPU variants", 8(e)): one context per device, one host thread per device, no collective —
+// image batches shard as independent units (image i -> device i mod G), one large frame shards as horizontal bands with
+// 7-row input halos (overlap-recompute; bit-identical to the unsharded frame).  The one-process-per-GPU form of the same
+// plans (torchrun, NCCL) lives in rusty_sr_b200/sharding.py and bench.py.
+struct rsr_multi {
+    std::vector<rsr_ctx*> ctx;
+};
+
+extern "C" rsr_multi* rsr_create_multi(const float* params, size_t n_params, int factor, const int* devices, int n_devices, int flags) {
+    g_err.clear();
+    g_err_code = 0;
+    std::vector<int> dev;
+    if (devices) {
+        if (n_devices < 1) { fail(RSR_E_BAD_ARG, "n_devices must be >= 1 (got %d)", n_devices); return nullptr; }
+        dev.assign(devices, devices + n_devices);
+    } else {   // all visible devices (at most n_devices of them when n_devices > 0)
+        int cnt = 0;
+        cudaError_t e = cudaGetDeviceCount(&cnt);
+        if (e != cudaSuccess || cnt < 1) {
+            fail(RSR_E_CUDA, "no CUDA device: %s", e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+            return nullptr;
+        }
+        if (n_devices > 0 && n_devices < cnt) cnt = n_devices;
+        for (int i = 0; i < cnt; ++i) dev.push_back(i);
+    }
+    rsr_multi* m = new (std::nothrow) rsr_multi;
+    if (!m) { fail(RSR_E_OOM, "out of host memory"); return nullptr; }
+    for (int d : dev) {
+        rsr_ctx* c = rsr_create(params, n_params, factor, d, flags);
+        if (!c) {   // keep rsr_create's error for the caller
+            const std::string keep = g_err;
+            const int code = g_err_code;
+            for (rsr_ctx* x : m->ctx) rsr_destroy(x);
+            delete m;
+            g_err = keep;
+            g_err_code = code;
+            return nullptr;
+        }
+        m->ctx.push_back(c);
+    }
+    return m;
+}
+
+extern "C" void rsr_destroy_multi(rsr_multi* m) {
+    if (!m) return;
+    for (rsr_ctx* c : m->ctx) rsr_destroy(c);
+    delete m;
+}
+
+extern "C" int rsr_multi_size(rsr_multi* m) { return m ? (int)m->ctx.size() : 0; }
+extern "C" rsr_ctx* rsr_multi_ctx(rsr_multi* m, int i) { return (m && i >= 0 && i < (int)m->ctx.size()) ? m->ctx[i] : nullptr; }
+
+// Runs job(g) on one host thread per context; the first failure (lowest device slot) becomes the caller's error.
+template <class Job>
+static int multi_run(rsr_multi* m, Job job) {
+    const int G = (int)m->ctx.size();
+    std::vector<int> rc(G, 0);
+    std::vector<std::string> msg(G);
+    std::vector<std::thread> th;
+    th.reserve(G);
+    for (int g = 0; g < G; ++g)
+        th.emplace_back([&, g]() {
+            rc[g] = job(g);
+            if (rc[g] != 0) msg[g] = g_err;   // thread-local in the worker: hand it to the caller
+        });
+    for (auto& t : th) t.join();
+    for (int g = 0; g < G; ++g)
+        if (rc[g] != 0) return fail(rc[g] < 0 ? rc[g] : RSR_E_CUDA, "device slot %d (cuda:%d): %s", g, m->ctx[g]->device, msg[g].c_str());
+    return 0;
+}
+
+static int multi_batch(rsr_multi* m, const void* in, bool u8, int in_ch, int n, int w, int h, void* out) {
+    if (!m || m->ctx.empty()) return fail(RSR_E_BAD_ARG, "multi context is null");
+    if (!in || !out) return fail(RSR_E_BAD_ARG, "null buffer");
+    if (n < 1 || w < 1 || h < 1) return fail(RSR_E_BAD_ARG, "bad dimensions n=%d w=%d h=%d", n, w, h);
+    if (u8 && in_ch != 3 && in_ch != 4) return fail(RSR_E_BAD_ARG, "in_channels must be 3 or 4 (got %d)", in_ch);
+    const int G = (int)m->ctx.size(), F = m->ctx[0]->factor;
+    const size_t in_img = (size_t)w * h * (u8 ? (size_t)in_ch : 3 * sizeof(float));
+    const size_t out_img = (size_t)w * h * F * F * (u8 ? 4 : 3 * sizeof(float));
+    return multi_run(m, [&](int g) -> int {
+        rsr_ctx* c = m->ctx[g];
+        for (int i = g; i < n; i += G) {   // image i -> device slot i mod G; up to three frames in flight per device
+            const uint8_t* src = (const uint8_t*)in + (size_t)i * in_img;
+            uint8_t* dst = (uint8_t*)out + (size_t)i * out_img;
+            const int t = u8 ? rsr_submit_u8(c, src, w, h, in_ch, dst) : rsr_submit_f32(c, (const float*)src, w, h, (float*)dst);
+            if (t < 0) { rsr_wait_all(c); return t; }
+        }
+        return rsr_wait_all(c);
+    });
+}
+extern "C" int rsr_multi_upscale_batch_u8(rsr_multi* m, const uint8_t* in, int n, int w, int h, int in_channels, uint8_t* out_rgba) {
+    return multi_batch(m, in, true, in_channels, n, w, h, out_rgba);
+}
+extern "C" int rsr_multi_upscale_batch_f32(rsr_multi* m, const float* in, int n, int w, int h, float* out) {
+    return multi_batch(m, in, false, 3, n, w, h, out);
+}
+
+static int multi_frame(rsr_multi* m, const void* in, bool u8, int in_ch, int w, int h, void* out) {
+    if (!m || m->ctx.empty()) return fail(RSR_E_BAD_ARG, "multi context is null");
+    if (!in || !out) return fail(RSR_E_BAD_ARG, "null buffer");
+    if (w < 1 || h < 1) return fail(RSR_E_BAD_ARG, "bad dimensions w=%d h=%d", w, h);
+    if (u8 && in_ch != 3 && in_ch != 4) return fail(RSR_E_BAD_ARG, "in_channels must be 3 or 4 (got %d)", in_ch);
+    const int G = (int)m->ctx.size(), F = m->ctx[0]->factor;
+    const int HALO = 7;   // receptive field of sr_net in rows: 2 + 2 + 1 + 1 + 1 (network.rs:33,60-72)
+    const size_t in_row = (size_t)w * (u8 ? (size_t)in_ch : 3 * sizeof(float));
+    const size_t out_row = (size_t)w * F * (u8 ? 4 : 3 * sizeof(float));
+    return multi_run(m, [&](int g) -> int {
+        // band g owns LR rows [y0, y1) (sizes differ by at most one row; slots beyond the row count stay idle)
+        const int y0 = (int)((long long)g * h / G), y1 = (int)((long long)(g + 1) * h / G);
+        if (y1 <= y0) return 0;
+        const int top = y0 < HALO ? y0 : HALO, bot = h - y1 < HALO ? h - y1 : HALO;
+        const uint8_t* src = (const uint8_t*)in + (size_t)(y0 - top) * in_row;
+        uint8_t* dst = (uint8_t*)out + (size_t)y0 * F * out_row;
+        const int rows_in = y1 - y0 + top + bot;
+        return u8 ? rsr_upscale_band_u8(m->ctx[g], src, w, rows_in, top, bot, in_ch, dst)
+                  : rsr_upscale_band_f32(m->ctx[g], (const float*)src, w, rows_in, top, bot, (float*)dst);
+    });
+}
+extern "C" int rsr_multi_upscale_frame_f32(rsr_multi* m, const float* in, int w, int h, float* out) {
+    return multi_frame(m, in, false, 3, w, h, out);
+}
+extern "C" int rsr_multi_upscale_frame_u8(rsr_multi* m, const uint8_t* in, int w, int h, int in_channels, uint8_t* out_rgba) {
+    return multi_frame(m, in, true, in_channels, w, h, out_rgba);
 }
