@@ -120,21 +120,33 @@ class Upscaler:
         raise ValueError("expected [H][W][C] or [N][H][W][C]")
 
     # -- pipelined host calls: copies of neighbouring frames overlap the compute -----------------
+    def _check_frame(self, a: np.ndarray, out: np.ndarray, dtype, in_channels, out_channels: int) -> tuple:
+        # explicit checks (not asserts): a wrongly sized `out` would let the asynchronous copy write past the buffer
+        for name, t in (("input", a), ("out", out)):
+            if not isinstance(t, np.ndarray) or t.dtype != dtype or not t.flags.c_contiguous:
+                raise ValueError(f"{name} must be a C-contiguous numpy array of dtype {np.dtype(dtype).name}")
+        if a.ndim != 3 or a.shape[2] not in in_channels:
+            raise ValueError(f"expected an [H][W][{'|'.join(map(str, in_channels))}] frame, got shape {a.shape}")
+        H, W, C = a.shape
+        want = (H * self.factor, W * self.factor, out_channels)
+        if out.shape != want:
+            raise ValueError(f"out must have shape {want}, got {out.shape}")
+        return H, W, C
+
     def submit_u8(self, img: np.ndarray, out: np.ndarray) -> int:
-        """Enqueue one frame (u8 [H][W][3|4] -> u8 RGBA `out`, both C-contiguous and ideally pinned);
-        returns a ticket for wait().  Buffers must stay alive until then."""
-        assert img.dtype == np.uint8 and img.flags.c_contiguous and out.dtype == np.uint8 and out.flags.c_contiguous
-        H, W, C = img.shape
-        assert out.shape == (H * self.factor, W * self.factor, 4)
-        t = self._L.rsr_submit_u8(self._h, _as_ptr(img), W, H, C, _as_ptr(out))
+        """Enqueue one frame (u8 [H][W][3|4] -> u8 `out`, both C-contiguous and ideally pinned); `out` is RGBA
+        [fH][fW][4] (data_to_img(..).to_rgba(), main.rs:175) or RGB [fH][fW][3] (data_to_img alone: the alpha the
+        reference adds on the host is constant 255).  Returns a ticket for wait(); buffers must stay alive until then."""
+        oc = out.shape[2] if isinstance(out, np.ndarray) and out.ndim == 3 and out.shape[2] in (3, 4) else 4
+        H, W, C = self._check_frame(img, out, np.uint8, (3, 4), oc)
+        fn = self._L.rsr_submit_u8 if oc == 4 else self._L.rsr_submit_u8_rgb
+        t = fn(self._h, _as_ptr(img), W, H, C, _as_ptr(out))
         if t < 0:
             _lib.check(t)
         return t
 
     def submit_f32(self, x: np.ndarray, out: np.ndarray) -> int:
-        assert x.dtype == np.float32 and x.flags.c_contiguous and out.dtype == np.float32 and out.flags.c_contiguous
-        H, W, _ = x.shape
-        assert out.shape == (H * self.factor, W * self.factor, 3)
+        H, W, _ = self._check_frame(x, out, np.float32, (3,), 3)
         t = self._L.rsr_submit_f32(self._h, _as_ptr(x), W, H, _as_ptr(out))
         if t < 0:
             _lib.check(t)

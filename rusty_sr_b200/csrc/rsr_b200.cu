@@ -294,7 +294,7 @@ struct rsr_ctx {
         bool used = false;
     } slot[3];
     cudaStream_t s_h2d = nullptr, s_d2h = nullptr;
-    long next_ticket = 0;
+    long long next_ticket = 0;
     long long* prof = nullptr;  // test hook: [K_COUNT][256][16] wait-cycle counters
     int prof_grid[K_COUNT] = {};
     PFN_cuTensorMapEncodeTiled_v12000 encode = nullptr;
@@ -877,7 +877,7 @@ static int submit_host(rsr_ctx* c, const void* in, bool u8, int in_ch, int w, in
     if (w < 1 || h < 1) return fail(RSR_E_BAD_ARG, "bad dimensions w=%d h=%d", w, h);
     if (u8 && in_ch != 3 && in_ch != 4) return fail(RSR_E_BAD_ARG, "in_channels must be 3 or 4 (got %d)", in_ch);
     CUDA_TRY(cudaSetDevice(c->device));
-    const long ticket = c->next_ticket;
+    const long long ticket = c->next_ticket;
     rsr_ctx::Slot& sl = c->slot[ticket % 3];
     const int F = c->factor;
     const size_t npx = (size_t)w * h, opx = npx * F * F;
@@ -914,11 +914,14 @@ extern "C" int rsr_submit_f32(rsr_ctx* c, const float* in, int w, int h, float* 
 }
 extern "C" int rsr_wait(rsr_ctx* c, int ticket) {
     if (!c) return fail(RSR_E_BAD_ARG, "ctx is null");
-    const long newest = c->next_ticket - 1;
-    const long t = newest - ((newest - ticket) & 0x3fffffff);   // undo the 30-bit wrap
-    if (ticket < 0 || t > newest) return fail(RSR_E_BAD_ARG, "unknown ticket %d", ticket);
-    if (newest - t >= 3) return 0;  // slot already recycled: frames complete in order, so it is done
+    const long long newest = c->next_ticket - 1;
+    // tickets are handed out modulo 2^30: the one meant is the most recent ticket number congruent to `ticket`
+    const long long t = newest - ((newest - (long long)ticket) & 0x3fffffff);
+    if (ticket < 0 || ticket > 0x3fffffff || t < 0) return fail(RSR_E_BAD_ARG, "unknown ticket %d (%lld issued so far)", ticket, newest + 1);
     CUDA_TRY(cudaSetDevice(c->device));
+    // Frame t used slot t % NSLOT.  If the slot has been re-used since, its event belongs to a LATER frame of the same slot;
+    // device->host copies are ordered on one stream, so that event completing implies frame t's copy has completed too
+    // (conservative, never early).
     cudaError_t e = cudaEventSynchronize(c->slot[t % 3].ev_out);
     if (e != cudaSuccess)
         return fail(RSR_E_CUDA, "frame failed: %s (fault word 0x%x)", cudaGetErrorString(e), c->fault_host ? c->fault_host[0] : 0);

@@ -38,7 +38,9 @@ inline Image read_png(const std::string& path) {
         const char* type = reinterpret_cast<const char*>(&buf[off + 4]);
         const uint8_t* data = &buf[off + 8];
         if (off + 12 + len > buf.size()) throw std::runtime_error("truncated PNG");
+        if (crc32(crc32(0L, Z_NULL, 0), &buf[off + 4], 4 + len) != be32(&buf[off + 8 + len])) throw std::runtime_error("PNG chunk CRC mismatch");
         if (!memcmp(type, "IHDR", 4)) {
+            if (len != 13) throw std::runtime_error("malformed PNG: IHDR length is not 13");
             w = (int)be32(data); h = (int)be32(data + 4); depth = data[8]; ctype = data[9]; interlace = data[12];
         } else if (!memcmp(type, "PLTE", 4)) plte.assign(data, data + len);
         else if (!memcmp(type, "tRNS", 4)) trns.assign(data, data + len);

@@ -1,6 +1,6 @@
 """Static description of the reference graph `sr_net(factor, None)` (src/network.rs:16-109):
-which ops exist, in which order their parameters sit in the flat vector (op-registration
-order, network.rs:27-76), and how the GPU path groups the ten convolutions into launches.
+which ops exist and in which order their parameters sit in the flat vector (op-registration
+order, network.rs:27-76).
 Pure metadata — the arithmetic is in csrc/."""
 from __future__ import annotations
 
@@ -53,39 +53,3 @@ def num_params(factor: int = FACTOR) -> int:
     """graph.num_params() (main.rs:162): 130459 for factor 3."""
     spans = param_layout(factor)
     return spans[-1].offset + spans[-1].count
-
-
-# conv name -> (input node, output node, kernel size, Cin, Cout at factor 3)   network.rs:33,60-72
-CONVS = {
-    "conv0": ("input", "f_conv", 5, 3, 32),
-    "conv1": ("f_activ", "l1_conv", 5, 32, 32), "conv2": ("f_activ", "l2_conv", 5, 32, 32),
-    "conv3": ("f_activ", "l3_conv", 5, 32, 32),
-    "conv5": ("l1_activ", "l2_conv", 3, 32, 32), "conv6": ("l1_activ", "l3_conv", 3, 32, 32),
-    "conv7": ("l1_activ", "expand", 3, 32, 27),
-    "conv8": ("l2_activ", "l3_conv", 3, 32, 32), "conv9": ("l2_activ", "expand", 3, 32, 27),
-    "conv10": ("l3_activ", "expand", 3, 32, 27),
-}
-
-# GPU launches in order (names match rsr_kernel_name()): which reference convs each one fuses.
-LAUNCHES = [
-    ("pack_input", []),
-    ("conv0", ["conv0"]),
-    ("conv1|2|3", ["conv1", "conv2", "conv3"]),
-    ("conv5|6|7", ["conv5", "conv6", "conv7"]),
-    ("conv8|9", ["conv8", "conv9"]),
-    ("conv10+expand+skip", ["conv10"]),
-]
-
-
-def conv_flops_per_lr_pixel(name: str) -> int:
-    _, _, k, ci, co = CONVS[name]
-    return 2 * k * k * ci * co
-
-
-def conv_bytes_per_lr_pixel(name: str) -> int:
-    """fp32 activations read once + written once (weights are negligible)."""
-    _, _, _, ci, co = CONVS[name]
-    return 4 * (ci + co)
-
-
-FLOPS_PER_LR_PIXEL = sum(conv_flops_per_lr_pixel(c) for c in CONVS)  # 260352
