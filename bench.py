@@ -215,6 +215,8 @@ def run_ours(args):
     if sampler:
         sampler.start()
     plan_flags = {"default": 0, "fused": R.RSR_FLAG_FUSED_MID, "split": R.RSR_FLAG_SPLIT_MID}[args.plan]
+    if args.prec == "bf16x3":
+        plan_flags |= R.RSR_FLAG_BF16X3
     up = R.Upscaler(parameters="imagenet", device=local, flags=plan_flags)
     stream = torch.cuda.Stream(device=dev)
     up.set_stream(stream.cuda_stream)
@@ -394,6 +396,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--plan", default="default", choices=["default", "fused", "split"],
                     help="launch plan of the middle levels (include/rsr_b200.h RSR_FLAG_*_MID); default = library default")
+    ap.add_argument("--prec", default="default", choices=["default", "bf16x3"],
+                    help="operand format of the 32-channel convolutions: default = fp16 + 2 x fp8 (2 MMAs per K chunk), bf16x3 = RSR_FLAG_BF16X3")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

@@ -39,16 +39,23 @@ enum {
      * FUSED_MID: conv5|6|7 and conv8|9 run as ONE launch that keeps l2 in shared memory and the running
      *            partial sums in tensor memory (5 launches per call, 768 B/pixel less HBM traffic);
      * SPLIT_MID: two launches with l2 and the partial sums stored to HBM in between (6 launches per call).
-     * Neither flag: the library default (the RSR_B200_FUSED=0|1 environment variable overrides it). */
+     * Neither flag: chosen per call from the image width (the fused launch works on 124-pixel strips, the split launches
+     *            on 128-pixel strips, so e.g. 256-pixel-wide patches run the split plan).  Factor 4 always runs SPLIT_MID. */
     RSR_FLAG_FUSED_MID = 1,
     RSR_FLAG_SPLIT_MID = 2,
     /* Run every conv launch on single CTAs (conv_strip.cuh) even where the library default uses CTA pairs
-     * (tcgen05 cta_group::2, conv_pair.cuh; RSR_B200_PAIR=<launch bit mask> overrides the default). */
-    RSR_FLAG_NO_PAIRS = 4
+     * (tcgen05 cta_group::2, conv_pair.cuh). */
+    RSR_FLAG_NO_PAIRS = 4,
+    /* Operand precision of the 32-channel convolutions.  Default: fp16 x fp16 plus two fp8 (e4m3) correction products per
+     * term, 2 tensor-core MMAs per K chunk: max-abs error vs the fp64 reference <= 3e-4 in linear light on uniform-noise
+     * input, <= 5e-5 on natural images (contract: 1e-3).  BF16X3: three bf16 products per term (3 MMAs per K chunk):
+     * <= 8e-5 everywhere, ~1.3x slower. */
+    RSR_FLAG_BF16X3 = 8
 };
 
 /* graph.num_params() of sr_net(factor, None): 130459 for factor 3 (main.rs:162; layout in
- * network.rs:27-76 op-registration order).  Returns 0 for an unsupported factor. */
+ * network.rs:27-76 op-registration order; the three `expand` convolutions have 3 * factor^2 output channels,
+ * network.rs:37).  Factors 1..4 are supported (the reference is compiled with FACTOR = 3, main.rs:31); 0 otherwise. */
 size_t rsr_num_params(int factor);
 
 /* Builds the device-side network from the flat parameter vector the reference passes as
@@ -69,6 +76,10 @@ int rsr_upscale_f32(rsr_ctx* ctx, const float* in_hwc3, int w, int h, float* out
  * in  : host [h][w][in_channels] u8, in_channels 3 (RGB) or 4 (RGBA)
  * out : host [factor*h][factor*w][4] u8 RGBA. */
 int rsr_upscale_u8(rsr_ctx* ctx, const uint8_t* in, int w, int h, int in_channels, uint8_t* out_rgba);
+/* The same without the constant alpha channel: out is [factor*h][factor*w][3] u8 RGB = data_to_img(..) (main.rs:175);
+ * `.to_rgba()` is a host-side step in the reference, so a host that adds alpha itself saves a quarter of the
+ * device->host bytes. */
+int rsr_upscale_u8_rgb(rsr_ctx* ctx, const uint8_t* in, int w, int h, int in_channels, uint8_t* out_rgb);
 
 /* Batches of n equally sized images, contiguous [n][h][w][c] (image-batch sharding unit). */
 int rsr_upscale_batch_f32(rsr_ctx* ctx, const float* in, int n, int w, int h, float* out);
@@ -82,6 +93,14 @@ int rsr_upscale_device_f32(rsr_ctx* ctx, const float* d_in, int n, int w, int h,
                            uint8_t* d_out_rgba);
 int rsr_upscale_device_u8(rsr_ctx* ctx, const uint8_t* d_in, int n, int w, int h, int in_channels,
                           float* d_out_f32, uint8_t* d_out_rgba);
+int rsr_upscale_device_u8_rgb(rsr_ctx* ctx, const uint8_t* d_in, int n, int w, int h, int in_channels, uint8_t* d_out_rgb);
+/* Device-resident band of a larger frame (see rsr_upscale_band_f32): d_in_rows holds rows_in input rows including
+ * top_halo / bottom_halo halo rows; only the factor * (rows_in - top_halo - bottom_halo) output rows of the band are
+ * computed by the last launch and written to d_out_rows (out_channels 3 = RGB, 4 = RGBA).  Enqueued, not synchronised. */
+int rsr_upscale_band_device_f32(rsr_ctx* ctx, const float* d_in_rows, int w, int rows_in, int top_halo, int bottom_halo,
+                                float* d_out_rows);
+int rsr_upscale_band_device_u8(rsr_ctx* ctx, const uint8_t* d_in_rows, int w, int rows_in, int top_halo, int bottom_halo,
+                               int in_channels, uint8_t* d_out_rows, int out_channels);
 int rsr_synchronize(rsr_ctx* ctx);
 
 /* Pipelined host entry points: submit returns at once with a ticket (>= 0, or a negative error);
@@ -90,6 +109,7 @@ int rsr_synchronize(rsr_ctx* ctx);
  * flight).  `in` and `out_rgba` must stay valid — and should be pinned host memory for the copies to
  * be asynchronous — until rsr_wait(ticket) returns.  Frames complete in submission order. */
 int rsr_submit_u8(rsr_ctx* ctx, const uint8_t* in, int w, int h, int in_channels, uint8_t* out_rgba);
+int rsr_submit_u8_rgb(rsr_ctx* ctx, const uint8_t* in, int w, int h, int in_channels, uint8_t* out_rgb);
 int rsr_submit_f32(rsr_ctx* ctx, const float* in_hwc3, int w, int h, float* out_hwc3);
 int rsr_wait(rsr_ctx* ctx, int ticket);
 int rsr_wait_all(rsr_ctx* ctx);
@@ -146,6 +166,14 @@ int rsr_downsample_u8(int device, const uint8_t* in, int w, int h, int in_channe
 int rsr_conv2d_3x3_f32(int device, const float* x, const float* weights, int w, int h, int cin, int cout,
                        float* out, int iters, float* kernel_ms);
 
+/* The parameter-file codec of the reference: bytevec `<Vec<f32>>::decode::<u32>` (main.rs:138,146-152,194) and
+ * `.encode::<u32>()` (main.rs:213): u32 LE count | count x u32 LE element sizes (all 4) | count x f32 LE.  Host only.
+ * encode returns the bytes written (rsr_rsr_encoded_size(n)), decode the number of parameters in the blob (at most `cap`
+ * of them are written; params may be NULL to query); negative RSR_E_BAD_ARG on a malformed blob / short buffer. */
+size_t rsr_rsr_encoded_size(size_t n_params);
+long long rsr_rsr_encode(const float* params, size_t n_params, uint8_t* out, size_t cap);
+long long rsr_rsr_decode(const uint8_t* data, size_t len, float* params, size_t cap);
+
 /* Use an externally created CUDA stream (cudaStream_t passed as void*) instead of the
  * context's own; NULL restores the internal stream. */
 int rsr_set_stream(rsr_ctx* ctx, void* cuda_stream);
@@ -162,13 +190,15 @@ int rsr_last_launch_count(rsr_ctx* ctx);
 const char* rsr_plan(rsr_ctx* ctx);
 
 /* Test hooks (used by tests/ to localise a parity failure to one launch; not needed by a host
- * integration).  rsr_debug_stop_after(k): subsequent calls stop after launch index k (see
+ * integration).  rsr_debug_create = rsr_create with an explicit CTA-pair launch mask (bit 2: conv1|2|3, bit 3: the fused
+ * middle launch; negative = library default).  rsr_debug_stop_after(k): subsequent calls stop after launch index k (see
  * rsr_kernel_name; negative = run everything; outputs are then not written).  rsr_debug_read_node
  * copies one workspace buffer of the most recent call to the host as f32 [n*h*w][32]:
  * which = 0: activation buffer A (f, later l2), 1: activation buffer B (l1, later l3),
  *         2: partial buffer A (conv2(f), later expand), 3: partial buffer B (l3_conv partial),
  *         4: partial buffer C (expand partial of the fused middle launch; there l3 lives in buffer A),
  *         5, 6: debug dumps of the fused middle launch (rsr_debug_fused). */
+rsr_ctx* rsr_debug_create(const float* params, size_t n_params, int factor, int device, int flags, int pair_mask);
 int rsr_debug_stop_after(rsr_ctx* ctx, int launch_index);
 int rsr_debug_read_node(rsr_ctx* ctx, int which, float* out, size_t n_pixels);
 /* Per-CTA wait-cycle counters of the conv launches (which mbarrier each warp role waited on, in SM
@@ -187,7 +217,7 @@ int rsr_debug_read_profile(rsr_ctx* ctx, int launch_index, long long* out, int c
 const char* rsr_last_error(void);
 int rsr_last_error_code(void);
 
-/* Build identification, e.g. "rsr_b200 0.1 sm_100a". */
+/* Build identification, e.g. "rsr_b200 0.2 sm_100a ...". */
 const char* rsr_version(void);
 
 #ifdef __cplusplus

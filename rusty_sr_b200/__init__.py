@@ -15,12 +15,12 @@ from typing import Optional, Sequence
 import numpy as np
 
 from . import _lib
-from ._lib import RsrError, RSR_FLAG_FUSED_MID, RSR_FLAG_SPLIT_MID, RSR_FLAG_NO_PAIRS
+from ._lib import RsrError, RSR_FLAG_FUSED_MID, RSR_FLAG_SPLIT_MID, RSR_FLAG_NO_PAIRS, RSR_FLAG_BF16X3
 from .network import FACTOR, num_params, param_layout
 from .rsr_format import decode_rsr, encode_rsr
 
 __all__ = ["Upscaler", "MultiUpscaler", "upscale", "bilinear", "downsample", "conv2d_3x3", "load_builtin_params", "decode_rsr", "encode_rsr", "RsrError",
-           "num_params", "param_layout", "FACTOR", "BUILTIN_PARAMETERS", "RSR_FLAG_FUSED_MID", "RSR_FLAG_SPLIT_MID", "RSR_FLAG_NO_PAIRS"]
+           "num_params", "param_layout", "FACTOR", "BUILTIN_PARAMETERS", "RSR_FLAG_FUSED_MID", "RSR_FLAG_SPLIT_MID", "RSR_FLAG_NO_PAIRS", "RSR_FLAG_BF16X3"]
 
 _RES = os.path.join(os.path.dirname(os.path.abspath(__file__)), "res")
 
@@ -45,9 +45,10 @@ class Upscaler:
     main.rs:133-158).  Not thread-safe, like the reference's `&mut Graph`."""
 
     def __init__(self, params: Optional[np.ndarray] = None, parameters: str = "imagenet",
-                 factor: int = FACTOR, device: int = 0, flags: int = 0):
-        """`flags`: RSR_FLAG_FUSED_MID / RSR_FLAG_SPLIT_MID select the launch plan of the middle levels
-        (include/rsr_b200.h); 0 = library default."""
+                 factor: int = FACTOR, device: int = 0, flags: int = 0, pair_mask: Optional[int] = None):
+        """`flags`: RSR_FLAG_FUSED_MID / RSR_FLAG_SPLIT_MID select the launch plan of the middle levels, RSR_FLAG_BF16X3
+        the three-product operand split (include/rsr_b200.h); 0 = library default.  `pair_mask` (tests only): which
+        launches run on CTA pairs (rsr_debug_create)."""
         if params is None:
             params = load_builtin_params(parameters)
         params = np.ascontiguousarray(params, dtype=np.float32).ravel()
@@ -55,8 +56,11 @@ class Upscaler:
         self.factor = factor
         self.device = device
         self.n_params = int(params.size)
-        h = self._L.rsr_create(params.ctypes.data_as(ctypes.POINTER(ctypes.c_float)), params.size,
-                               factor, device, int(flags))
+        pp = params.ctypes.data_as(ctypes.POINTER(ctypes.c_float))
+        if pair_mask is None:
+            h = self._L.rsr_create(pp, params.size, factor, device, int(flags))
+        else:
+            h = self._L.rsr_debug_create(pp, params.size, factor, device, int(flags), int(pair_mask))
         if not h:
             code = self._L.rsr_last_error_code()
             msg = self._L.rsr_last_error().decode("utf-8", "replace")
@@ -103,14 +107,16 @@ class Upscaler:
             return out
         raise ValueError("expected [H][W][3] or [N][H][W][3]")
 
-    def forward_u8(self, img: np.ndarray) -> np.ndarray:
+    def forward_u8(self, img: np.ndarray, rgb: bool = False) -> np.ndarray:
         """img_to_data -> forward -> data_to_img(..).to_rgba() fused on the device
-        (main.rs:170-175).  img: u8 [H][W][3|4] or [N][H][W][3|4] -> u8 RGBA [.., fH, fW, 4]."""
+        (main.rs:170-175).  img: u8 [H][W][3|4] or [N][H][W][3|4] -> u8 RGBA [.., fH, fW, 4];
+        rgb=True (single images): u8 RGB [fH][fW][3], i.e. data_to_img without the constant alpha."""
         a = np.ascontiguousarray(img, dtype=np.uint8)
         if a.ndim == 3:
             H, W, C = a.shape
-            out = np.empty((H * self.factor, W * self.factor, 4), np.uint8)
-            _lib.check(self._L.rsr_upscale_u8(self._h, _as_ptr(a), W, H, C, _as_ptr(out)))
+            out = np.empty((H * self.factor, W * self.factor, 3 if rgb else 4), np.uint8)
+            fn = self._L.rsr_upscale_u8_rgb if rgb else self._L.rsr_upscale_u8
+            _lib.check(fn(self._h, _as_ptr(a), W, H, C, _as_ptr(out)))
             return out
         if a.ndim == 4:
             N, H, W, C = a.shape
@@ -180,6 +186,18 @@ class Upscaler:
             rc = self._L.rsr_upscale_device_f32(self._h, ctypes.c_void_p(d_in), n, w, h,
                                                 ctypes.c_void_p(d_out_f32 or None),
                                                 ctypes.c_void_p(d_out_rgba or None))
+        _lib.check(rc)
+
+    def forward_band_device(self, d_in_rows: int, w: int, rows_in: int, top_halo: int, bottom_halo: int, d_out: int,
+                            u8_channels: int = 0, out_channels: int = 0) -> None:
+        """Device-resident band (rsr_upscale_band_device_*): u8_channels = 0 -> f32 in / f32 out, else u8 in / u8 out with
+        out_channels 3 (RGB) or 4 (RGBA).  Enqueued on the context's stream, not synchronised."""
+        if u8_channels:
+            rc = self._L.rsr_upscale_band_device_u8(self._h, ctypes.c_void_p(d_in_rows), w, rows_in, top_halo, bottom_halo,
+                                                    u8_channels, ctypes.c_void_p(d_out), out_channels or 4)
+        else:
+            rc = self._L.rsr_upscale_band_device_f32(self._h, ctypes.c_void_p(d_in_rows), w, rows_in, top_halo, bottom_halo,
+                                                     ctypes.c_void_p(d_out))
         _lib.check(rc)
 
     def set_stream(self, cuda_stream: int) -> None:

@@ -17,6 +17,7 @@ RSR_E_UNSUPPORTED = -5
 RSR_FLAG_FUSED_MID = 1   # rsr_create flags (include/rsr_b200.h)
 RSR_FLAG_SPLIT_MID = 2
 RSR_FLAG_NO_PAIRS = 4    # every launch on single CTAs (no cta_group::2 kernels)
+RSR_FLAG_BF16X3 = 8      # three bf16 products per term instead of fp16 + two fp8 corrections (more accurate, slower)
 
 # every symbol include/rsr_b200.h declares (checked by tests/test_abi.py)
 EXPORTS = (
@@ -29,6 +30,8 @@ EXPORTS = (
     "rsr_last_error_code", "rsr_version", "rsr_debug_stop_after", "rsr_debug_read_node",
     "rsr_debug_profile", "rsr_debug_read_profile", "rsr_debug_fused", "rsr_debug_read_fused_profile",
     "rsr_bilinear_f32", "rsr_bilinear_u8", "rsr_downsample_f32", "rsr_downsample_u8", "rsr_conv2d_3x3_f32",
+    "rsr_upscale_u8_rgb", "rsr_upscale_device_u8_rgb", "rsr_upscale_band_device_f32", "rsr_upscale_band_device_u8",
+    "rsr_submit_u8_rgb", "rsr_rsr_encoded_size", "rsr_rsr_encode", "rsr_rsr_decode", "rsr_debug_create",
 )
 
 _lib = None
@@ -54,6 +57,8 @@ def load() -> ctypes.CDLL:
     L.rsr_num_params.argtypes = [ci]
     L.rsr_create.restype = vp
     L.rsr_create.argtypes = [fp, ctypes.c_size_t, ci, ci, ci]
+    L.rsr_debug_create.restype = vp
+    L.rsr_debug_create.argtypes = [fp, ctypes.c_size_t, ci, ci, ci, ci]
     L.rsr_destroy.restype = None
     L.rsr_destroy.argtypes = [vp]
     L.rsr_upscale_f32.argtypes = [vp, vp, ci, ci, vp]
@@ -63,6 +68,17 @@ def load() -> ctypes.CDLL:
     L.rsr_upscale_device_f32.argtypes = [vp, vp, ci, ci, ci, vp, vp]
     L.rsr_upscale_device_u8.argtypes = [vp, vp, ci, ci, ci, ci, vp, vp]
     L.rsr_synchronize.argtypes = [vp]
+    L.rsr_upscale_u8_rgb.argtypes = [vp, u8p, ci, ci, ci, u8p]
+    L.rsr_upscale_device_u8_rgb.argtypes = [vp, vp, ci, ci, ci, ci, vp]
+    L.rsr_upscale_band_device_f32.argtypes = [vp, vp, ci, ci, ci, ci, vp]
+    L.rsr_upscale_band_device_u8.argtypes = [vp, vp, ci, ci, ci, ci, ci, vp, ci]
+    L.rsr_submit_u8_rgb.argtypes = [vp, u8p, ci, ci, ci, u8p]
+    L.rsr_rsr_encoded_size.restype = ctypes.c_size_t
+    L.rsr_rsr_encoded_size.argtypes = [ctypes.c_size_t]
+    L.rsr_rsr_encode.restype = ctypes.c_longlong
+    L.rsr_rsr_encode.argtypes = [vp, ctypes.c_size_t, vp, ctypes.c_size_t]
+    L.rsr_rsr_decode.restype = ctypes.c_longlong
+    L.rsr_rsr_decode.argtypes = [vp, ctypes.c_size_t, vp, ctypes.c_size_t]
     L.rsr_submit_u8.argtypes = [vp, u8p, ci, ci, ci, u8p]
     L.rsr_submit_f32.argtypes = [vp, vp, ci, ci, vp]
     L.rsr_wait.argtypes = [vp, ci]
@@ -113,8 +129,9 @@ def load() -> ctypes.CDLL:
     for name in ("rsr_upscale_f32", "rsr_upscale_u8", "rsr_upscale_batch_f32", "rsr_upscale_batch_u8",
                  "rsr_upscale_device_f32", "rsr_upscale_device_u8", "rsr_synchronize", "rsr_submit_u8",
                  "rsr_submit_f32", "rsr_wait", "rsr_wait_all", "rsr_submit_u8", "rsr_submit_f32", "rsr_wait", "rsr_wait_all",
-                 "rsr_upscale_band_f32", "rsr_set_stream", "rsr_last_kernel_times",
-                 "rsr_last_launch_count"):
+                 "rsr_upscale_band_f32", "rsr_upscale_band_u8", "rsr_set_stream", "rsr_last_kernel_times",
+                 "rsr_last_launch_count", "rsr_upscale_u8_rgb", "rsr_upscale_device_u8_rgb", "rsr_upscale_band_device_f32",
+                 "rsr_upscale_band_device_u8", "rsr_submit_u8_rgb"):
         getattr(L, name).restype = ci
     _lib = L
     return L

@@ -5,8 +5,8 @@
 //     l2 = BeLU(conv2(f) + conv5(l1) + l2_bias)                        (network.rs:61,65,51,55)
 //     l3 = BeLU(conv3(f) + conv6(l1) + conv8(l2) + l3_bias)            (network.rs:62,66,69,52,56)
 //     E  = conv7(l1) + conv9(l2)            (partial of `expand`;      network.rs:67,70)
-// Inputs from HBM: l1 (split bf16), P2 = conv2(f), P3 = conv3(f) (fp32, written by the conv1|2|3 launch).
-// Outputs to HBM: l3 (split bf16) and E (fp32).  l2, the updated P3 and the first half of E never leave
+// Inputs from HBM: l1 (split storage format, conv_strip.cuh), P2 = conv2(f), P3 = conv3(f) (fp32, written by the conv1|2|3
+// launch).  Outputs to HBM: l3 (split format) and E (fp32).  l2, the updated P3 and the first half of E never leave
 // the SM: 640 B per pixel of HBM traffic instead of 1408 B for the two separate launches.
 //
 // How: a CTA walks down a 124-pixel-wide column strip, one image row per step.
@@ -99,9 +99,10 @@ enum : int {
 #ifndef RSR_FUSED_PAIR_NR1
 #define RSR_FUSED_PAIR_NR1 4
 #endif
-template <bool PAIR_>
+template <bool PAIR_, int PREC_ = PREC_BF16X3>
 struct FusedCfgT {
     static constexpr bool PAIR = PAIR_;
+    static constexpr int PREC = PREC_;          // operand / activation storage format (conv_strip.cuh)
     static constexpr int STRIP = 124;          // output pixels per strip
     static constexpr int L2W = 126;            // valid l2 pixels per strip row
     static constexpr int SLOT = 128 * 128;     // one row slot: 128 pixels x 128 B
@@ -118,6 +119,7 @@ struct FusedCfgT {
     static_assert(9 % TPS == 0, "taps per stage must divide 9");
     static constexpr int NT = 5;               // TMEM row slots of 96 columns
     static constexpr int TCOLS = 96;
+    static constexpr int SF_COL = NT * TCOLS;  // PREC_F16MX: scale-factor columns 480..511 of the 512 allocated
     static constexpr int LOOKAHEAD = 4;        // S1 rows issued before the first S2 of a work item
     static constexpr int NTHREADS = 13 * 32;
     static constexpr int NARR = PAIR ? 8 : 4;  // epilogue-warp arrivals on l2_full / t_empty (both CTAs of a pair)
@@ -134,7 +136,7 @@ struct FusedCfgT {
     static_assert(OFF_BAR % 1024 == 0 && BST % 1024 == 0, "1024-byte swizzle atoms");
     static_assert(SMEM_BYTES <= 232448, "shared memory budget");
 };
-using FusedCfg = FusedCfgT<false>;
+using FusedCfg = FusedCfgT<false>;   // (geometry constants that do not depend on PAIR / PREC)
 
 struct FItem {
     int img, x0, y_b, n, y_e;   // rows y_b .. y_b+n-1 are computed, rows >= y_e are not stored
@@ -198,9 +200,9 @@ __device__ __forceinline__ bool fitem_next(const FusedParams& p, long long& cur,
 
 // DBG: compile the test hooks (dumps, S2 skip, wait profile) in — they cost ~25 % when merely present.
 // PAIR: CTA-pair variant; must be launched with cluster dimension 2.
-template <bool DBG, bool PAIR>
+template <bool DBG, bool PAIR, int PREC>
 __global__ void __launch_bounds__(FusedCfg::NTHREADS, 1) conv_fused_mid_kernel(const __grid_constant__ FusedParams p) {
-    using C = FusedCfgT<PAIR>;
+    using C = FusedCfgT<PAIR, PREC>;
     const uint32_t rank = PAIR ? cluster_ctarank() : 0u;
     const bool leader = rank == 0;
     extern __shared__ uint8_t smem_raw[];
@@ -255,9 +257,14 @@ __global__ void __launch_bounds__(FusedCfg::NTHREADS, 1) conv_fused_mid_kernel(c
     }
     tc_fence_before();
     __syncthreads();
-    if (PAIR) cluster_sync_all();   // both CTAs' barriers exist before any cross-CTA signal
     tc_fence_after();
     const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
+    init_scale_factors<C>(tmem_base, warp);
+    if (PAIR) {   // both CTAs' barriers exist (and scale factors are written) before any cross-CTA signal
+        tc_fence_before();
+        cluster_sync_all();
+        tc_fence_after();
+    }
 
     // work ranges are per cluster (pair) or per CTA
     const long long nrange = PAIR ? gridDim.x >> 1 : gridDim.x, irange = PAIR ? blockIdx.x >> 1 : blockIdx.x;
@@ -360,18 +367,13 @@ __global__ void __launch_bounds__(FusedCfg::NTHREADS, 1) conv_fused_mid_kernel(c
     } else if (warp == 1) {
         // ===== MMA issuer (pair: the leader's, for both CTAs) =====
         if (leader) {
-        constexpr uint32_t HI = (uint32_t)make_sdesc_hi(1024, UMMA_SW_128B);
-        constexpr uint32_t IDESC1 = make_idesc_bf16(PAIR ? 256 : 128, 96);
-        constexpr uint32_t IDESC2 = make_idesc_bf16(PAIR ? 256 : 128, 64);
-        auto mma = [](uint32_t d, uint64_t a, uint64_t b, uint32_t idesc, uint32_t acc) {
-            if (PAIR) umma2_f16(d, a, b, idesc, acc); else umma_f16(d, a, b, idesc, acc);
-        };
+        using MM = SplitMma<PREC, PAIR ? 2 : 1, 128>;
+        constexpr int MM_M = PAIR ? 256 : 128;
+        const uint32_t sf = tmem_base + C::SF_COL;
         auto commit = [](uint64_t* bar) { if (PAIR) umma2_commit(bar); else umma_commit(bar); };
         // (barriers that the epilogue warps of both CTAs arrive on need a cluster-scope acquire in the pair kernel: FWPC)
         constexpr uint32_t LBO = 1u << 16;
-        constexpr uint32_t MID = 64 >> 4;   // encoded offset of the mid plane inside a pixel's 128 B
         const uint32_t sA_e = (smem_u32(sA) >> 4) | LBO, sL_e = (smem_u32(sL) >> 4) | LBO, sB_e = (smem_u32(sB) >> 4) | LBO;
-        auto desc = [](uint32_t hi, uint32_t lo) { return ((uint64_t)hi << 32) | lo; };
         uint32_t c1_item = 0, a_item = 0;   // counters at the start of the current item
         uint32_t a_wait = 0, l2_wait = 0;   // rows already waited for
         uint32_t c2 = 0;                    // S2 rows so far
@@ -408,11 +410,7 @@ __global__ void __launch_bounds__(FusedCfg::NTHREADS, 1) conv_fused_mid_kernel(c
                         const uint32_t b_e = sB_e + bst * (C::BST >> 4) + tt * (C::TAP1 >> 4);
                         const uint32_t a_e = arow[ta] + tb * (128 >> 4);
                         #pragma unroll
-                        for (int k = 0; k < 2; ++k) {
-                            mma(d, desc(HI, a_e + 2 * k), desc(HI, b_e + 2 * k), IDESC1, (t | k) != 0 ? 1u : 0u);
-                            mma(d, desc(HI, a_e + MID + 2 * k), desc(HI, b_e + 2 * k), IDESC1, 1);
-                            mma(d, desc(HI, a_e + 2 * k), desc(HI, b_e + MID + 2 * k), IDESC1, 1);
-                        }
+                        for (int k = 0; k < 2; ++k) MM::chunk(d, a_e, b_e, k, MM_M, 96, sf, (t | k) != 0 ? 1u : 0u);
                         if (t == 2) commit(&a_empty[(a_item + q) % C::NR1]);   // top window row is dead
                     }
                     commit(&b_empty[bst]);
@@ -459,9 +457,7 @@ __global__ void __launch_bounds__(FusedCfg::NTHREADS, 1) conv_fused_mid_kernel(c
                         #pragma unroll
                         for (int k = 0; k < 2; ++k) {
                             if (DBG && (p.dbg_flags & 1)) continue;
-                            mma(d, desc(HI, a_e + 2 * k), desc(HI, b_e + 2 * k), IDESC2, 1);
-                            mma(d, desc(HI, a_e + MID + 2 * k), desc(HI, b_e + 2 * k), IDESC2, 1);
-                            mma(d, desc(HI, a_e + 2 * k), desc(HI, b_e + MID + 2 * k), IDESC2, 1);
+                            MM::chunk(d, a_e, b_e, k, MM_M, 64, sf, 1);
                         }
                         if (t == 2) commit(&l2_empty[(c1_item + r) % C::NR2]);
                     }
@@ -537,21 +533,11 @@ __global__ void __launch_bounds__(FusedCfg::NTHREADS, 1) conv_fused_mid_kernel(c
                     #pragma unroll
                     for (int i = 0; i < 8; ++i) dst[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
                 }
-                uint32_t hi[16], mid[16];
-                #pragma unroll
-                for (int i = 0; i < 16; ++i) {
-                    split_pair(v[2 * i], v[2 * i + 1], hi[i], mid[i]);
-                    if (!valid) { hi[i] = 0u; mid[i] = 0u; }
-                }
+                uint32_t words[32];
+                pack_split_row<PREC>(v, words, !valid);
                 // the MMAs that read the previous occupant of this ring slot must have completed
                 FWP(&l2_empty[ls], ((c / C::NR2) & 1) ^ 1, 32, FP_E1_L2_EMPTY);
-                const uint32_t row = sL_u + ls * C::SLOT + m * 128;
-                const uint32_t sw = m & 7;
-                #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    st_shared_v4(row + ((j ^ sw) << 4), hi[4 * j], hi[4 * j + 1], hi[4 * j + 2], hi[4 * j + 3]);
-                    st_shared_v4(row + (((4 + j) ^ sw) << 4), mid[4 * j], mid[4 * j + 1], mid[4 * j + 2], mid[4 * j + 3]);
-                }
+                store_row_swizzled(words, sL_u + ls * C::SLOT + m * 128, m & 7);
                 fence_proxy_async_smem();   // generic-proxy writes -> visible to the tensor core's async-proxy reads
                 tc_fence_before();
                 __syncwarp();
@@ -615,7 +601,7 @@ __global__ void __launch_bounds__(FusedCfg::NTHREADS, 1) conv_fused_mid_kernel(c
                         __syncwarp();
                         if (FPROF_ON) prof_acc[FP_E2_STORE_READ] += clock64() - t0s;
                     }
-                    if (srow >= 0) epi_split_to_stage(p.g_l3, v, stage, srow);
+                    if (srow >= 0) epi_split_to_stage<PREC>(p.g_l3, v, stage, srow);
                     fence_proxy_async_smem();
                     __syncwarp();
                     if (elect_one()) {

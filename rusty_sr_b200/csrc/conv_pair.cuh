@@ -27,78 +27,6 @@
 
 namespace rsr {
 
-// ---- cluster / cta_group::2 PTX ----------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t cluster_ctarank() {
-    uint32_t r;
-    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-    return r;
-}
-__device__ __forceinline__ void cluster_sync_all() {
-    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
-    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-// shared::cluster address of `addr` (a shared::cta address of this CTA) in CTA `rank` of the cluster
-__device__ __forceinline__ uint32_t map_to_cta(uint32_t addr, uint32_t rank) {
-    uint32_t r;
-    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
-    return r;
-}
-__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
-}
-__device__ __forceinline__ bool mbar_try_wait_cluster(uint64_t* bar, uint32_t parity) {
-    uint32_t ok;
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n"
-        "selp.u32 %0, 1, 0, p;\n"
-        "}\n"
-        : "=r"(ok)
-        : "r"(smem_u32(bar)), "r"(parity)
-        : "memory");
-    return ok != 0;
-}
-__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity, int* g_fault, int tag) {
-    if (mbar_try_wait_cluster(bar, parity)) return;
-    uint32_t spins = 0;
-    while (!mbar_try_wait_cluster(bar, parity)) {
-        if (++spins > (1u << 24)) mbar_timeout(bar, parity, g_fault, tag);
-    }
-}
-// TMA loads whose completion is signalled on a barrier of the CTA pair (here: always the leader's)
-__device__ __forceinline__ void tma2_load_2d(uint32_t smem_dst, const CUtensorMap* m, uint32_t bar_cluster, int c0, int c1) {
-    asm volatile(
-        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.tile.mbarrier::complete_tx::bytes"
-        " [%0], [%1, {%3, %4}], [%2];"
-        ::"r"(smem_dst), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar_cluster), "r"(c0), "r"(c1)
-        : "memory");
-}
-__device__ __forceinline__ void tma2_load_4d(uint32_t smem_dst, const CUtensorMap* m, uint32_t bar_cluster, int c0, int c1,
-                                             int c2, int c3) {
-    asm volatile(
-        "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.tile.mbarrier::complete_tx::bytes"
-        " [%0], [%1, {%3, %4, %5, %6}], [%2];"
-        ::"r"(smem_dst), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar_cluster), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
-        : "memory");
-}
-__device__ __forceinline__ void umma2_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "setp.ne.b32 p, %4, 0;\n"
-        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n"
-        "}\n"
-        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-        : "memory");
-}
-// arrives (count 1) on the barrier at this shared-memory offset in BOTH CTAs once all prior MMAs of this thread completed
-__device__ __forceinline__ void umma2_commit(uint64_t* bar) {
-    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
-                 ::"r"(smem_u32(bar)), "h"((uint16_t)3)
-                 : "memory");
-}
-
 struct PairIter {
     long long cur, end;
     int rows;
@@ -129,7 +57,6 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(C::NTHREADS, 1) conv
     uint8_t* sA = smem;
     uint8_t* sB = smem + P::OFF_B;
     uint8_t* sP = smem + P::OFF_P;
-    uint8_t* sO = smem + P::OFF_O;
     uint64_t* a_full = reinterpret_cast<uint64_t*>(smem + P::OFF_BAR);
     uint64_t* a_empty = a_full + C::NR;
     uint64_t* b_full = a_empty + C::NR;
@@ -168,9 +95,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(C::NTHREADS, 1) conv
     }
     tc_fence_before();
     __syncthreads();
-    cluster_sync_all();     // both CTAs' barriers are initialised before any cross-CTA signal
     tc_fence_after();
     const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
+    init_scale_factors<C>(tmem_base, warp);   // (each CTA its own tensor memory; before the cluster barrier)
+    tc_fence_before();
+    cluster_sync_all();     // both CTAs' barriers are initialised (and scale factors written) before any cross-CTA signal
+    tc_fence_after();
 
     PairIter it;
     {
@@ -240,14 +170,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(C::NTHREADS, 1) conv
     } else if (warp == 1) {
         // ===== MMA issuer: leader CTA only; every MMA multiplies both CTAs' pixel tiles (M = 256) =====
         if (leader) {
-            constexpr uint32_t HI = (uint32_t)make_sdesc_hi(8 * C::RB, C::SWZ);
-            constexpr uint32_t IDESC = make_idesc_bf16(256, C::NCOL);
+            using MM = SplitMma<C::PREC, 2, C::RB>;
             constexpr uint32_t LBO = 1u << 16;
-            constexpr uint32_t MID = (C::RB / 2) >> 4;
             constexpr int WIN = C::R + 2 * C::PH;
             constexpr int NEARLY = C::R < C::KH ? C::R : C::KH;
             const uint32_t sA_e = (smem_u32(sA) >> 4) | LBO, sB_e = (smem_u32(sB) >> 4) | LBO;
-            auto desc = [](uint32_t hi, uint32_t lo) { return ((uint64_t)hi << 32) | lo; };
+            const uint32_t sf = tmem_base + C::SF_COL;
             uint32_t slot0 = 0;
             uint32_t wslot = 0, wpar = 0;
             uint32_t bst = 0, bpar = 0;
@@ -288,11 +216,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(C::NTHREADS, 1) conv
                                         const uint32_t a_e = arow[r + ta] + tb * (C::RB >> 4);
                                         const uint32_t d = d_pass + r * C::NCOL;
                                         #pragma unroll
-                                        for (int c = 0; c < C::KC; ++c) {
-                                            umma2_f16(d, desc(HI, a_e + 2 * c), desc(HI, b_e + 2 * c), IDESC, (t | c) != 0 ? 1u : 0u);
-                                            umma2_f16(d, desc(HI, a_e + MID + 2 * c), desc(HI, b_e + 2 * c), IDESC, 1);
-                                            umma2_f16(d, desc(HI, a_e + 2 * c), desc(HI, b_e + MID + 2 * c), IDESC, 1);
-                                        }
+                                        for (int c = 0; c < C::KC; ++c) MM::chunk(d, a_e, b_e, c, 256, C::NCOL, sf, (t | c) != 0 ? 1u : 0u);
                                     }
                                     if (tb == C::KW - 1 && ta < NEARLY) {
                                         uint32_t sl = slot0 + ta;
@@ -327,146 +251,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(C::NTHREADS, 1) conv
             }
         }
     } else if (warp >= 4) {
-        // ===== epilogue (per CTA, as in conv_strip.cuh; "drained" is signalled to the leader's t_empty) =====
-        const int e = warp - 4;
-        const int ew = e & 3;
-        const int eh = e >> 2;
-        const uint32_t stage0 = smem_u32(sO) + e * (C::NOUT * 4096);
+        // ===== epilogue (per CTA, conv_strip.cuh; "drained" is signalled to the LEADER's t_empty) =====
         const uint32_t t_empty0 = map_to_cta(smem_u32(t_empty), 0);
-        uint32_t buf = 0, tpar = 0, oc = 0;
-        uint32_t pst = 0, ppar = 0;
-        const uint32_t sP_u = smem_u32(sP);
-        while (pair_item_next<C>(p, it, rank, w)) {
-            const int xw = w.x0 + ew * 32;
-            const int x = xw + lane;
-            for (int j = 0; j < w.npass; ++j, buf ^= 1, tpar ^= (buf == 0)) {
-                SkipNb nb;
-                if (C::SHUF) {
-                    const int y = w.y_b + j * C::R + eh;
-                    if (y < w.y_e && x < p.W) load_skip_nb(p, w.img, y, x, nb);
-                }
-                mbar_wait(&t_full[buf], tpar, p.fault, 6);
-                tc_fence_after();
-                #pragma unroll 1
-                for (int r = 0; r < C::R; ++r) {
-                    const int y = w.y_b + j * C::R + r;
-                    const bool row_live = y < w.y_e && xw < p.W;
-                    #pragma unroll 1
-                    for (int g = 0; g < C::NG; ++g) {
-                        const EpiGroup& eg = p.grp[g];
-                        if (eg.kind == EPI_NONE) continue;
-                        const bool pin = C::NPIN > 0 && eg.has_pin;
-                        const bool mine = C::NEPI == 4 || (((r * C::NG + g) & 1) == eh);
-                        if (!mine || !row_live) {
-                            // every epilogue warp observes every partial-sum tile (see conv_strip.cuh)
-                            if (pin) {
-                                mbar_wait(&p_full[pst], ppar, p.fault, 9);
-                                __syncwarp();
-                                if (lane == 0) mbar_arrive(&p_empty[pst]);
-                                if (++pst == NPB) { pst = 0; ppar ^= 1; }
-                            }
-                            continue;
-                        }
-                        uint32_t raw[32];
-                        tmem_ld_32x32(tmem_base + ((uint32_t)(ew * 32) << 16) + buf * (C::R * C::NCOL) + r * C::NCOL + g * 32, raw);
-                        tmem_ld_wait();
-                        float v[32];
-                        #pragma unroll
-                        for (int k = 0; k < 32; ++k) v[k] = __uint_as_float(raw[k]);
-                        if (pin) {
-                            mbar_wait(&p_full[pst], ppar, p.fault, 9);
-                            epi_add_partial_tile(v, sP_u + pst * C::PIN_BYTES, ew * 32 + lane);
-                            __syncwarp();
-                            if (lane == 0) mbar_arrive(&p_empty[pst]);
-                            if (++pst == NPB) { pst = 0; ppar ^= 1; }
-                        }
-                        const uint32_t stage = stage0 + (oc % C::NOUT) * 4096;
-                        if (elect_one())
-                            asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(C::NOUT - 1) : "memory");
-                        __syncwarp();
-                        if (!C::SHUF) {
-                            if (eg.kind == EPI_RAW) epi_raw_to_stage(v, stage, lane);
-                            else epi_split_to_stage(eg, v, stage, lane);
-                            fence_proxy_async_smem();
-                            __syncwarp();
-                            if (elect_one()) {
-                                asm volatile(
-                                    "cp.async.bulk.tensor.4d.global.shared::cta.tile.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
-                                    ::"l"(reinterpret_cast<uint64_t>(&p.tmOut[g])), "r"(stage), "r"(eg.c0), "r"(xw), "r"(y),
-                                      "r"(w.img)
-                                    : "memory");
-                                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-                            }
-                        } else {
-                            if (r > eh && x < p.W) load_skip_nb(p, w.img, y, x, nb);
-                            {
-                                const float4* b4 = reinterpret_cast<const float4*>(eg.bias);
-                                #pragma unroll
-                                for (int i = 0; i < 8; ++i) {
-                                    const float4 t = __ldg(b4 + i);
-                                    v[4 * i + 0] += t.x; v[4 * i + 1] += t.y; v[4 * i + 2] += t.z; v[4 * i + 3] += t.w;
-                                }
-                            }
-                            float o[3][9];
-                            if (x >= p.W) {
-                                #pragma unroll
-                                for (int a = 0; a < 3; ++a)
-                                    #pragma unroll
-                                    for (int b = 0; b < 3; ++b) { nb.v[a][b][0] = 0.f; nb.v[a][b][1] = 0.f; nb.v[a][b][2] = 0.f; }
-                            }
-                            shuffle_pixel(v, nb, o);
-                            const int npx_valid = min(32, p.W - xw);
-                            const size_t W3 = (size_t)p.W * 3;
-                            const size_t orow0 = ((size_t)w.img * p.H * 3 + (size_t)y * 3) * W3 + (size_t)xw * 3;
-                            if (p.out_f32) {
-                                float* sf = reinterpret_cast<float*>(smem + P::OFF_O) + (e * C::NOUT + (oc % C::NOUT)) * 1024;
-                                #pragma unroll
-                                for (int dy = 0; dy < 3; ++dy)
-                                    #pragma unroll
-                                    for (int k = 0; k < 9; ++k) sf[dy * 288 + lane * 9 + k] = o[dy][k];
-                                __syncwarp();
-                                const int nfl = npx_valid * 9;
-                                #pragma unroll
-                                for (int dy = 0; dy < 3; ++dy) {
-                                    float* dst = p.out_f32 + (orow0 + (size_t)dy * W3) * 3;
-                                    if (npx_valid == 32 && p.out_vec_ok) {
-                                        for (int i = lane; i < 72; i += 32)
-                                            reinterpret_cast<float4*>(dst)[i] = reinterpret_cast<const float4*>(sf + dy * 288)[i];
-                                    } else {
-                                        for (int i = lane; i < nfl; i += 32) dst[i] = sf[dy * 288 + i];
-                                    }
-                                }
-                            }
-                            if (p.out_u8) {
-                                uint32_t* sq = reinterpret_cast<uint32_t*>(smem + P::OFF_O) + (e * C::NOUT + (oc % C::NOUT)) * 1024;
-                                #pragma unroll
-                                for (int dy = 0; dy < 3; ++dy)
-                                    #pragma unroll
-                                    for (int dx = 0; dx < 3; ++dx) {
-                                        const uint32_t r8 = (uint32_t)(fminf(fmaxf(o[dy][dx * 3 + 0], 0.f), 1.f) * 255.0f + 0.5f);
-                                        const uint32_t g8 = (uint32_t)(fminf(fmaxf(o[dy][dx * 3 + 1], 0.f), 1.f) * 255.0f + 0.5f);
-                                        const uint32_t b8 = (uint32_t)(fminf(fmaxf(o[dy][dx * 3 + 2], 0.f), 1.f) * 255.0f + 0.5f);
-                                        sq[dy * 96 + lane * 3 + dx] = r8 | (g8 << 8) | (b8 << 16) | 0xFF000000u;
-                                    }
-                                __syncwarp();
-                                const int nu = npx_valid * 3;
-                                #pragma unroll
-                                for (int dy = 0; dy < 3; ++dy) {
-                                    uint32_t* dst = reinterpret_cast<uint32_t*>(p.out_u8) + orow0 + (size_t)dy * W3;
-                                    for (int i = lane; i < nu; i += 32) dst[i] = sq[dy * 96 + i];
-                                }
-                            }
-                            __syncwarp();
-                        }
-                        ++oc;
-                    }
-                }
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive_cluster(t_empty0 + buf * 8);
-            }
-        }
-        if (elect_one()) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+        long long prof_acc[8];   // (the pair kernel carries no wait profile; dead)
+        conv_epilogue_role<C>(p, smem, p_full, p_empty, t_full, tmem_base, warp, lane, prof_acc,
+                              [&](WorkItem& wi) { return pair_item_next<C>(p, it, rank, wi); },
+                              [&](uint32_t buf) { mbar_arrive_cluster(t_empty0 + buf * 8); });
     }
     // neither CTA may leave (or free its tensor memory) while the pair's MMAs / remote arrivals can still touch it
     tc_fence_before();

@@ -3,14 +3,23 @@
 // Replaces alumina's Convolution (+ Bias + BeLU + Expand + LinearInterp) ops that
 // `graph.forward` executes for sr_net (reference src/network.rs:27-72, src/main.rs:171).
 //
-// Formulation ("by input"): one launch takes ONE input node (32 channels, stored as a split-bf16
-// pair hi|mid = 128 B per pixel) and computes EVERY convolution that reads it, as one GEMM with
-// the output channels of those convolutions concatenated along N:
+// Formulation ("by input"): one launch takes ONE input node (32 channels, 128 B per pixel in a split
+// storage format, below) and computes EVERY convolution that reads it, as one GEMM with the output
+// channels of those convolutions concatenated along N:
 //     D[pixel, n] = sum_{tap, ci} A[pixel + tap, ci] * W[tap][n][ci]
 //   M = 128 consecutive pixels of one image row, N = 32 * NG, K = taps * 32.
-// fp32-grade accuracy on the bf16 tensor pipe comes from the 3-term split product
-//     a*w ~= a_hi*w_hi + a_mid*w_hi + a_hi*w_mid          ("BF16x3")
-// i.e. three tcgen05.mma (kind::f16, fp32 accumulate in TMEM) per 16-channel K chunk.
+//
+// Operand precision (template parameter PREC; SURVEY.md F8 — one bf16 / tf32 product misses the 1e-3 contract):
+//   PREC_F16MX  (default of the library)  a*w ~= a_h*w_h + 2^-11 * ( e4m3(2^11 a_l) * e4m3(w) + e4m3(a) * e4m3(2^11 w_l) )
+//               with x_h = fp16(x), x_l = x - x_h: per 16-channel K chunk ONE kind::f16 MMA (K = 16) plus ONE
+//               kind::mxf8f6f4 block-scaled MMA (K = 32: both cross terms concatenated along K) whose UE8M0 scale
+//               factor 2^-11 is applied by the tensor core, so everything lands in one fp32 accumulator.  Executed
+//               cost 2 MMAs per chunk; error <= 2.5e-4 linear light on uniform noise, <= 5e-5 on natural images
+//               (tools/precision_probe.py; tests/cuda/umma_mx_probe.cu pins the instruction semantics).
+//               Pixel row: [32 x fp16 a_h | 16 x e4m3 2^11 a_l, 16 x e4m3 a  (ch 0-15) | the same for ch 16-31];
+//               weight row: [32 x fp16 w_h | 16 x e4m3 w, 16 x e4m3 2^11 w_l | ...].
+//   PREC_BF16X3 (RSR_FLAG_BF16X3, conv0's x-im2col input, the generic conv) a_hi*w_hi + a_mid*w_hi + a_hi*w_mid, all
+//               bf16: three kind::f16 MMAs per chunk, error <= 8e-5.  Pixel row: [32 x bf16 hi | 32 x bf16 mid].
 //
 // Data movement: a CTA walks down a 128-pixel-wide column strip.  Input rows are TMA-loaded ONCE
 // each into a ring of row slots in shared memory (box = 128 + KW - 1 pixels, SWIZZLE_128B,
@@ -22,14 +31,14 @@
 // sum all their writers: network.rs:61+65, :62+66+69, :67+70+72) travel as fp32 [pixel][32] tiles:
 // a producer warp TMA-loads each 128-pixel tile into shared memory ahead of time and the epilogue
 // adds it from there, so the epilogue never waits on global memory:
-// TMEM -> registers (+ partial from smem) -> bias / BeLU / split -> swizzled staging -> TMA store.  R output rows are accumulated per pass in TMEM, double
-// buffered, so the epilogue of pass j overlaps the MMAs of pass j + 1.
+// TMEM -> registers (+ partial from smem) -> bias / BeLU / split -> swizzled staging -> TMA store.  R output rows are
+// accumulated per pass in TMEM, double buffered, so the epilogue of pass j overlaps the MMAs of pass j + 1.
 //
-// Row folding (ConvCfg::FOLD, experimental): at N <= 64 an MMA is bound by the shared-memory read of its 4 KB A tile
+// Row folding (ConvCfg::FOLD; conv0 and conv10): at N <= 64 an MMA is bound by the shared-memory read of its 4 KB A tile
 // (tests/cuda/umma_bench.cu: max(N/2, 32 + N/4) cycles).  Input row i of a pass window contributes to the output rows
 // r = i - ta, ta = 0..KH-1; with the accumulators of the R rows of a pass adjacent in TMEM and the KH weight taps of one tap
 // column stored bottom tap first, those contributions are ONE MMA with N = (rows hit) x NCOL: same tensor work, KH times
-// fewer A reads (conv10: 54 N=32 MMAs per row -> 36 MMAs of N = 32..96 per two rows).
+// fewer A reads (measured, profiles/r02a_fold_session.log: conv10 207 -> 172 us, conv0 83 -> 79 us).
 //
 // Warp roles: warp 0 = input-row producer, warp 3 = weight producer, warp 2 = TMEM allocator +
 // partial-sum producer, warp 1 = MMA issuer (one lane), warps 4.. = epilogue (4 or 8 warps per config;
@@ -37,6 +46,7 @@
 // instruction latency of the ALU-heavy epilogues: conv0 -11 %, conv5|6|7 -6 %, conv10 -10 %, measured).
 #pragma once
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include "ptx.cuh"
 
 // Timing-ablation switches (tools/ablate.sh builds variants; results are then WRONG on purpose).
@@ -48,14 +58,18 @@
 #define ABL_NO_PIN (RSR_ABL & 4)        // partial-sum tiles: no TMA (MMAs still issued)
 #define ABL_NO_MMA (RSR_ABL & 8)        // no tcgen05.mma at all
 #define ABL_NO_EPI_OUT (RSR_ABL & 16)   // epilogue: TMEM load only, no math / staging / store
-#define ABL_NO_PIN_MMA (RSR_ABL & 32)   // partial-sum fold MMAs skipped
 
 namespace rsr {
+
+enum : int { PREC_BF16X3 = 0, PREC_F16MX = 1 };
+constexpr float F16MX_SCALE = 2048.0f;          // 2^11: the fp8 "low" operands are stored pre-multiplied by this ...
+constexpr uint32_t F16MX_SFA_BYTES = 0x74747474u;   // ... and the block-scaled MMA multiplies A rows by UE8M0 116 = 2^-11
+constexpr uint32_t F16MX_SFB_BYTES = 0x7f7f7f7fu;   // B columns by UE8M0 127 = 2^0
 
 // What happens to one 32-column group of the accumulator.
 enum EpiKind : int {
     EPI_NONE = 0,
-    EPI_ACT = 1,      // y = BeLU(acc + bias; slope); store split-bf16 activation
+    EPI_ACT = 1,      // y = BeLU(acc + bias; slope); store split activation
     EPI_RAW = 2,      // store acc (+ partial) as fp32 [pixel][32]: partial sum for a later launch
     EPI_SHUFFLE = 3,  // acc + bias; depth-to-space + bilinear skip; store image
 };
@@ -73,19 +87,21 @@ struct ConvParams {
     CUtensorMap tmA;       // input node, rank 4: (RB/2 elems, W, H, NIMG), box (RB/2, BOXW, 1, 1)
     CUtensorMap tmB;       // packed weights, rank 2: (RB/2 elems, taps * NCOL), box (RB/2, NCOL)
     CUtensorMap tmPin[3];  // per group: fp32 partial-sum input, rank 4 (32, W, H, NIMG), box (32, 128, 1, 1)
-    CUtensorMap tmOut[8];  // per group: output, rank 4, box (.., 32 px, 1, 1): split-bf16 (64 elems) or fp32 (32)
+    CUtensorMap tmOut[8];  // per group: output, rank 4, box (.., 32 px, 1, 1): split activation (64 x 2 B) or fp32 (32)
     int W, H, NIMG;
     int row_begin, row_end;  // output rows computed; [0, H) normally
     int n_strips;
     long long total_rowtiles;  // NIMG * n_strips * (row_end - row_begin)
-    int factor;
     EpiGroup grp[8];
     int n_cb;           // input channel blocks of 32 accumulated per output (1 for the sr_net launches; the
-                        // generic conv of csrc/conv2d.cu uses Cin / 32, planes stored as images img * n_cb + cb)
+                        // generic conv uses Cin / 32, planes stored as images img * n_cb + cb)
     const float4* xf4;  // EPI_SHUFFLE: input image as float4 [N][H][W] (bilinear skip)
     float* out_f32;     // EPI_SHUFFLE: [N][fH][fW][3] (or null)
-    uint8_t* out_u8;    // EPI_SHUFFLE: [N][fH][fW][4] RGBA (or null)
-    int out_vec_ok;     // f32 output rows are 16-byte aligned (W % 4 == 0 and aligned base)
+    uint8_t* out_u8;    // EPI_SHUFFLE: [N][fH][fW][out_u8_ch] (or null)
+    int out_u8_ch;      // 4 = RGBA (alpha 255, data_to_img(..).to_rgba()), 3 = RGB (data_to_img alone)
+    int out_row0;       // EPI_SHUFFLE: LR row that maps to output row 0 (band mode: the rows above are halo)
+    int out_rows;       // EPI_SHUFFLE: LR rows per image in the output tensor
+    int out_vec_ok;     // output rows are 16-byte aligned (W * factor % 4 == 0 and aligned base)
     int* fault;
     long long* prof;    // test hook: per-CTA wait-cycle counters [gridDim.x][16] (null = off)
 };
@@ -106,19 +122,23 @@ struct ConvParams {
         }                                                                \
     } while (0)
 
-template <int KH_, int KW_, int RB_, int NG_, int R_, int NR_, int TPS_, int NBS_, int NPIN_, int NOUT_, bool SHUF_, int NEPI_ = 4,
-          bool PAIR_ = false, bool FOLD_ = false>
+// SHUF_: 0 = ordinary launch, f > 0 = last launch of the net with upscaling factor f (Expand + LinearInterp epilogue).
+// PREC_: operand format of the INPUT node and the weights; OFMT_: storage format of the activations this launch writes.
+template <int KH_, int KW_, int RB_, int NG_, int R_, int NR_, int TPS_, int NBS_, int NPIN_, int NOUT_, int SHUF_, int NEPI_ = 4,
+          bool PAIR_ = false, bool FOLD_ = false, int PREC_ = PREC_BF16X3, int OFMT_ = PREC_>
 struct ConvCfg {
     static constexpr bool PAIR = PAIR_;                                // CTA-pair kernel (conv_pair.cuh): half a weight tap per CTA
-    // Row-folded MMAs (experimental, off in every shipped launch; see the MMA role): the KH vertical taps of one tap column
-    // become ONE MMA per input row whose N spans the up to KH output rows that row contributes to.
+    // Row-folded MMAs (see the MMA role): the KH vertical taps of one tap column become ONE MMA per input row whose N spans
+    // the up to KH output rows that row contributes to.
     static constexpr bool FOLD = FOLD_;
+    static constexpr int PREC = PREC_, OFMT = OFMT_;
     static constexpr int KH = KH_, KW = KW_, RB = RB_, NG = NG_, R = R_;
     static constexpr int NEPI = NEPI_;                                 // epilogue warps (4 or 8)
     static_assert(NEPI == 4 || NEPI == 8, "4 or 8 epilogue warps");
     static constexpr int NTHREADS = 128 + 32 * NEPI;
     static constexpr int NBS = NBS_, NPIN = NPIN_, NOUT = NEPI == 8 ? 1 : NOUT_;   // staging tiles per epilogue warp
-    static constexpr bool SHUF = SHUF_;
+    static constexpr bool SHUF = SHUF_ > 0;
+    static constexpr int FACTOR = SHUF_;
     static constexpr int NCOL = 32 * NG;
     static constexpr int PH = KH / 2, PW = KW / 2;
     static constexpr int TAPS = KH * KW;
@@ -134,8 +154,10 @@ struct ConvCfg {
     static constexpr int KC = RB / 64;                                 // 16-channel chunks per plane
     static constexpr int PIN_BYTES = 128 * 128;                        // one partial-sum tile
     static constexpr int ACC_COLS = 2 * R * NCOL;                      // double-buffered accumulators
-    static constexpr int TMEM_COLS = ACC_COLS <= 32 ? 32 : ACC_COLS <= 64 ? 64 : ACC_COLS <= 128 ? 128
-                                   : ACC_COLS <= 256 ? 256 : 512;
+    static constexpr int SF_COL = ACC_COLS;                            // PREC_F16MX: 16 scale-factor columns for A, 16 for B
+    static constexpr int USED_COLS = ACC_COLS + (PREC == PREC_F16MX ? 32 : 0);
+    static constexpr int TMEM_COLS = USED_COLS <= 32 ? 32 : USED_COLS <= 64 ? 64 : USED_COLS <= 128 ? 128
+                                   : USED_COLS <= 256 ? 256 : 512;
     static constexpr int OFF_B = NR * SLOT;
     static constexpr int OFF_P = OFF_B + NBS * BST;
     static constexpr int OFF_O = OFF_P + NPIN * PIN_BYTES;
@@ -143,14 +165,16 @@ struct ConvCfg {
     static constexpr int NBAR = 2 * NR + 2 * NBS + 2 * (NPIN > 0 ? NPIN : 1) + 4;
     static constexpr int SMEM_BYTES = 1024 + OFF_BAR + NBAR * 8 + 16;
     static constexpr uint32_t SWZ = RB == 128 ? UMMA_SW_128B : UMMA_SW_64B;
-    static_assert(ACC_COLS <= 512, "accumulators exceed TMEM");
+    static_assert(USED_COLS <= 512, "accumulators (+ scale factors) exceed TMEM");
     static_assert(RB == 128 || RB == 64, "pixel row must be 128 or 64 bytes");
+    static_assert(PREC == PREC_BF16X3 || RB == 128, "the F16MX pixel row is 128 bytes");
     static_assert(TAP_BYTES % 1024 == 0, "weight tap tile must keep 1024-byte alignment");
     static_assert(PAIR || TPS * NCOL <= 256, "weight stage exceeds the TMA box limit");   // (pairs load tap by tap)
     static_assert(HB % 8 == 0, "a CTA's share of a tap must be whole 8-row core-matrix groups");
     static_assert(NR >= R + 2 * PH, "row ring smaller than one pass window");
     static_assert(SMEM_BYTES <= 232448, "shared memory budget");
     static_assert(!FOLD || (!PAIR && TPS == KH && KH * NCOL <= 256), "row folding: one weight stage = the KH taps of one tap column");
+    static_assert(!SHUF || 3 * FACTOR * FACTOR <= NCOL, "expand channels must fit the accumulator groups");
 };
 
 struct WorkItem {
@@ -210,14 +234,59 @@ __device__ __forceinline__ void split_pair(float v0, float v1, uint32_t& hi, uin
     const float h0 = __uint_as_float(hi << 16), h1 = __uint_as_float(hi & 0xffff0000u);
     mid = cvt_bf16x2(v0 - h0, v1 - h1);
 }
+// (lo, hi) floats -> two e4m3 bytes (lo in bits 0-7), round to nearest even, saturating
+__device__ __forceinline__ uint32_t cvt_e4m3x2(float lo, float hi) {
+    uint16_t r;
+    asm("cvt.rn.satfinite.e4m3x2.f32 %0, %1, %2;" : "=h"(r) : "f"(hi), "f"(lo));
+    return r;
+}
+// F16MX split of two floats: fp16 parts (packed), e4m3(2^11 * residual) (2 bytes), e4m3(value) (2 bytes)
+__device__ __forceinline__ void split_pair_f16mx(float v0, float v1, uint32_t& h, uint32_t& lo8, uint32_t& a8) {
+    const __half2 h2 = __floats2half2_rn(v0, v1);
+    const float2 hf = __half22float2(h2);
+    h = *reinterpret_cast<const uint32_t*>(&h2);
+    lo8 = cvt_e4m3x2((v0 - hf.x) * F16MX_SCALE, (v1 - hf.y) * F16MX_SCALE);
+    a8 = cvt_e4m3x2(v0, v1);
+}
 
 __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
     asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
 
-// One thread = one pixel; v[] = its 32 accumulator columns.  Applies bias / BeLU, splits every
-// value into bf16 hi + mid and writes the pixel's 128-byte row (hi 0..31 | mid 0..31) into the
-// warp's staging tile with the 128-byte TMA swizzle (16-byte chunk j of row r sits at j ^ (r & 7)).
+// A pixel's 128-byte row as 8 chunks of 16 bytes, written at `row` (shared-memory address of the row inside a tile laid out
+// with the 128-byte TMA swizzle: chunk j of row r sits at chunk j ^ (r & 7)); sw = r & 7.
+__device__ __forceinline__ void store_row_swizzled(const uint32_t (&w)[32], uint32_t row, uint32_t sw) {
+    #pragma unroll
+    for (int j = 0; j < 8; ++j) st_shared_v4(row + ((j ^ sw) << 4), w[4 * j], w[4 * j + 1], w[4 * j + 2], w[4 * j + 3]);
+}
+// One pixel's 32 activation values -> the 32 words of its row in storage format OFMT (zero: a padding pixel, all zeros).
+template <int OFMT>
+__device__ __forceinline__ void pack_split_row(const float (&v)[32], uint32_t (&w)[32], bool zero = false) {
+    if (OFMT == PREC_F16MX) {
+        // chunks 0-3: fp16 a_h (8 channels each) | 4: e4m3 2^11 a_l ch 0-15 | 5: e4m3 a ch 0-15 | 6, 7: the same for ch 16-31
+        #pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            uint32_t la, lb, aa, ab;
+            split_pair_f16mx(v[4 * i], v[4 * i + 1], w[2 * i], la, aa);
+            split_pair_f16mx(v[4 * i + 2], v[4 * i + 3], w[2 * i + 1], lb, ab);
+            const int c = i >> 2, k = i & 3;   // 16-channel chunk, word within its 16 bytes
+            w[16 + 8 * c + k] = la | (lb << 16);
+            w[20 + 8 * c + k] = aa | (ab << 16);
+        }
+    } else {
+        // chunks 0-3: bf16 hi | 4-7: bf16 mid
+        #pragma unroll
+        for (int i = 0; i < 16; ++i) split_pair(v[2 * i], v[2 * i + 1], w[i], w[16 + i]);
+    }
+    if (zero) {
+        #pragma unroll
+        for (int i = 0; i < 32; ++i) w[i] = 0u;
+    }
+}
+
+// One thread = one pixel; v[] = its 32 accumulator columns.  Applies bias / BeLU, splits every value into the storage
+// format and writes the pixel's 128-byte row into the warp's staging tile.
+template <int OFMT>
 __device__ __forceinline__ void epi_split_to_stage(const EpiGroup& g, float (&v)[32], uint32_t stage_addr, int lane) {
     if (g.bias) {
         const float4* b4 = reinterpret_cast<const float4*>(g.bias);
@@ -236,16 +305,9 @@ __device__ __forceinline__ void epi_split_to_stage(const EpiGroup& g, float (&v)
             v[4 * i + 2] = belu(v[4 * i + 2], t.z); v[4 * i + 3] = belu(v[4 * i + 3], t.w);
         }
     }
-    uint32_t hi[16], mid[16];
-    #pragma unroll
-    for (int i = 0; i < 16; ++i) split_pair(v[2 * i], v[2 * i + 1], hi[i], mid[i]);
-    const uint32_t row = stage_addr + lane * 128;
-    const uint32_t sw = lane & 7;
-    #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        st_shared_v4(row + ((j ^ sw) << 4), hi[4 * j], hi[4 * j + 1], hi[4 * j + 2], hi[4 * j + 3]);
-        st_shared_v4(row + (((4 + j) ^ sw) << 4), mid[4 * j], mid[4 * j + 1], mid[4 * j + 2], mid[4 * j + 3]);
-    }
+    uint32_t w[32];
+    pack_split_row<OFMT>(v, w);
+    store_row_swizzled(w, stage_addr + lane * 128, lane & 7);
 }
 
 // 3x3 neighbourhood of the input pixel, edge clamped, for the LinearInterp skip (network.rs:27).
@@ -266,42 +328,126 @@ __device__ __forceinline__ void load_skip_nb(const ConvParams& p, int img, int y
         }
 }
 
-// Expand (depth-to-space, network.rs:39: out[F*h+dy, F*w+dx, c] = e[h, w, (dy*F+dx)*3 + c]) plus the
-// half-pixel-centre bilinear skip; factor 3.  o[dy][dx*3 + c].
-__device__ __forceinline__ void shuffle_pixel(const float (&v)[32], const SkipNb& nb, float (&o)[3][9]) {
+// LinearInterp (network.rs:27): half-pixel centres.  Sub-pixel d of F sits at s = (d + 0.5) / F - 0.5 relative to its LR pixel:
+// s < 0 blends neighbours (-1, 0) with weight s + 1 on the pixel itself, else (0, +1) with weight s on the next one.
+template <int F>
+struct Lerp {
+    __host__ __device__ static constexpr int first(int d) { return 2 * d + 1 < F ? 0 : 1; }   // index into the 3-wide neighbourhood
+    __host__ __device__ static constexpr float t(int d) {
+        return (float)(2 * d + 1 < F ? ((double)d + 0.5) / F + 0.5 : ((double)d + 0.5) / F - 0.5);
+    }
+};
+
+// Expand (depth-to-space, network.rs:39: out[F*h+dy, F*w+dx, c] = e[h, w, (dy*F+dx)*3 + c]) plus the bilinear skip, for one
+// output row dy of one LR pixel: o[dx*3 + c].
+template <int F, int NV>
+__device__ __forceinline__ void shuffle_row(const float (&v)[NV], const SkipNb& nb, int dy, float (&o)[3 * F]) {
+    const int ya = Lerp<F>::first(dy);
+    const float ty = Lerp<F>::t(dy);
     #pragma unroll
-    for (int dy = 0; dy < 3; ++dy) {
-        // sy = (dy + 0.5)/3 - 0.5 = -1/3, 0, +1/3  ->  rows (ya, ya+1) of the 3x3 block, weight ty
-        const int ya = dy == 0 ? 0 : 1;
-        const float ty = dy == 0 ? (2.0f / 3.0f) : (dy == 1 ? 0.0f : (1.0f / 3.0f));
+    for (int dx = 0; dx < F; ++dx) {
+        const int xa = Lerp<F>::first(dx);
+        const float tx = Lerp<F>::t(dx);
         #pragma unroll
-        for (int dx = 0; dx < 3; ++dx) {
-            const int xa = dx == 0 ? 0 : 1;
-            const float tx = dx == 0 ? (2.0f / 3.0f) : (dx == 1 ? 0.0f : (1.0f / 3.0f));
+        for (int c = 0; c < 3; ++c) {
+            const float v00 = nb.v[ya][xa][c], v01 = nb.v[ya][xa + 1][c];
+            const float v10 = nb.v[ya + 1][xa][c], v11 = nb.v[ya + 1][xa + 1][c];
+            const float top = v00 + (v01 - v00) * tx;
+            const float bot = v10 + (v11 - v10) * tx;
+            o[dx * 3 + c] = v[(dy * F + dx) * 3 + c] + top + (bot - top) * ty;
+        }
+    }
+}
+
+__device__ __forceinline__ uint32_t quant_u8(float v) {   // data_to_img (main.rs:175): round(clamp(v, 0, 1) * 255)
+    return (uint32_t)(fminf(fmaxf(v, 0.f), 1.f) * 255.0f + 0.5f);
+}
+
+// The image store of the last launch for one warp = 32 LR pixels of LR row y: F output rows of 32 * F pixels each, staged
+// in the warp's 4 KB tile `stg` and written with coalesced (vector where aligned) stores as f32 RGB, u8 RGBA or u8 RGB.
+template <int F, int NV>
+__device__ __forceinline__ void epi_shuffle_store(const ConvParams& p, const float (&v)[NV], const SkipNb& nb, uint8_t* stg, int img,
+                                                  int y, int xw, int lane) {
+    const int npx_valid = min(32, p.W - xw);
+    const size_t OW = (size_t)p.W * F;                                              // output pixels per row
+    const size_t opx0 = ((size_t)img * p.out_rows * F + (size_t)(y - p.out_row0) * F) * OW + (size_t)xw * F;
+    if (p.out_f32) {
+        constexpr int DYC = F * F * 384 <= 4096 ? F : 4096 / (F * 384);              // output rows staged at once
+        float* sf = reinterpret_cast<float*>(stg);
+        #pragma unroll
+        for (int dy0 = 0; dy0 < F; dy0 += DYC) {
             #pragma unroll
-            for (int c = 0; c < 3; ++c) {
-                const float v00 = nb.v[ya][xa][c], v01 = nb.v[ya][xa + 1][c];
-                const float v10 = nb.v[ya + 1][xa][c], v11 = nb.v[ya + 1][xa + 1][c];
-                const float top = v00 + (v01 - v00) * tx;
-                const float bot = v10 + (v11 - v10) * tx;
-                o[dy][dx * 3 + c] = v[(dy * 3 + dx) * 3 + c] + top + (bot - top) * ty;
+            for (int dd = 0; dd < DYC; ++dd) {
+                if (dy0 + dd >= F) continue;
+                float o[3 * F];
+                shuffle_row<F, NV>(v, nb, dy0 + dd, o);
+                #pragma unroll
+                for (int k = 0; k < 3 * F; ++k) sf[dd * (96 * F) + lane * (3 * F) + k] = o[k];
+            }
+            __syncwarp();
+            #pragma unroll
+            for (int dd = 0; dd < DYC; ++dd) {
+                if (dy0 + dd >= F) continue;
+                float* dst = p.out_f32 + (opx0 + (size_t)(dy0 + dd) * OW) * 3;
+                if (npx_valid == 32 && p.out_vec_ok) {
+                    for (int i = lane; i < 24 * F; i += 32)
+                        reinterpret_cast<float4*>(dst)[i] = reinterpret_cast<const float4*>(sf + dd * (96 * F))[i];
+                } else {
+                    for (int i = lane; i < npx_valid * 3 * F; i += 32) dst[i] = sf[dd * (96 * F) + i];
+                }
+            }
+            __syncwarp();
+        }
+    } else {
+        // u8: stage RGBA words (alpha 255: data_to_img(..).to_rgba(), main.rs:175), [dy][32 * F pixels]
+        uint32_t* sq = reinterpret_cast<uint32_t*>(stg);
+        #pragma unroll
+        for (int dy = 0; dy < F; ++dy) {
+            float o[3 * F];
+            shuffle_row<F, NV>(v, nb, dy, o);
+            #pragma unroll
+            for (int dx = 0; dx < F; ++dx)
+                sq[dy * (32 * F) + lane * F + dx] = quant_u8(o[dx * 3]) | (quant_u8(o[dx * 3 + 1]) << 8) | (quant_u8(o[dx * 3 + 2]) << 16) | 0xFF000000u;
+        }
+        __syncwarp();
+        const int nop = npx_valid * F;   // valid output pixels per row
+        if (p.out_u8_ch == 4) {
+            #pragma unroll
+            for (int dy = 0; dy < F; ++dy) {
+                uint32_t* dst = reinterpret_cast<uint32_t*>(p.out_u8) + opx0 + (size_t)dy * OW;
+                for (int i = lane; i < nop; i += 32) dst[i] = sq[dy * (32 * F) + i];
+            }
+        } else {
+            // packed RGB: 4 pixels = 3 words; word j takes its bytes from staged pixels 4(j/3) + j%3 and the next one
+            #pragma unroll
+            for (int dy = 0; dy < F; ++dy) {
+                uint8_t* dst = p.out_u8 + (opx0 + (size_t)dy * OW) * 3;
+                const uint32_t* src = sq + dy * (32 * F);
+                if (npx_valid == 32 && p.out_vec_ok) {
+                    for (int j = lane; j < 24 * F; j += 32) {
+                        const int q = j / 3, m = j - 3 * q;
+                        const uint32_t w0 = src[4 * q + m], w1 = src[4 * q + m + 1];
+                        reinterpret_cast<uint32_t*>(dst)[j] = __byte_perm(w0, w1, m == 0 ? 0x4210 : m == 1 ? 0x5421 : 0x6542);
+                    }
+                } else {
+                    for (int i = lane; i < nop * 3; i += 32) dst[i] = (uint8_t)(src[i / 3] >> (8 * (i % 3)));
+                }
             }
         }
+        __syncwarp();
     }
 }
 
 // fp32 [pixel][32] row (128 B) into the warp's staging tile, 128-byte swizzle.
 __device__ __forceinline__ void epi_raw_to_stage(const float (&v)[32], uint32_t stage_addr, int lane) {
-    const uint32_t row = stage_addr + lane * 128;
-    const uint32_t sw = lane & 7;
+    uint32_t w[32];
     #pragma unroll
-    for (int j = 0; j < 8; ++j)
-        st_shared_v4(row + ((j ^ sw) << 4), __float_as_uint(v[4 * j]), __float_as_uint(v[4 * j + 1]),
-                     __float_as_uint(v[4 * j + 2]), __float_as_uint(v[4 * j + 3]));
+    for (int i = 0; i < 32; ++i) w[i] = __float_as_uint(v[i]);
+    store_row_swizzled(w, stage_addr + lane * 128, lane & 7);
 }
 
 // v += the pixel's 32 fp32 partial sums from a TMA-loaded (128 B swizzled) tile of 128 pixels.
-__device__ __forceinline__ void epi_add_partial_tile(float (&v)[32], uint32_t tile_addr, int row) {
+__device__ __forceinline__ void epi_add_partial_tile(float* v, uint32_t tile_addr, int row) {
     const uint32_t base = tile_addr + row * 128;
     const uint32_t sw = row & 7;
     #pragma unroll
@@ -313,6 +459,193 @@ __device__ __forceinline__ void epi_add_partial_tile(float (&v)[32], uint32_t ti
     }
 }
 
+// ---- MMA issue: the split products of one 16-channel K chunk ---------------------------------------------------
+// a_e / b_e: encoded (>> 4) shared-memory addresses of the pixel row / weight row starts (with the LBO bits);
+// chunk c lives at +32 B (encoded +2), the second plane (bf16 mid / fp8 section) at +RB/2 bytes.
+template <int PREC, int CG, int RB>
+struct SplitMma {
+    static constexpr uint32_t HI = (uint32_t)make_sdesc_hi(8 * RB, RB == 128 ? UMMA_SW_128B : UMMA_SW_64B);
+    static constexpr uint32_t PLANE2 = (RB / 2) >> 4;
+    static __device__ __forceinline__ uint64_t desc(uint32_t lo) { return ((uint64_t)HI << 32) | lo; }
+    static __host__ __device__ constexpr uint32_t idesc(int M, int N) {
+        return PREC == PREC_F16MX ? make_idesc_f16(M, N) : make_idesc_bf16(M, N);
+    }
+    // the leading product (hi x hi): the only one that may overwrite the accumulator
+    static __device__ __forceinline__ void head(uint32_t d, uint32_t a_e, uint32_t b_e, int c, int M, int N, uint32_t acc) {
+        umma_f16_cg<CG>(d, desc(a_e + 2 * c), desc(b_e + 2 * c), idesc(M, N), acc);
+    }
+    // the correction products, always accumulated; sf = TMEM address of the scale-factor columns (F16MX)
+    static __device__ __forceinline__ void tail(uint32_t d, uint32_t a_e, uint32_t b_e, int c, int M, int N, uint32_t sf) {
+        if (PREC == PREC_F16MX) {
+            umma_mxf8<CG>(d, desc(a_e + PLANE2 + 2 * c), desc(b_e + PLANE2 + 2 * c), make_idesc_mxf8(M, N), sf, sf + 16, 1);
+        } else {
+            umma_f16_cg<CG>(d, desc(a_e + PLANE2 + 2 * c), desc(b_e + 2 * c), idesc(M, N), 1);
+            umma_f16_cg<CG>(d, desc(a_e + 2 * c), desc(b_e + PLANE2 + 2 * c), idesc(M, N), 1);
+        }
+    }
+    static __device__ __forceinline__ void chunk(uint32_t d, uint32_t a_e, uint32_t b_e, int c, int M, int N, uint32_t sf, uint32_t acc) {
+        head(d, a_e, b_e, c, M, N, acc);
+        tail(d, a_e, b_e, c, M, N, sf);
+    }
+};
+
+// PREC_F16MX: the four epilogue warps 4..7 (one per TMEM lane quarter) fill the scale-factor columns; call from ALL threads
+// right after the TMEM base address is known (contains a CTA barrier).
+template <class C>
+__device__ __forceinline__ void init_scale_factors(uint32_t tmem_base, int warp) {
+    if (C::PREC == PREC_F16MX) {
+        if (warp >= 4 && warp < 8) {
+            const uint32_t t = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + C::SF_COL;
+            tmem_fill_x16(t, F16MX_SFA_BYTES);
+            tmem_fill_x16(t + 16, F16MX_SFB_BYTES);
+        }
+        tc_fence_before();
+        __syncthreads();
+        tc_fence_after();
+    }
+}
+
+// ---- the epilogue role (shared by conv_strip_kernel and conv_pair_kernel) ------------------------------------------
+// next_item(w): the CTA's next work item; arrive_t_empty(buf): "accumulator buffer drained" (local or cluster arrive).
+template <class C, class NextItem, class ArriveTEmpty>
+__device__ __forceinline__ void conv_epilogue_role(const ConvParams& p, uint8_t* smem, uint64_t* p_full, uint64_t* p_empty,
+                                                   uint64_t* t_full, uint32_t tmem_base, int warp, int lane, long long* prof_acc,
+                                                   NextItem next_item, ArriveTEmpty arrive_t_empty) {
+    constexpr int NPB = C::NPIN > 0 ? C::NPIN : 1;
+    uint8_t* sO = smem + C::OFF_O;
+    const int e = warp - 4;   // epilogue warp index
+    const int ew = e & 3;     // == warp % 4: TMEM lane quarter this warp may read
+    const int eh = e >> 2;    // with 8 epilogue warps: which half of the pass's tiles this warp takes
+    const uint32_t stage0 = smem_u32(sO) + e * (C::NOUT * 4096);
+    uint32_t buf = 0, tpar = 0, oc = 0;
+    uint32_t pst = 0, ppar = 0;  // partial-sum tile ring (consumed in producer order: row, then group)
+    const uint32_t sP_u = smem_u32(smem + C::OFF_P);
+    // observe (and, when `use`, add) the next partial-sum tile: every epilogue warp sees every tile (wait full, arrive empty);
+    // a warp that skipped the wait could fall two phases behind the barrier and mistake parity for completion
+    auto take_pin = [&](float* v, bool use) {
+        RSR_WAIT(&p_full[pst], ppar, 9, 3);
+        if (use) epi_add_partial_tile(v, sP_u + pst * C::PIN_BYTES, ew * 32 + lane);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&p_empty[pst]);
+        if (++pst == NPB) { pst = 0; ppar ^= 1; }
+    };
+    auto wait_stage = [&]() {   // the staging tile used NOUT stores ago must have been read out by the TMA engine
+        const long long t0s = RSR_PROF_ON ? clock64() : 0;
+        if (elect_one()) asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(C::NOUT - 1) : "memory");
+        __syncwarp();
+        if (RSR_PROF_ON) prof_acc[1] += clock64() - t0s;
+    };
+    WorkItem w;
+    while (next_item(w)) {
+        const int xw = w.x0 + ew * 32;  // first pixel of this warp's 32-pixel slice
+        const int x = xw + lane;
+        for (int j = 0; j < w.npass; ++j, buf ^= 1, tpar ^= (buf == 0)) {
+            SkipNb nb;
+            if (C::SHUF) {
+                // the skip input does not depend on the MMAs: fetch this warp's first row before waiting
+                // (SHUF launches: one tile per row; with 8 warps this warp owns rows r % 2 == eh)
+                const int y = w.y_b + j * C::R + eh;
+                if (y < w.y_e && x < p.W) load_skip_nb(p, w.img, y, x, nb);
+            }
+            RSR_WAIT(&t_full[buf], tpar, 6, 0);
+            tc_fence_after();
+            const long long te0 = RSR_PROF_ON ? clock64() : 0;
+            const uint32_t t_pass = tmem_base + ((uint32_t)(ew * 32) << 16) + buf * (C::R * C::NCOL);
+            #pragma unroll 1
+            for (int r = 0; r < C::R; ++r) {
+                const int y = w.y_b + j * C::R + r;
+                const bool row_live = y < w.y_e && xw < p.W;   // warp-uniform
+                if constexpr (C::SHUF) {
+                    // bias, depth-to-space, bilinear skip -> staging -> coalesced stores; all groups of the row together
+                    constexpr int NV = 32 * C::NG;
+                    const bool mine = C::NEPI == 4 || ((r & 1) == eh);
+                    if (!mine || !row_live) {
+                        #pragma unroll
+                        for (int g = 0; g < C::NG; ++g)
+                            if (C::NPIN > 0 && p.grp[g].has_pin) take_pin(nullptr, false);
+                        continue;
+                    }
+                    float v[NV];
+                    #pragma unroll
+                    for (int g = 0; g < C::NG; ++g) {
+                        uint32_t raw[32];
+                        tmem_ld_32x32(t_pass + r * C::NCOL + g * 32, raw);
+                        tmem_ld_wait();
+                        #pragma unroll
+                        for (int k = 0; k < 32; ++k) v[g * 32 + k] = __uint_as_float(raw[k]);
+                        if (C::NPIN > 0 && p.grp[g].has_pin) take_pin(&v[g * 32], true);
+                        const float4* b4 = reinterpret_cast<const float4*>(p.grp[g].bias);
+                        #pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            const float4 t = __ldg(b4 + i);
+                            v[g * 32 + 4 * i + 0] += t.x; v[g * 32 + 4 * i + 1] += t.y; v[g * 32 + 4 * i + 2] += t.z; v[g * 32 + 4 * i + 3] += t.w;
+                        }
+                    }
+                    if (ABL_NO_EPI_OUT) { if (v[0] == 123.456f && p.out_f32) p.out_f32[0] = v[1]; ++oc; continue; }
+                    const long long to0 = RSR_PROF_ON ? clock64() : 0;
+                    if (r > eh && x < p.W) load_skip_nb(p, w.img, y, x, nb);
+                    if (x >= p.W) {
+                        #pragma unroll
+                        for (int a = 0; a < 3; ++a)
+                            #pragma unroll
+                            for (int b = 0; b < 3; ++b) { nb.v[a][b][0] = 0.f; nb.v[a][b][1] = 0.f; nb.v[a][b][2] = 0.f; }
+                    }
+                    epi_shuffle_store<C::FACTOR, NV>(p, v, nb, smem + C::OFF_O + (e * C::NOUT + (oc % C::NOUT)) * 4096, w.img, y, xw, lane);
+                    if (RSR_PROF_ON) prof_acc[6] += clock64() - to0;
+                    ++oc;
+                } else {
+                    #pragma unroll 1
+                    for (int g = 0; g < C::NG; ++g) {
+                        const EpiGroup& eg = p.grp[g];
+                        if (eg.kind == EPI_NONE) continue;
+                        const bool pin = C::NPIN > 0 && eg.has_pin;
+                        const bool mine = C::NEPI == 4 || (((r * C::NG + g) & 1) == eh);   // warp-uniform tile ownership
+                        if (!mine || !row_live) {
+                            // the other warp of this lane quarter handles the tile (or nothing is stored): the partial
+                            // tile the producer fetched must still be observed and released
+                            if (pin) take_pin(nullptr, false);
+                            continue;
+                        }
+                        uint32_t raw[32];
+                        const long long tl0 = RSR_PROF_ON ? clock64() : 0;
+                        tmem_ld_32x32(t_pass + r * C::NCOL + g * 32, raw);
+                        tmem_ld_wait();
+                        if (RSR_PROF_ON) prof_acc[5] += clock64() - tl0;
+                        float v[32];
+                        #pragma unroll
+                        for (int k = 0; k < 32; ++k) v[k] = __uint_as_float(raw[k]);
+                        if (pin) take_pin(v, true);
+                        if (ABL_NO_EPI_OUT) { if (v[0] == 123.456f && p.out_f32) p.out_f32[0] = v[1]; ++oc; continue; }
+                        const long long to0 = RSR_PROF_ON ? clock64() : 0;
+                        const uint32_t stage = stage0 + (oc % C::NOUT) * 4096;
+                        wait_stage();
+                        if (eg.kind == EPI_RAW) epi_raw_to_stage(v, stage, lane);
+                        else epi_split_to_stage<C::OFMT>(eg, v, stage, lane);
+                        fence_proxy_async_smem();
+                        __syncwarp();
+                        if (elect_one()) {
+                            asm volatile(
+                                "cp.async.bulk.tensor.4d.global.shared::cta.tile.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+                                ::"l"(reinterpret_cast<uint64_t>(&p.tmOut[g])), "r"(stage), "r"(eg.c0), "r"(xw), "r"(y),
+                                  "r"(w.img)
+                                : "memory");
+                            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                        }
+                        if (RSR_PROF_ON) prof_acc[6] += clock64() - to0;
+                        ++oc;
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (RSR_PROF_ON) prof_acc[2] += clock64() - te0;
+            if (lane == 0) arrive_t_empty(buf);
+        }
+    }
+    // all TMA stores of this warp must have completed before the CTA exits
+    if (elect_one()) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+}
+
 // ---- the kernel ------------------------------------------------------------------------------
 template <class C>
 __global__ void __launch_bounds__(C::NTHREADS, 1) conv_strip_kernel(const __grid_constant__ ConvParams p) {
@@ -321,7 +654,6 @@ __global__ void __launch_bounds__(C::NTHREADS, 1) conv_strip_kernel(const __grid
     uint8_t* sA = smem;
     uint8_t* sB = smem + C::OFF_B;
     uint8_t* sP = smem + C::OFF_P;
-    uint8_t* sO = smem + C::OFF_O;
     uint64_t* a_full = reinterpret_cast<uint64_t*>(smem + C::OFF_BAR);
     uint64_t* a_empty = a_full + C::NR;
     uint64_t* b_full = a_empty + C::NR;
@@ -342,7 +674,7 @@ __global__ void __launch_bounds__(C::NTHREADS, 1) conv_strip_kernel(const __grid
     int pin_g[3], npg = 0;
     #pragma unroll
     for (int g = 0; g < C::NG; ++g)
-        if (C::NPIN > 0 && p.grp[g].has_pin) pin_g[npg++] = g;
+        if (C::NPIN > 0 && p.grp[g].has_pin && npg < 3) pin_g[npg++] = g;
     const int n_pin = npg * C::R;  // partial tiles per pass
 
     if (threadIdx.x == 0) {
@@ -359,6 +691,7 @@ __global__ void __launch_bounds__(C::NTHREADS, 1) conv_strip_kernel(const __grid
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);  // warp-uniform for the compiler
+    init_scale_factors<C>(tmem_base, warp);
 
     // All role loops below are executed by the whole warp with warp-uniform control flow; only the
     // TMA / MMA / commit instructions themselves are issued by one lane, chosen with elect.sync —
@@ -444,15 +777,13 @@ __global__ void __launch_bounds__(C::NTHREADS, 1) conv_strip_kernel(const __grid
         // positions advance incrementally (no division); the tap loop is fully unrolled so that tap
         // offsets are immediates.  The issue thread must stay ahead of an 8-deep MMA queue
         // (tests/cuda/umma_queue.cu), so every instruction here counts.
-        constexpr uint32_t HI = (uint32_t)make_sdesc_hi(8 * C::RB, C::SWZ);
-        constexpr uint32_t IDESC = make_idesc_bf16(128, C::NCOL);
+        using MM = SplitMma<C::PREC, 1, C::RB>;
         constexpr uint32_t LBO = 1u << 16;
-        constexpr uint32_t MID = (C::RB / 2) >> 4;   // encoded offset of the mid plane
         constexpr int WIN = C::R + 2 * C::PH;        // input rows one pass reads
         constexpr int NEARLY = C::FOLD ? 0 : (C::R < C::KH ? C::R : C::KH);   // rows retired during the pass (folded: every
                                                                                // stage reads the whole window)
         const uint32_t sA_e = (smem_u32(sA) >> 4) | LBO, sB_e = (smem_u32(sB) >> 4) | LBO;
-        auto desc = [](uint32_t hi, uint32_t lo) { return ((uint64_t)hi << 32) | lo; };
+        const uint32_t sf = tmem_base + C::SF_COL;
         uint32_t slot0 = 0;              // ring slot of the first window row of the current pass
         uint32_t wslot = 0, wpar = 0;    // next row slot to wait for, and its parity
         uint32_t bst = 0, bpar = 0;      // weight stage ring
@@ -501,22 +832,18 @@ __global__ void __launch_bounds__(C::NTHREADS, 1) conv_strip_kernel(const __grid
                                 const uint32_t a_e = arow[i] + sp * (C::RB >> 4);
                                 const uint32_t b_e = b_st + (C::KH - 1 - (i - r_lo)) * (C::TAP_BYTES >> 4);
                                 const uint32_t d = d_pass + r_lo * C::NCOL;
-                                const uint32_t idesc_n = make_idesc_bf16(128, n * C::NCOL);
                                 #pragma unroll
                                 for (int c = 0; c < C::KC; ++c) {
                                     if (ABL_NO_MMA) continue;
                                     if (sp == 0 && c == 0 && i < C::R) {
                                         // the first product that reaches output row i (= r_hi) overwrites its accumulator; the
                                         // rows above it in the same block already hold sums: two MMAs instead of one
-                                        if (n > 1)
-                                            umma_f16(d, desc(HI, a_e), desc(HI, b_e), make_idesc_bf16(128, (n - 1) * C::NCOL), 1);
-                                        umma_f16(d + (n - 1) * C::NCOL, desc(HI, a_e), desc(HI, b_e + (n - 1) * (C::TAP_BYTES >> 4)),
-                                                 make_idesc_bf16(128, C::NCOL), 0);
+                                        if (n > 1) MM::head(d, a_e, b_e, c, 128, (n - 1) * C::NCOL, 1);
+                                        MM::head(d + (n - 1) * C::NCOL, a_e, b_e + (n - 1) * (C::TAP_BYTES >> 4), c, 128, C::NCOL, 0);
                                     } else {
-                                        umma_f16(d, desc(HI, a_e + 2 * c), desc(HI, b_e + 2 * c), idesc_n, 1);
+                                        MM::head(d, a_e, b_e, c, 128, n * C::NCOL, 1);
                                     }
-                                    umma_f16(d, desc(HI, a_e + MID + 2 * c), desc(HI, b_e + 2 * c), idesc_n, 1);
-                                    umma_f16(d, desc(HI, a_e + 2 * c), desc(HI, b_e + MID + 2 * c), idesc_n, 1);
+                                    MM::tail(d, a_e, b_e, c, 128, n * C::NCOL, sf);
                                 }
                             }
                             umma_commit(&b_empty[bst]);
@@ -546,9 +873,7 @@ __global__ void __launch_bounds__(C::NTHREADS, 1) conv_strip_kernel(const __grid
                                     #pragma unroll
                                     for (int c = 0; c < C::KC; ++c) {
                                         if (ABL_NO_MMA) continue;
-                                        umma_f16(d, desc(HI, a_e + 2 * c), desc(HI, b_e + 2 * c), IDESC, (t | c) != 0 ? 1u : (uint32_t)(cb != 0));
-                                        umma_f16(d, desc(HI, a_e + MID + 2 * c), desc(HI, b_e + 2 * c), IDESC, 1);
-                                        umma_f16(d, desc(HI, a_e + 2 * c), desc(HI, b_e + MID + 2 * c), IDESC, 1);
+                                        MM::chunk(d, a_e, b_e, c, 128, C::NCOL, sf, (t | c) != 0 ? 1u : (uint32_t)(cb != 0));
                                     }
                                 }
                                 // the top window rows are dead once their tap row is done: free them early
@@ -588,176 +913,10 @@ __global__ void __launch_bounds__(C::NTHREADS, 1) conv_strip_kernel(const __grid
         }
     } else if (warp >= 4) {
         // ===== epilogue =====
-        const int e = warp - 4;   // epilogue warp index
-        const int ew = e & 3;     // == warp % 4: TMEM lane quarter this warp may read
-        const int eh = e >> 2;    // with 8 epilogue warps: which half of the pass's (row, group) tiles this warp takes
-        const uint32_t stage0 = smem_u32(sO) + e * (C::NOUT * 4096);
-        uint32_t buf = 0, tpar = 0, oc = 0;
-        uint32_t pst = 0, ppar = 0;  // partial-sum tile ring (consumed in producer order: row, then group)
-        const uint32_t sP_u = smem_u32(sP);
         ItemIter it = item_begin(p);
-        WorkItem w;
-        while (item_next<C>(p, it, w)) {
-            const int xw = w.x0 + ew * 32;  // first pixel of this warp's 32-pixel slice
-            const int x = xw + lane;
-            for (int j = 0; j < w.npass; ++j, buf ^= 1, tpar ^= (buf == 0)) {
-                SkipNb nb;
-                if (C::SHUF) {
-                    // the skip input does not depend on the MMAs: fetch this warp's first row before waiting
-                    // (SHUF launches have one group, so tile u == row r; with 8 warps this warp owns rows r % 2 == eh)
-                    const int y = w.y_b + j * C::R + eh;
-                    if (y < w.y_e && x < p.W) load_skip_nb(p, w.img, y, x, nb);
-                }
-                RSR_WAIT(&t_full[buf], tpar, 6, 0);
-                tc_fence_after();
-                const long long te0 = RSR_PROF_ON ? clock64() : 0;
-                #pragma unroll 1
-                for (int r = 0; r < C::R; ++r) {
-                    const int y = w.y_b + j * C::R + r;
-                    const bool row_live = y < w.y_e && xw < p.W;   // warp-uniform
-                    #pragma unroll 1
-                    for (int g = 0; g < C::NG; ++g) {
-                        const EpiGroup& eg = p.grp[g];
-                        if (eg.kind == EPI_NONE) continue;
-                        const bool pin = C::NPIN > 0 && eg.has_pin;
-                        const bool mine = C::NEPI == 4 || (((r * C::NG + g) & 1) == eh);   // warp-uniform tile ownership
-                        if (!mine) {
-                            // The other warp of this lane quarter handles the tile.  Every epilogue warp still
-                            // observes every partial-sum tile (wait full, arrive empty): a warp that skipped the
-                            // wait could fall two phases behind the barrier and mistake parity for completion.
-                            if (pin) {
-                                RSR_WAIT(&p_full[pst], ppar, 9, 3);
-                                __syncwarp();
-                                if (lane == 0) mbar_arrive(&p_empty[pst]);
-                                if (++pst == NPB) { pst = 0; ppar ^= 1; }
-                            }
-                            continue;
-                        }
-                        if (!row_live) {
-                            // nothing to store, but the partial tile the producer fetched must be released
-                            if (pin) {
-                                RSR_WAIT(&p_full[pst], ppar, 9, 3);
-                                __syncwarp();
-                                if (lane == 0) mbar_arrive(&p_empty[pst]);
-                                if (++pst == NPB) { pst = 0; ppar ^= 1; }
-                            }
-                            continue;
-                        }
-                        uint32_t raw[32];
-                        const long long tl0 = RSR_PROF_ON ? clock64() : 0;
-                        tmem_ld_32x32(tmem_base + ((uint32_t)(ew * 32) << 16) + buf * (C::R * C::NCOL) + r * C::NCOL + g * 32, raw);
-                        tmem_ld_wait();
-                        if (RSR_PROF_ON) prof_acc[5] += clock64() - tl0;
-                        float v[32];
-                        #pragma unroll
-                        for (int k = 0; k < 32; ++k) v[k] = __uint_as_float(raw[k]);
-                        if (pin) {
-                            RSR_WAIT(&p_full[pst], ppar, 9, 3);
-                            epi_add_partial_tile(v, sP_u + pst * C::PIN_BYTES, ew * 32 + lane);
-                            __syncwarp();
-                            if (lane == 0) mbar_arrive(&p_empty[pst]);
-                            if (++pst == NPB) { pst = 0; ppar ^= 1; }
-                        }
-                        if (ABL_NO_EPI_OUT) { if (v[0] == 123.456f && p.out_f32) p.out_f32[0] = v[1]; ++oc; continue; }
-                        const long long to0 = RSR_PROF_ON ? clock64() : 0;
-                        const uint32_t stage = stage0 + (oc % C::NOUT) * 4096;
-                        // the staging tile used NOUT stores ago must have been read out by the TMA engine
-                        {
-                            const long long t0s = RSR_PROF_ON ? clock64() : 0;
-                            if (elect_one())
-                                asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(C::NOUT - 1) : "memory");
-                            __syncwarp();
-                            if (RSR_PROF_ON) prof_acc[1] += clock64() - t0s;
-                        }
-                        if (!C::SHUF) {
-                            if (eg.kind == EPI_RAW) epi_raw_to_stage(v, stage, lane);
-                            else epi_split_to_stage(eg, v, stage, lane);
-                            fence_proxy_async_smem();
-                            __syncwarp();
-                            if (elect_one()) {
-                                asm volatile(
-                                    "cp.async.bulk.tensor.4d.global.shared::cta.tile.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
-                                    ::"l"(reinterpret_cast<uint64_t>(&p.tmOut[g])), "r"(stage), "r"(eg.c0), "r"(xw), "r"(y),
-                                      "r"(w.img)
-                                    : "memory");
-                                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-                            }
-                        } else {
-                            // bias, depth-to-space, bilinear skip -> staging [3 dy][32 px * 9] -> coalesced stores
-                            if (r > eh && x < p.W) load_skip_nb(p, w.img, y, x, nb);
-                            {
-                                const float4* b4 = reinterpret_cast<const float4*>(eg.bias);
-                                #pragma unroll
-                                for (int i = 0; i < 8; ++i) {
-                                    const float4 t = __ldg(b4 + i);
-                                    v[4 * i + 0] += t.x; v[4 * i + 1] += t.y; v[4 * i + 2] += t.z; v[4 * i + 3] += t.w;
-                                }
-                            }
-                            float o[3][9];
-                            if (x >= p.W) {
-                                #pragma unroll
-                                for (int a = 0; a < 3; ++a)
-                                    #pragma unroll
-                                    for (int b = 0; b < 3; ++b) { nb.v[a][b][0] = 0.f; nb.v[a][b][1] = 0.f; nb.v[a][b][2] = 0.f; }
-                            }
-                            shuffle_pixel(v, nb, o);
-                            const int npx_valid = min(32, p.W - xw);
-                            const size_t W3 = (size_t)p.W * 3;
-                            const size_t orow0 = ((size_t)w.img * p.H * 3 + (size_t)y * 3) * W3 + (size_t)xw * 3;  // in output pixels
-                            if (p.out_f32) {
-                                float* sf = reinterpret_cast<float*>(smem + C::OFF_O) + (e * C::NOUT + (oc % C::NOUT)) * 1024;
-                                #pragma unroll
-                                for (int dy = 0; dy < 3; ++dy)
-                                    #pragma unroll
-                                    for (int k = 0; k < 9; ++k) sf[dy * 288 + lane * 9 + k] = o[dy][k];
-                                __syncwarp();
-                                const int nfl = npx_valid * 9;
-                                #pragma unroll
-                                for (int dy = 0; dy < 3; ++dy) {
-                                    float* dst = p.out_f32 + (orow0 + (size_t)dy * W3) * 3;
-                                    if (npx_valid == 32 && p.out_vec_ok) {
-                                        for (int i = lane; i < 72; i += 32)
-                                            reinterpret_cast<float4*>(dst)[i] = reinterpret_cast<const float4*>(sf + dy * 288)[i];
-                                    } else {
-                                        for (int i = lane; i < nfl; i += 32) dst[i] = sf[dy * 288 + i];
-                                    }
-                                }
-                            }
-                            if (p.out_u8) {
-                                // alumina data_to_img + to_rgba (main.rs:175): round(clamp(v,0,1)*255), alpha 255
-                                // (the host guarantees exactly one of out_f32 / out_u8, so the tile is shared)
-                                uint32_t* sq = reinterpret_cast<uint32_t*>(smem + C::OFF_O) + (e * C::NOUT + (oc % C::NOUT)) * 1024;
-                                #pragma unroll
-                                for (int dy = 0; dy < 3; ++dy)
-                                    #pragma unroll
-                                    for (int dx = 0; dx < 3; ++dx) {
-                                        const uint32_t r8 = (uint32_t)(fminf(fmaxf(o[dy][dx * 3 + 0], 0.f), 1.f) * 255.0f + 0.5f);
-                                        const uint32_t g8 = (uint32_t)(fminf(fmaxf(o[dy][dx * 3 + 1], 0.f), 1.f) * 255.0f + 0.5f);
-                                        const uint32_t b8 = (uint32_t)(fminf(fmaxf(o[dy][dx * 3 + 2], 0.f), 1.f) * 255.0f + 0.5f);
-                                        sq[dy * 96 + lane * 3 + dx] = r8 | (g8 << 8) | (b8 << 16) | 0xFF000000u;
-                                    }
-                                __syncwarp();
-                                const int nu = npx_valid * 3;
-                                #pragma unroll
-                                for (int dy = 0; dy < 3; ++dy) {
-                                    uint32_t* dst = reinterpret_cast<uint32_t*>(p.out_u8) + orow0 + (size_t)dy * W3;
-                                    for (int i = lane; i < nu; i += 32) dst[i] = sq[dy * 96 + i];
-                                }
-                            }
-                            __syncwarp();
-                        }
-                        if (RSR_PROF_ON) prof_acc[6] += clock64() - to0;
-                        ++oc;
-                    }
-                }
-                tc_fence_before();
-                __syncwarp();
-                if (RSR_PROF_ON) prof_acc[2] += clock64() - te0;
-                if (lane == 0) mbar_arrive(&t_empty[buf]);
-            }
-        }
-        // all TMA stores of this warp must have completed before the CTA exits
-        if (elect_one()) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+        conv_epilogue_role<C>(p, smem, p_full, p_empty, t_full, tmem_base, warp, lane, prof_acc,
+                              [&](WorkItem& w) { return item_next<C>(p, it, w); },
+                              [&](uint32_t buf) { mbar_arrive(&t_empty[buf]); });
     }
     if (RSR_PROF_ON && lane == 0 && (warp < 5)) {
         // row per CTA: [warp0: a_empty] [warp1: t_empty a_full b_full p_full] [warp2: p_empty] [warp3: b_empty]

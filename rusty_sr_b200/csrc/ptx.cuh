@@ -1,5 +1,5 @@
 // ptx.cuh — thin inline-PTX wrappers for the sm_100a features the conv kernels use:
-// mbarrier, TMA (cp.async.bulk.tensor), tcgen05 (alloc / mma / commit / ld / fences) and the
+// mbarrier, TMA (cp.async.bulk.tensor), tcgen05 (alloc / mma / commit / ld / st / fences), CTA pairs (cta_group::2) and the
 // shared-memory + instruction descriptors of tcgen05.mma.  Hand-written; no CUTLASS/CuTe.
 #pragma once
 #include <cuda.h>
@@ -170,12 +170,124 @@ __device__ __forceinline__ void tmem_ld_wait() {
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+// D[tmem] (+)= (A[smem] * 2^sfa) * (B[smem] * 2^sfb), kind::mxf8f6f4 block-scaled: 8-bit float operands, K = 32, one UE8M0
+// scale factor per row of A / column of B read from tensor memory at [sfa] / [sfb].  The conv kernels fill those columns
+// with ONE constant byte each, so the scale-factor layout is immaterial (tests/cuda/umma_mx_probe.cu pins this on hardware).
+template <int CG>
+__device__ __forceinline__ void umma_mxf8(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t sfa,
+                                          uint32_t sfb, uint32_t accumulate) {
+    if (CG == 1)
+        asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %6, 0;\n"
+                     "tcgen05.mma.cta_group::1.kind::mxf8f6f4.block_scale.scale_vec::1X [%0], %1, %2, %3, [%4], [%5], p;\n}\n"
+                     ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(sfa), "r"(sfb), "r"(accumulate) : "memory");
+    else
+        asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %6, 0;\n"
+                     "tcgen05.mma.cta_group::2.kind::mxf8f6f4.block_scale.scale_vec::1X [%0], %1, %2, %3, [%4], [%5], p;\n}\n"
+                     ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(sfa), "r"(sfb), "r"(accumulate) : "memory");
+}
+// registers -> TMEM: this warp's 32 lanes x 16 consecutive columns := v (whole warp; lane quarter = warp_id % 4)
+__device__ __forceinline__ void tmem_fill_x16(uint32_t taddr, uint32_t v) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1};"
+                 ::"r"(taddr), "r"(v) : "memory");
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+}
+
+// ------------------------------------------------------------------ clusters / cta_group::2
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cluster address of `addr` (a shared::cta address of this CTA) in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t map_to_cta(uint32_t addr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait_cluster(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity, int* g_fault, int tag) {
+    if (mbar_try_wait_cluster(bar, parity)) return;
+    uint32_t spins = 0;
+    while (!mbar_try_wait_cluster(bar, parity)) {
+        if (++spins > (1u << 24)) mbar_timeout(bar, parity, g_fault, tag);
+    }
+}
+// TMA loads whose completion is signalled on a barrier of the CTA pair (here: always the leader's)
+__device__ __forceinline__ void tma2_load_2d(uint32_t smem_dst, const CUtensorMap* m, uint32_t bar_cluster, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.tile.mbarrier::complete_tx::bytes"
+        " [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(smem_dst), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar_cluster), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void tma2_load_4d(uint32_t smem_dst, const CUtensorMap* m, uint32_t bar_cluster, int c0, int c1,
+                                             int c2, int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.tile.mbarrier::complete_tx::bytes"
+        " [%0], [%1, {%3, %4, %5, %6}], [%2];"
+        ::"r"(smem_dst), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar_cluster), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
+}
+__device__ __forceinline__ void umma2_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n"
+        "}\n"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// arrives (count 1) on the barrier at this shared-memory offset in BOTH CTAs once all prior MMAs of this thread completed
+__device__ __forceinline__ void umma2_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(smem_u32(bar)), "h"((uint16_t)3)
+                 : "memory");
+}
+template <int CG>
+__device__ __forceinline__ void umma_f16_cg(uint32_t d, uint64_t a, uint64_t b, uint32_t idesc, uint32_t acc) {
+    if (CG == 2) umma2_f16(d, a, b, idesc, acc); else umma_f16(d, a, b, idesc, acc);
+}
+template <int CG>
+__device__ __forceinline__ void umma_commit_cg(uint64_t* bar) {
+    if (CG == 2) umma2_commit(bar); else umma_commit(bar);
+}
+
 // ------------------------------------------------------------------ descriptors
 // Instruction descriptor for kind::f16: bf16 x bf16 -> fp32, A and B both K-major.
 //   [4,6) c_format = 1 (F32) | [7,10) a_format = 1 (BF16) | [10,13) b_format = 1 (BF16)
 //   [15] a_major = 0 (K) | [16] b_major = 0 (K) | [17,23) N >> 3 | [24,29) M >> 4
 __host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N) {
     return (1u << 4) | (1u << 7) | (1u << 10) | (uint32_t(N >> 3) << 17) | (uint32_t(M >> 4) << 24);
+}
+
+// The same with fp16 operands (a_format = b_format = 0).
+__host__ __device__ constexpr uint32_t make_idesc_f16(int M, int N) {
+    return (1u << 4) | (uint32_t(N >> 3) << 17) | (uint32_t(M >> 4) << 24);
+}
+// Block-scaled descriptor for kind::mxf8f6f4 (cute::UMMA::InstrDescriptorBlockScaled): e4m3 x e4m3 (formats 0), K-major,
+//   [4,6) b_sf_id | [7,10) a_format | [10,13) b_format | [17,23) N >> 3 | [23] scale format = 1 (UE8M0) | [24,29) M >> 4 | [29,31) a_sf_id
+__host__ __device__ constexpr uint32_t make_idesc_mxf8(int M, int N) {
+    return (uint32_t(N >> 3) << 17) | (1u << 23) | (uint32_t(M >> 4) << 24);
 }
 
 // Shared-memory matrix descriptor (K-major operand):

@@ -6,6 +6,8 @@
 // No CPU fallback: every entry point fails with RSR_E_CUDA if no sm_100 device is usable.
 #include <cudaTypedefs.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <cuda_fp8.h>
 #include <cuda_runtime.h>
 
 #include <cmath>
@@ -13,6 +15,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <initializer_list>
 #include <new>
 #include <string>
 #include <thread>
@@ -84,14 +87,14 @@ static Layout make_layout(int factor) {
 }
 
 // --------------------------------------------------------------------------- kernel configs
-//                      KH KW  RB NG R NR TPS NBS NPIN NOUT SHUF NEPI
+// Ring geometry of the launches, overridable at build time for same-box A/B runs (tools/ab_session.py):
+// rows per pass R, input-row slots NR, taps per weight stage TPS, weight stages NBS, partial-sum tile slots NPIN.
 #ifndef RSR_CFG0_R
-#define RSR_CFG0_R 8   // 8 rows per pass: conv0's MMAs are tiny (15 per row), so the per-pass hand-offs dominate; 4 -> 8: -20 % (same-box A/B, r01j)
+#define RSR_CFG0_R 8   // 8 rows per pass: conv0's MMAs are tiny, so the per-pass hand-offs dominate; 4 -> 8: -20 % (same-box A/B, r01j)
 #endif
 #ifndef RSR_CFG0_NR
 #define RSR_CFG0_NR 16
 #endif
-using Cfg0 = ConvCfg<5, 1,  64, 1, RSR_CFG0_R, RSR_CFG0_NR, 5, 2, 0, 2, false, 8>;  // conv0 on the x-im2col'd input (K = 5 taps x 16)
 #ifndef RSR_CFG1_NR
 #define RSR_CFG1_NR 7
 #endif
@@ -104,9 +107,6 @@ using Cfg0 = ConvCfg<5, 1,  64, 1, RSR_CFG0_R, RSR_CFG0_NR, 5, 2, 0, 2, false, 8
 #ifndef RSR_L2PROMO
 #define RSR_L2PROMO CU_TENSOR_MAP_L2_PROMOTION_L2_256B
 #endif
-using Cfg1 = ConvCfg<5, 5, 128, 3, 2, RSR_CFG1_NR, RSR_CFG1_TPS, RSR_CFG1_NBS, 0, 2, false>;  // f  -> conv1 | conv2 | conv3
-// Ring geometry of the 3x3 launches, overridable at build time for same-box A/B runs (tools/ab_session.py):
-// rows per pass R, input-row slots NR, taps per weight stage TPS, weight stages NBS, partial-sum tile slots NPIN.
 #ifndef RSR_CFG2_R
 #define RSR_CFG2_R 2
 #endif
@@ -124,7 +124,7 @@ using Cfg1 = ConvCfg<5, 5, 128, 3, 2, RSR_CFG1_NR, RSR_CFG1_TPS, RSR_CFG1_NBS, 0
 #endif
 #define RSR_CFG2_GEOM RSR_CFG2_R, RSR_CFG2_NR, RSR_CFG2_TPS, RSR_CFG2_NBS, RSR_CFG2_NPIN
 #ifndef RSR_CFG3_R
-#define RSR_CFG3_R 3   // (split plan only) 3 rows per pass, 2 weight stages: -2 % on conv8|9, same-box A/B r01j
+#define RSR_CFG3_R 3   // 3 rows per pass, 2 weight stages: -2 % on conv8|9, same-box A/B r01j
 #endif
 #ifndef RSR_CFG3_NR
 #define RSR_CFG3_NR 6
@@ -145,38 +145,15 @@ using Cfg1 = ConvCfg<5, 5, 128, 3, 2, RSR_CFG1_NR, RSR_CFG1_TPS, RSR_CFG1_NBS, 0
 #ifndef RSR_CFG4_NR
 #define RSR_CFG4_NR 6
 #endif
-#ifndef RSR_CFG4_TPS
-#define RSR_CFG4_TPS 3
-#endif
 #ifndef RSR_CFG4_NBS
 #define RSR_CFG4_NBS 3
 #endif
 #ifndef RSR_CFG4_NPIN
 #define RSR_CFG4_NPIN 3
 #endif
-#define RSR_CFG4_GEOM RSR_CFG4_R, RSR_CFG4_NR, RSR_CFG4_TPS, RSR_CFG4_NBS, RSR_CFG4_NPIN
 #ifndef RSR_CFG3_NEPI
 #define RSR_CFG3_NEPI 4
 #endif
-//                                   R NR TPS NBS NPIN
-using Cfg2 = ConvCfg<3, 3, 128, 3, RSR_CFG2_GEOM, 2, false, 8>;  // l1 -> conv5 | conv6 | conv7   (+ P2, P3)
-using Cfg3 = ConvCfg<3, 3, 128, 2, RSR_CFG3_GEOM, 2, false, RSR_CFG3_NEPI>;  // l2 -> conv8 | conv9           (+ P3, E)
-using Cfg4 = ConvCfg<3, 3, 128, 1, RSR_CFG4_GEOM, 2, true, 8>;  // l3 -> conv10 (+ E) + expand + bilinear skip
-
-// Launches that run on CTA pairs (bit = launch index) when neither RSR_B200_PAIR nor RSR_FLAG_NO_PAIRS says otherwise:
-// conv1|2|3 (index 2: -12..18 % on pairs) and, in the fused plan, the fused middle launch (index 3: 455 vs 605 us).  The
-// separate 3x3 launches, conv0 and conv10 are slower on pairs (measured, profiles/README.md), so the split plan keeps bit 2 only.
-#ifndef RSR_DEFAULT_PAIR_MASK
-#define RSR_DEFAULT_PAIR_MASK 12
-#endif
-#ifndef RSR_DEFAULT_PAIR_MASK_SPLIT
-#define RSR_DEFAULT_PAIR_MASK_SPLIT 4
-#endif
-#ifndef RSR_DEFAULT_FUSED_MID
-#define RSR_DEFAULT_FUSED_MID 1   // conv5|6|7 + conv8|9 as one launch on CTA pairs: 455 vs 583 us, frame 1.495 -> 1.368 ms (same-box bench A/B, r01j)
-#endif
-// CTA-pair variants (conv_pair.cuh): same geometry, half a weight tap per CTA, so the shared memory freed can go
-// into deeper weight rings
 #ifndef RSR_PCFG1_NR
 #define RSR_PCFG1_NR 7
 #endif
@@ -189,24 +166,37 @@ using Cfg4 = ConvCfg<3, 3, 128, 1, RSR_CFG4_GEOM, 2, true, 8>;  // l3 -> conv10 
 #ifndef RSR_PCFG1_NEPI
 #define RSR_PCFG1_NEPI 4
 #endif
-using PCfg0 = ConvCfg<5, 1,  64, 1, 4, 12, 5, 2, 0, 2, false, 8, true>;
-using PCfg1 = ConvCfg<5, 5, 128, 3, 2, RSR_PCFG1_NR, RSR_PCFG1_TPS, RSR_PCFG1_NBS, 0, 2, false, RSR_PCFG1_NEPI, true>;
-using PCfg2 = ConvCfg<3, 3, 128, 3, 2,  5, 2, 3, 2, 2, false, 8, true>;
-using PCfg3 = ConvCfg<3, 3, 128, 2, 2,  5, 2, 3, 3, 2, false, 4, true>;
-using PCfg4 = ConvCfg<3, 3, 128, 1, 2,  6, 3, 3, 3, 2, true, 8, true>;
-// Row-folded variants (ConvCfg::FOLD, conv_strip.cuh; EXPERIMENTAL: selected only by RSR_B200_FOLD=<launch bit mask>, off by
-// default and not yet timed on hardware): conv0 and conv10, the two N = 32 launches whose MMAs are bound by the A-tile read.
-using FCfg0 = ConvCfg<5, 1,  64, 1, RSR_CFG0_R, RSR_CFG0_NR, 5, 2, 0, 2, false, 8, false, true>;
-using FCfg4 = ConvCfg<3, 3, 128, 1, RSR_CFG4_R, RSR_CFG4_NR, 3, RSR_CFG4_NBS, RSR_CFG4_NPIN, 2, true, 8, false, true>;
-template <class C> struct FoldOf { using type = void; };
-template <> struct FoldOf<Cfg0> { using type = FCfg0; };
-template <> struct FoldOf<Cfg4> { using type = FCfg4; };
-template <class C> struct PairOf;
-template <> struct PairOf<Cfg0> { using type = PCfg0; };
-template <> struct PairOf<Cfg1> { using type = PCfg1; };
-template <> struct PairOf<Cfg2> { using type = PCfg2; };
-template <> struct PairOf<Cfg3> { using type = PCfg3; };
-template <> struct PairOf<Cfg4> { using type = PCfg4; };
+// Launches that run on CTA pairs (bit = launch index): conv1|2|3 (index 2: -12..18 % on pairs) and the fused middle launch
+// (index 3: 455 vs 605 us).  The separate 3x3 launches, conv0 and conv10 were slower on pairs (r01i/r01j, profiles/README.md)
+// and have no pair instantiation any more.
+#ifndef RSR_DEFAULT_PAIR_MASK
+#define RSR_DEFAULT_PAIR_MASK 12
+#endif
+#ifndef RSR_DEFAULT_FUSED_MID
+#define RSR_DEFAULT_FUSED_MID 1   // conv5|6|7 + conv8|9 as one launch on CTA pairs: 455 vs 583 us (same-box bench A/B, r01j)
+#endif
+
+// The launch configurations of sr_net(F, None) for operand format PREC.  NGE = 32-column accumulator groups of the `expand`
+// node (3 F^2 channels, network.rs:37): 1 for F <= 3, 2 for F = 4.
+template <int PREC, int F>
+struct Net {
+    static constexpr int NGE = (3 * F * F + 31) / 32;
+    //                      KH KW  RB NG  R NR TPS NBS NPIN NOUT SHUF NEPI PAIR  FOLD  PREC OFMT
+    // conv0 on the x-im2col'd input (K = 5 taps x 16, always BF16x3 operands), row-folded; writes f in format PREC
+    using C0 = ConvCfg<5, 1,  64, 1, RSR_CFG0_R, RSR_CFG0_NR, 5, 2, 0, 2, 0, 8, false, true, PREC_BF16X3, PREC>;
+    // f -> conv1 | conv2 | conv3
+    using C1 = ConvCfg<5, 5, 128, 3, 2, RSR_CFG1_NR, RSR_CFG1_TPS, RSR_CFG1_NBS, 0, 2, 0, 4, false, false, PREC>;
+    using P1 = ConvCfg<5, 5, 128, 3, 2, RSR_PCFG1_NR, RSR_PCFG1_TPS, RSR_PCFG1_NBS, 0, 2, 0, RSR_PCFG1_NEPI, true, false, PREC>;
+    // l1 -> conv5 | conv6 | conv7 (+ P2, P3)   [split plan]
+    using C2 = std::conditional_t<NGE == 1, ConvCfg<3, 3, 128, 3, RSR_CFG2_GEOM, 2, 0, 8, false, false, PREC>,
+                                            ConvCfg<3, 3, 128, 4, 1, 4, 1, 4, 2, 2, 0, 8, false, false, PREC>>;
+    // l2 -> conv8 | conv9 (+ P3, E)            [split plan]
+    using C3 = std::conditional_t<NGE == 1, ConvCfg<3, 3, 128, 2, RSR_CFG3_GEOM, 2, 0, RSR_CFG3_NEPI, false, false, PREC>,
+                                            ConvCfg<3, 3, 128, 3, 2, 5, 2, 2, 3, 2, 0, 4, false, false, PREC>>;
+    // l3 -> conv10 (+ E) + expand + bilinear skip, row-folded
+    using C4 = std::conditional_t<NGE == 1, ConvCfg<3, 3, 128, 1, RSR_CFG4_R, RSR_CFG4_NR, 3, RSR_CFG4_NBS, RSR_CFG4_NPIN, 2, F, 8, false, true, PREC>,
+                                            ConvCfg<3, 3, 128, 2, 2, 6, 3, 2, 2, 2, F, 8, false, true, PREC>>;
+};
 
 enum { K_PACK = 0, K_CONV0, K_F, K_L1, K_L2, K_L3, K_COUNT };
 static const char* kKernelNames[K_COUNT] = {"pack_input", "conv0", "conv1|2|3", "conv5|6|7", "conv8|9",
@@ -217,45 +207,50 @@ static const char* kKernelNames[K_COUNT] = {"pack_input", "conv0", "conv1|2|3", 
 // horizontal neighbours x-2..x+2 (zero outside the image = Padding::Same) x 3 channels become
 // one 16-element K chunk (15 used), stored split as bf16 hi | mid = 64 B per pixel.  Also keeps
 // the pixel as a float4 for the bilinear skip of the last kernel.
+// A warp covers 28 consecutive pixels of one row: lane l loads pixel x0 - 2 + l once (coalesced), the neighbours come from
+// warp shuffles, lanes 2..29 produce the outputs.
 template <bool U8>
 __global__ void __launch_bounds__(256) pack_input_kernel(const void* __restrict__ in, int in_ch, int W, int H,
                                                           int NIMG, __nv_bfloat16* __restrict__ xcol,
                                                           float4* __restrict__ xf4) {
-    const size_t npx = (size_t)NIMG * H * W;
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < npx; i += (size_t)gridDim.x * blockDim.x) {
-        const int x = (int)(i % W);
-        const size_t rowbase = i - x;  // (img*H + y) * W
-        float v[16];
-        #pragma unroll
-        for (int d = 0; d < 5; ++d) {
-            const int xx = x + d - 2;
-            const bool ok = xx >= 0 && xx < W;
-            #pragma unroll
-            for (int c = 0; c < 3; ++c) {
-                float t = 0.f;
-                if (ok) {
-                    if (U8) t = (float)reinterpret_cast<const uint8_t*>(in)[(rowbase + xx) * in_ch + c] / 255.0f;
-                    else    t = reinterpret_cast<const float*>(in)[(rowbase + xx) * 3 + c];
-                }
-                v[d * 3 + c] = t;
+    const int lane = threadIdx.x & 31;
+    const int segs = (W + 27) / 28;                       // warp segments per row
+    const long long nseg = (long long)NIMG * H * segs;
+    const long long wstride = (long long)gridDim.x * (blockDim.x >> 5);
+    for (long long sgi = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); sgi < nseg; sgi += wstride) {
+        const long long row = sgi / segs;                 // img * H + y
+        const int x = (int)(sgi - row * segs) * 28 - 2 + lane;
+        float r = 0.f, g = 0.f, b = 0.f;
+        if (x >= 0 && x < W) {
+            const size_t i = (size_t)row * W + x;
+            if (U8) {
+                const uint8_t* q = reinterpret_cast<const uint8_t*>(in) + i * in_ch;
+                r = (float)q[0] / 255.0f; g = (float)q[1] / 255.0f; b = (float)q[2] / 255.0f;
+            } else {
+                const float* q = reinterpret_cast<const float*>(in) + i * 3;
+                r = q[0]; g = q[1]; b = q[2];
             }
         }
-        v[15] = 0.f;
-        uint32_t hi[8], mid[8];
+        float v[16];
         #pragma unroll
-        for (int k = 0; k < 8; ++k) {
-            const __nv_bfloat16 h0 = __float2bfloat16_rn(v[2 * k]), h1 = __float2bfloat16_rn(v[2 * k + 1]);
-            const __nv_bfloat16 m0 = __float2bfloat16_rn(v[2 * k] - __bfloat162float(h0));
-            const __nv_bfloat16 m1 = __float2bfloat16_rn(v[2 * k + 1] - __bfloat162float(h1));
-            hi[k] = pack_bf16x2(h0, h1);
-            mid[k] = pack_bf16x2(m0, m1);
+        for (int d = 0; d < 5; ++d) {                     // neighbour x + d - 2 lives in lane + d - 2
+            v[d * 3 + 0] = __shfl_sync(0xffffffffu, r, (lane + d - 2) & 31);
+            v[d * 3 + 1] = __shfl_sync(0xffffffffu, g, (lane + d - 2) & 31);
+            v[d * 3 + 2] = __shfl_sync(0xffffffffu, b, (lane + d - 2) & 31);
         }
-        uint4* dst = reinterpret_cast<uint4*>(xcol + i * 32);
-        dst[0] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-        dst[1] = make_uint4(hi[4], hi[5], hi[6], hi[7]);
-        dst[2] = make_uint4(mid[0], mid[1], mid[2], mid[3]);
-        dst[3] = make_uint4(mid[4], mid[5], mid[6], mid[7]);
-        xf4[i] = make_float4(v[6], v[7], v[8], 0.f);  // d = 2 is the pixel itself
+        v[15] = 0.f;
+        if (lane >= 2 && lane < 30 && x < W) {
+            uint32_t hi[8], mid[8];
+            #pragma unroll
+            for (int k = 0; k < 8; ++k) split_pair(v[2 * k], v[2 * k + 1], hi[k], mid[k]);
+            const size_t i = (size_t)row * W + x;
+            uint4* dst = reinterpret_cast<uint4*>(xcol + i * 32);
+            dst[0] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+            dst[1] = make_uint4(hi[4], hi[5], hi[6], hi[7]);
+            dst[2] = make_uint4(mid[0], mid[1], mid[2], mid[3]);
+            dst[3] = make_uint4(mid[4], mid[5], mid[6], mid[7]);
+            xf4[i] = make_float4(r, g, b, 0.f);
+        }
     }
 }
 
@@ -267,17 +262,17 @@ struct DevBuf {
 
 struct rsr_ctx {
     int device = 0, factor = 3, num_sms = 148;
+    int prec = PREC_F16MX;      // operand / activation storage format of the 32-channel launches (RSR_FLAG_BF16X3 -> PREC_BF16X3)
     Layout L{};
     cudaStream_t own_stream = nullptr, stream = nullptr;
-    // packed weights (bf16 hi|mid), biases / slopes (32 floats each, zero padded)
-    __nv_bfloat16 *w0 = nullptr, *w1 = nullptr, *w2 = nullptr, *w3 = nullptr, *w4 = nullptr;
-    float* vecs = nullptr;  // 9 x 32 floats: f_bias f_activ l1_bias l1_activ l2_bias l2_activ l3_bias l3_activ expand_bias
+    // packed weights (conv_strip.cuh storage formats), biases / slopes (32 floats each, zero padded; expand_bias: 64)
+    uint8_t *w0 = nullptr, *w1 = nullptr, *w2 = nullptr, *w3 = nullptr, *w4 = nullptr;
+    float* vecs = nullptr;  // 8 x 32 floats: f_bias f_activ l1_bias l1_activ l2_bias l2_activ l3_bias l3_activ, then 64: expand_bias
     // workspace
     DevBuf xcol, xf4, actA, actB, partA, partB, partC, out_f32, out_u8, in_stage;
-    bool fused_mid = false;     // conv5|6|7 + conv8|9 in one launch (conv_fused.cuh); RSR_FLAG_FUSED_MID
-    int pair_mask = 0;          // bit k: launch index k (1 = conv0 .. 5 = conv10) runs as CTA pairs (conv_pair.cuh)
-    int fold_mask = 0;          // bit k: launch index k (1 = conv0, 5 = conv10) runs with row-folded MMAs (experimental)
-    __nv_bfloat16 *w0f = nullptr, *w4f = nullptr;   // the same weights, taps of a tap column stored bottom tap first
+    int plan = 0;               // middle levels: 0 = by width (fused unless the 124-pixel strips waste too much), 1 = fused, 2 = split
+    bool fused_last = false;    // plan the most recent call ran
+    int pair_mask = 0;          // bit 2: conv1|2|3 on CTA pairs, bit 3: fused middle launch on CTA pairs (conv_pair.cuh)
     int fused_dbg = 0;          // test hook rsr_debug_fused: bit 0 skip S2 MMAs, bit 1 dump l2 / raw accumulators, bit 2 profile (debug kernel),
                                 // bit 3 profile of the plan's own kernel (single CTA or pair; needs a -DRSR_FUSED_PROF=1 build)
     DevBuf dbg_l2, dbg_t3, dbg_prof;
@@ -324,24 +319,40 @@ static inline void split_bf16(float w, __nv_bfloat16& hi, __nv_bfloat16& mid) {
     mid = __float2bfloat16_rn(w - __bfloat162float(hi));
 }
 
-// Packs the convolutions that read one input node into the per-tap B tiles of the kernel:
-// out[t][n][0..31] = hi(w[n][t][ci]), out[t][n][32..63] = mid(...); n runs over the listed
-// convolutions, each padded to 32 output channels with zero rows.
-static void pack_group(const float* params, const size_t* offs, const int* couts, int nconv, int K,
-                       std::vector<__nv_bfloat16>& out) {
-    const int taps = K * K, ncol = 32 * nconv;
-    out.assign((size_t)taps * ncol * 64, __float2bfloat16_rn(0.f));
-    for (int g = 0; g < nconv; ++g)
-        for (int o = 0; o < couts[g]; ++o)
-            for (int t = 0; t < taps; ++t)
-                for (int ci = 0; ci < 32; ++ci) {
-                    const float w = params[offs[g] + ((size_t)o * taps + t) * 32 + ci];
-                    __nv_bfloat16 h, m;
-                    split_bf16(w, h, m);
-                    const size_t row = ((size_t)t * ncol + g * 32 + o) * 64;
-                    out[row + ci] = h;
-                    out[row + 32 + ci] = m;
-                }
+// 32 input-channel weights of one (tap, output channel) -> the 128-byte weight row of operand format `prec`
+// (conv_strip.cuh): BF16X3 [32 x bf16 hi | 32 x bf16 mid]; F16MX [32 x fp16 w_h | per 16 channels: 16 x e4m3(w), 16 x e4m3(2^11 w_l)].
+static void pack_weight_row(const float* w, uint8_t* row, int prec) {
+    if (prec == PREC_F16MX) {
+        __half* h = reinterpret_cast<__half*>(row);
+        for (int ci = 0; ci < 32; ++ci) {
+            const __half wh = __float2half_rn(w[ci]);
+            h[ci] = wh;
+            const float wl = w[ci] - __half2float(wh);
+            uint8_t* sec = row + 64 + (ci >> 4) * 32;
+            sec[ci & 15] = (uint8_t)__nv_cvt_float_to_fp8(w[ci], __NV_SATFINITE, __NV_E4M3);
+            sec[16 + (ci & 15)] = (uint8_t)__nv_cvt_float_to_fp8(wl * F16MX_SCALE, __NV_SATFINITE, __NV_E4M3);
+        }
+    } else {
+        __nv_bfloat16* q = reinterpret_cast<__nv_bfloat16*>(row);
+        for (int ci = 0; ci < 32; ++ci) split_bf16(w[ci], q[ci], q[32 + ci]);
+    }
+}
+
+// One 32-column accumulator group of a launch: output channels [o0, o0 + n) of the convolution stored at params + off.
+struct WGroup { size_t off; int o0, n; };
+// Packs the convolutions that read one input node into the per-tap B tiles of the kernel: out[t][group * 32 + o][128 B];
+// groups shorter than 32 output channels are padded with zero rows.  fold: store the taps of a tap column bottom tap first
+// (block tb * K + (K-1 - ta)), the order ConvCfg::FOLD reads them in.
+static void pack_group(const float* params, const std::vector<WGroup>& groups, int K, int prec, bool fold, std::vector<uint8_t>& out) {
+    const int taps = K * K, ncol = 32 * (int)groups.size();
+    out.assign((size_t)taps * ncol * 128, 0);
+    for (size_t g = 0; g < groups.size(); ++g)
+        for (int o = 0; o < groups[g].n; ++o)
+            for (int t = 0; t < taps; ++t) {
+                const int blk = fold ? (t % K) * K + (K - 1 - t / K) : t;
+                pack_weight_row(params + groups[g].off + ((size_t)(groups[g].o0 + o) * taps + t) * 32,
+                                &out[((size_t)blk * ncol + g * 32 + o) * 128], prec);
+            }
 }
 
 extern "C" size_t rsr_num_params(int factor) {
@@ -351,14 +362,14 @@ extern "C" size_t rsr_num_params(int factor) {
 
 extern "C" const char* rsr_last_error(void) { return g_err.c_str(); }
 extern "C" int rsr_last_error_code(void) { return g_err_code; }
-extern "C" const char* rsr_version(void) { return "rsr_b200 0.1 sm_100a (tcgen05 bf16x3 implicit-GEMM)"; }
+extern "C" const char* rsr_version(void) { return "rsr_b200 0.2 sm_100a (tcgen05 implicit-GEMM, fp16 + mxfp8 split operands)"; }
 extern "C" const char* rsr_kernel_name(int i) { return (i >= 0 && i < K_COUNT) ? kKernelNames[i] : ""; }
 
 extern "C" void rsr_destroy(rsr_ctx* c) {
     if (!c) return;
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
-    cudaFree(c->w0); cudaFree(c->w1); cudaFree(c->w2); cudaFree(c->w3); cudaFree(c->w4); cudaFree(c->w0f); cudaFree(c->w4f);
+    cudaFree(c->w0); cudaFree(c->w1); cudaFree(c->w2); cudaFree(c->w3); cudaFree(c->w4);
     cudaFree(c->vecs); cudaFree(c->prof);
     if (c->fault_host) cudaFreeHost(c->fault_host);
     release(c->xcol); release(c->xf4); release(c->actA); release(c->actB); release(c->partA);
@@ -382,6 +393,49 @@ static int upload(T** dst, const void* src, size_t bytes) {
     CUDA_TRY(cudaMemcpy(*dst, src, bytes, cudaMemcpyHostToDevice));
     return 0;
 }
+
+template <class C>
+static int set_smem(void (*k)(ConvParams)) {
+    CUDA_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+    return 0;
+}
+template <int PREC, int F>
+static int set_attrs() {
+    using N = Net<PREC, F>;
+    if (int rc = set_smem<typename N::C0>(conv_strip_kernel<typename N::C0>)) return rc;
+    if (int rc = set_smem<typename N::C1>(conv_strip_kernel<typename N::C1>)) return rc;
+    if (int rc = set_smem<typename N::P1>(conv_pair_kernel<typename N::P1>)) return rc;
+    if (int rc = set_smem<typename N::C2>(conv_strip_kernel<typename N::C2>)) return rc;
+    if (int rc = set_smem<typename N::C3>(conv_strip_kernel<typename N::C3>)) return rc;
+    if (int rc = set_smem<typename N::C4>(conv_strip_kernel<typename N::C4>)) return rc;
+    if (N::NGE == 1) {
+        CUDA_TRY(cudaFuncSetAttribute(conv_fused_mid_kernel<false, false, PREC>, cudaFuncAttributeMaxDynamicSharedMemorySize, FusedCfgT<false, PREC>::SMEM_BYTES));
+        CUDA_TRY(cudaFuncSetAttribute(conv_fused_mid_kernel<true, false, PREC>, cudaFuncAttributeMaxDynamicSharedMemorySize, FusedCfgT<false, PREC>::SMEM_BYTES));
+        CUDA_TRY(cudaFuncSetAttribute(conv_fused_mid_kernel<false, true, PREC>, cudaFuncAttributeMaxDynamicSharedMemorySize, FusedCfgT<true, PREC>::SMEM_BYTES));
+    }
+    return 0;
+}
+// Calls fn.template operator()<PREC, F>() for the context's operand format and factor.
+template <class Fn>
+static int dispatch(int prec, int factor, Fn&& fn) {
+    if (prec == PREC_F16MX) {
+        switch (factor) {
+            case 1: return fn.template operator()<PREC_F16MX, 1>();
+            case 2: return fn.template operator()<PREC_F16MX, 2>();
+            case 3: return fn.template operator()<PREC_F16MX, 3>();
+            case 4: return fn.template operator()<PREC_F16MX, 4>();
+        }
+    } else {
+        switch (factor) {
+            case 1: return fn.template operator()<PREC_BF16X3, 1>();
+            case 2: return fn.template operator()<PREC_BF16X3, 2>();
+            case 3: return fn.template operator()<PREC_BF16X3, 3>();
+            case 4: return fn.template operator()<PREC_BF16X3, 4>();
+        }
+    }
+    return fail(RSR_E_UNSUPPORTED, "factor %d", factor);
+}
+struct SetAttrs { template <int PREC, int F> int operator()() const { return set_attrs<PREC, F>(); } };
 
 static int create_impl(rsr_ctx* c, const float* params) {
     const Layout& L = c->L;
@@ -411,7 +465,8 @@ static int create_impl(rsr_ctx* c, const float* params) {
     memset(c->fault_host, 0, 64 * sizeof(int));
     CUDA_TRY(cudaHostGetDevicePointer((void**)&c->fault, c->fault_host, 0));
 
-    // conv0: [32][5][5][3] -> w0[a][n][k = dxi*3 + c | 16 + k]  (x-im2col form, 64 B rows)
+    // conv0: [32][5][5][3] -> w0[4 - a][n][k = b*3 + c | 16 + k]  (x-im2col form, 64 B rows of bf16 hi | mid; tap rows stored
+    // bottom tap first: the row-folded order)
     {
         std::vector<__nv_bfloat16> w((size_t)5 * 32 * 32, __float2bfloat16_rn(0.f));
         for (int n = 0; n < 32; ++n)
@@ -420,81 +475,61 @@ static int create_impl(rsr_ctx* c, const float* params) {
                     for (int ch = 0; ch < 3; ++ch) {
                         __nv_bfloat16 h, m;
                         split_bf16(params[L.conv0 + (((size_t)n * 5 + a) * 5 + b) * 3 + ch], h, m);
-                        const size_t row = ((size_t)a * 32 + n) * 32;
+                        const size_t row = ((size_t)(4 - a) * 32 + n) * 32;
                         w[row + b * 3 + ch] = h;
                         w[row + 16 + b * 3 + ch] = m;
                     }
         if (int rc = upload(&c->w0, w.data(), w.size() * 2)) return rc;
-        // row-folded order: tap row a stored at block 4 - a
-        std::vector<__nv_bfloat16> wf(w.size());
-        for (int a = 0; a < 5; ++a)
-            memcpy(&wf[(size_t)(4 - a) * 32 * 32], &w[(size_t)a * 32 * 32], sizeof(__nv_bfloat16) * 32 * 32);
-        if (int rc = upload(&c->w0f, wf.data(), wf.size() * 2)) return rc;
     }
-    std::vector<__nv_bfloat16> w;
+    const int ce = L.ce, nge = (ce + 31) / 32;
+    auto expand_groups = [&](std::vector<WGroup>& g, size_t off) {
+        for (int k = 0; k < nge; ++k) g.push_back({off, k * 32, std::min(32, ce - k * 32)});
+    };
+    std::vector<uint8_t> w;
     {
-        const size_t offs[3] = {L.conv1, L.conv2, L.conv3};
-        const int co[3] = {32, 32, 32};
-        pack_group(params, offs, co, 3, 5, w);
-        if (int rc = upload(&c->w1, w.data(), w.size() * 2)) return rc;
+        std::vector<WGroup> g = {{L.conv1, 0, 32}, {L.conv2, 0, 32}, {L.conv3, 0, 32}};
+        pack_group(params, g, 5, c->prec, false, w);
+        if (int rc = upload(&c->w1, w.data(), w.size())) return rc;
     }
     {
-        const size_t offs[3] = {L.conv5, L.conv6, L.conv7};
-        const int co[3] = {32, 32, L.ce};
-        pack_group(params, offs, co, 3, 3, w);
-        if (int rc = upload(&c->w2, w.data(), w.size() * 2)) return rc;
+        std::vector<WGroup> g = {{L.conv5, 0, 32}, {L.conv6, 0, 32}};
+        expand_groups(g, L.conv7);
+        pack_group(params, g, 3, c->prec, false, w);
+        if (int rc = upload(&c->w2, w.data(), w.size())) return rc;
     }
     {
-        const size_t offs[2] = {L.conv8, L.conv9};
-        const int co[2] = {32, L.ce};
-        pack_group(params, offs, co, 2, 3, w);
-        if (int rc = upload(&c->w3, w.data(), w.size() * 2)) return rc;
+        std::vector<WGroup> g = {{L.conv8, 0, 32}};
+        expand_groups(g, L.conv9);
+        pack_group(params, g, 3, c->prec, false, w);
+        if (int rc = upload(&c->w3, w.data(), w.size())) return rc;
     }
     {
-        const size_t offs[1] = {L.conv10};
-        const int co[1] = {L.ce};
-        pack_group(params, offs, co, 1, 3, w);
-        if (int rc = upload(&c->w4, w.data(), w.size() * 2)) return rc;
-        // row-folded order: tap (ta, tb) stored at block tb * 3 + (2 - ta)   (blocks of 32 rows x 64 bf16)
-        std::vector<__nv_bfloat16> wf(w.size());
-        for (int ta = 0; ta < 3; ++ta)
-            for (int tb = 0; tb < 3; ++tb)
-                memcpy(&wf[(size_t)(tb * 3 + (2 - ta)) * 32 * 64], &w[(size_t)(ta * 3 + tb) * 32 * 64], sizeof(__nv_bfloat16) * 32 * 64);
-        if (int rc = upload(&c->w4f, wf.data(), wf.size() * 2)) return rc;
+        std::vector<WGroup> g;
+        expand_groups(g, L.conv10);
+        pack_group(params, g, 3, c->prec, true, w);
+        if (int rc = upload(&c->w4, w.data(), w.size())) return rc;
     }
     {
-        std::vector<float> v(9 * 32, 0.f);
-        const size_t src[9] = {L.f_bias, L.f_activ, L.l1_bias, L.l1_activ, L.l2_bias, L.l2_activ,
-                               L.l3_bias, L.l3_activ, L.expand_bias};
-        for (int i = 0; i < 9; ++i) memcpy(&v[i * 32], params + src[i], sizeof(float) * (i == 8 ? L.ce : 32));
+        std::vector<float> v(8 * 32 + 64, 0.f);
+        const size_t src[8] = {L.f_bias, L.f_activ, L.l1_bias, L.l1_activ, L.l2_bias, L.l2_activ, L.l3_bias, L.l3_activ};
+        for (int i = 0; i < 8; ++i) memcpy(&v[i * 32], params + src[i], sizeof(float) * 32);
+        memcpy(&v[8 * 32], params + L.expand_bias, sizeof(float) * ce);
         if (int rc = upload(&c->vecs, v.data(), v.size() * 4)) return rc;
     }
-    CUDA_TRY(cudaFuncSetAttribute(conv_strip_kernel<Cfg0>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg0::SMEM_BYTES));
-    CUDA_TRY(cudaFuncSetAttribute(conv_strip_kernel<Cfg1>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg1::SMEM_BYTES));
-    CUDA_TRY(cudaFuncSetAttribute(conv_strip_kernel<Cfg2>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg2::SMEM_BYTES));
-    CUDA_TRY(cudaFuncSetAttribute(conv_strip_kernel<Cfg3>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg3::SMEM_BYTES));
-    CUDA_TRY(cudaFuncSetAttribute(conv_strip_kernel<Cfg4>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg4::SMEM_BYTES));
-    CUDA_TRY(cudaFuncSetAttribute(conv_strip_kernel<FCfg0>, cudaFuncAttributeMaxDynamicSharedMemorySize, FCfg0::SMEM_BYTES));
-    CUDA_TRY(cudaFuncSetAttribute(conv_strip_kernel<FCfg4>, cudaFuncAttributeMaxDynamicSharedMemorySize, FCfg4::SMEM_BYTES));
-    CUDA_TRY(cudaFuncSetAttribute(conv_fused_mid_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FusedCfg::SMEM_BYTES));
-    CUDA_TRY(cudaFuncSetAttribute(conv_fused_mid_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FusedCfg::SMEM_BYTES));
-    CUDA_TRY(cudaFuncSetAttribute(conv_fused_mid_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FusedCfgT<true>::SMEM_BYTES));
-    CUDA_TRY(cudaFuncSetAttribute(conv_pair_kernel<PCfg0>, cudaFuncAttributeMaxDynamicSharedMemorySize, PCfg0::SMEM_BYTES));
-    CUDA_TRY(cudaFuncSetAttribute(conv_pair_kernel<PCfg1>, cudaFuncAttributeMaxDynamicSharedMemorySize, PCfg1::SMEM_BYTES));
-    CUDA_TRY(cudaFuncSetAttribute(conv_pair_kernel<PCfg2>, cudaFuncAttributeMaxDynamicSharedMemorySize, PCfg2::SMEM_BYTES));
-    CUDA_TRY(cudaFuncSetAttribute(conv_pair_kernel<PCfg3>, cudaFuncAttributeMaxDynamicSharedMemorySize, PCfg3::SMEM_BYTES));
-    CUDA_TRY(cudaFuncSetAttribute(conv_pair_kernel<PCfg4>, cudaFuncAttributeMaxDynamicSharedMemorySize, PCfg4::SMEM_BYTES));
-    return 0;
+    return dispatch(c->prec, c->factor, SetAttrs{});
 }
 
-extern "C" rsr_ctx* rsr_create(const float* params, size_t n_params, int factor, int device, int flags) {
+// pair_mask < 0: the library default
+static rsr_ctx* create_ctx(const float* params, size_t n_params, int factor, int device, int flags, int pair_mask) {
     g_err.clear();
     g_err_code = 0;
     if (!params) { fail(RSR_E_BAD_ARG, "params is null"); return nullptr; }
-    if (factor != 3) {
-        // the reference is compiled with FACTOR = 3 (main.rs:31) and ships factor-3 weights only
-        fail(factor >= 1 && factor <= 4 ? RSR_E_UNSUPPORTED : RSR_E_BAD_ARG,
-             "factor %d not supported by the GPU path (reference FACTOR is 3, main.rs:31)", factor);
+    if (factor < 1 || factor > 4) {
+        fail(RSR_E_BAD_ARG, "factor %d out of range 1..4 (reference FACTOR is 3, main.rs:31)", factor);
+        return nullptr;
+    }
+    if ((flags & RSR_FLAG_FUSED_MID) && factor == 4) {
+        fail(RSR_E_UNSUPPORTED, "the fused middle launch holds 32 expand channels; factor 4 (48) runs the split plan");
         return nullptr;
     }
     const Layout L = make_layout(factor);
@@ -516,20 +551,16 @@ extern "C" rsr_ctx* rsr_create(const float* params, size_t n_params, int factor,
     c->device = device;
     c->factor = factor;
     c->L = L;
-    {
-        // fused middle launch: explicit flag wins, then the RSR_B200_FUSED environment variable (A/B runs),
-        // then the build default
-        bool fused = RSR_DEFAULT_FUSED_MID != 0;
-        if (const char* e = getenv("RSR_B200_FUSED")) fused = e[0] == '1';
-        if (flags & RSR_FLAG_FUSED_MID) fused = true;
-        if (flags & RSR_FLAG_SPLIT_MID) fused = false;
-        c->fused_mid = fused;
-        int pm = fused ? RSR_DEFAULT_PAIR_MASK : RSR_DEFAULT_PAIR_MASK_SPLIT;
-        if (const char* e = getenv("RSR_B200_PAIR")) pm = atoi(e);
-        if (flags & RSR_FLAG_NO_PAIRS) pm = 0;
-        c->pair_mask = pm;
-        if (const char* e = getenv("RSR_B200_FOLD")) c->fold_mask = atoi(e) & ((1 << K_CONV0) | (1 << K_L3)) & ~pm;
-    }
+    c->prec = (flags & RSR_FLAG_BF16X3) ? PREC_BF16X3 : PREC_F16MX;
+    c->plan = (flags & RSR_FLAG_SPLIT_MID) ? 2 : (flags & RSR_FLAG_FUSED_MID) ? 1 : (RSR_DEFAULT_FUSED_MID ? 0 : 2);
+    if (factor == 4) c->plan = 2;
+    c->pair_mask = (flags & RSR_FLAG_NO_PAIRS) ? 0 : (pair_mask >= 0 ? pair_mask & 12 : RSR_DEFAULT_PAIR_MASK);
+#ifdef RSR_LAB
+    // lab builds only (tools/ab_session.py): environment overrides for same-box A/B runs
+    if (const char* e = getenv("RSR_B200_FUSED")) c->plan = e[0] == '1' ? 1 : 2;
+    if (const char* e = getenv("RSR_B200_PAIR")) c->pair_mask = atoi(e) & 12;
+    if (const char* e = getenv("RSR_B200_PREC")) c->prec = e[0] == '0' ? PREC_BF16X3 : PREC_F16MX;
+#endif
     if (create_impl(c, params) != 0) {
         const std::string keep = g_err;
         const int code = g_err_code;
@@ -539,6 +570,12 @@ extern "C" rsr_ctx* rsr_create(const float* params, size_t n_params, int factor,
         return nullptr;
     }
     return c;
+}
+extern "C" rsr_ctx* rsr_create(const float* params, size_t n_params, int factor, int device, int flags) {
+    return create_ctx(params, n_params, factor, device, flags, -1);
+}
+extern "C" rsr_ctx* rsr_debug_create(const float* params, size_t n_params, int factor, int device, int flags, int pair_mask) {
+    return create_ctx(params, n_params, factor, device, flags, pair_mask);
 }
 
 extern "C" int rsr_set_stream(rsr_ctx* c, void* s) {
@@ -564,15 +601,17 @@ extern "C" int rsr_synchronize(rsr_ctx* c) {
 }
 
 // ------------------------------------------------------------------------------ tensor maps
-static int make_map_act(rsr_ctx* c, CUtensorMap* m, const void* base, int elems, int W, int H, int N, int boxw) {
-    const cuuint64_t rb = (cuuint64_t)elems * 2;
+// activation / xcol tensor: rows of `row_bytes` (128: swizzle 128B; 64: swizzle 64B) per pixel, described as 2-byte elements
+static int make_map_act(rsr_ctx* c, CUtensorMap* m, const void* base, int row_bytes, int W, int H, int N, int boxw) {
+    const cuuint64_t rb = (cuuint64_t)row_bytes;
+    const int elems = row_bytes / 2;
     cuuint64_t dims[4] = {(cuuint64_t)elems, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
     cuuint64_t strides[3] = {rb, rb * W, rb * W * H};
     cuuint32_t box[4] = {(cuuint32_t)elems, (cuuint32_t)boxw, 1, 1};
     cuuint32_t es[4] = {1, 1, 1, 1};
-    CUresult r = c->encode(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, es,
+    CUresult r = c->encode(m, CU_TENSOR_MAP_DATA_TYPE_UINT16, 4, const_cast<void*>(base), dims, strides, box, es,
                            CU_TENSOR_MAP_INTERLEAVE_NONE,
-                           elems == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                           row_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
                            RSR_L2PROMO, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail(RSR_E_CUDA, "cuTensorMapEncodeTiled(activation %dx%dx%d) failed: %d", W, H, N, (int)r);
     return 0;
@@ -588,24 +627,23 @@ static int make_map_part(rsr_ctx* c, CUtensorMap* m, const void* base, int W, in
     if (r != CUDA_SUCCESS) return fail(RSR_E_CUDA, "cuTensorMapEncodeTiled(partial %dx%dx%d) failed: %d", W, H, N, (int)r);
     return 0;
 }
-static int make_map_w(rsr_ctx* c, CUtensorMap* m, const void* base, int elems, int rows, int boxrows) {
-    const cuuint64_t rb = (cuuint64_t)elems * 2;
+static int make_map_w(rsr_ctx* c, CUtensorMap* m, const void* base, int row_bytes, int rows, int boxrows) {
+    const int elems = row_bytes / 2;
     cuuint64_t dims[2] = {(cuuint64_t)elems, (cuuint64_t)rows};
-    cuuint64_t strides[1] = {rb};
+    cuuint64_t strides[1] = {(cuuint64_t)row_bytes};
     cuuint32_t box[2] = {(cuuint32_t)elems, (cuuint32_t)boxrows};
     cuuint32_t es[2] = {1, 1};
-    CUresult r = c->encode(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, es,
+    CUresult r = c->encode(m, CU_TENSOR_MAP_DATA_TYPE_UINT16, 2, const_cast<void*>(base), dims, strides, box, es,
                            CU_TENSOR_MAP_INTERLEAVE_NONE,
-                           elems == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                           row_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
                            RSR_L2PROMO, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail(RSR_E_CUDA, "cuTensorMapEncodeTiled(weights) failed: %d", (int)r);
     return 0;
 }
 
-// CTA-pair variant (conv_pair.cuh): p.tmB must have been built with a box of NCOL / 2 rows (one CTA's half tap).
-template <class C0>
+// CTA-pair launch (conv_pair.cuh): p.tmB must have been built with a box of NCOL / 2 rows (one CTA's half tap).
+template <class C>
 static int launch_conv_pair(rsr_ctx* c, ConvParams& p, int kindex) {
-    using C = typename PairOf<C0>::type;
     p.n_strips = (p.W + 127) / 128;
     p.total_rowtiles = (long long)p.NIMG * p.n_strips * (p.row_end - p.row_begin);
     const int ncl = (int)std::min<long long>(p.total_rowtiles, c->num_sms / 2);
@@ -616,39 +654,46 @@ static int launch_conv_pair(rsr_ctx* c, ConvParams& p, int kindex) {
     c->last_launches++;
     return 0;
 }
-
 template <class C>
 static int launch_conv(rsr_ctx* c, ConvParams& p, int kindex) {
-    if (c->pair_mask >> kindex & 1) return launch_conv_pair<C>(c, p, kindex);
     p.n_strips = (p.W + 127) / 128;
     p.total_rowtiles = (long long)p.NIMG * p.n_strips * (p.row_end - p.row_begin);
     const int grid = (int)std::min<long long>(p.total_rowtiles, c->num_sms);
     p.prof = (c->prof && grid <= 256) ? c->prof + (size_t)kindex * 256 * 16 : nullptr;
     c->prof_grid[kindex] = grid;
-    using F = typename FoldOf<C>::type;
-    if constexpr (!std::is_void<F>::value) {
-        if (c->fold_mask >> kindex & 1) {   // p.tmB must then map the fold-ordered weight copy (same box)
-            conv_strip_kernel<F><<<grid, F::NTHREADS, F::SMEM_BYTES, c->stream>>>(p);
-            CUDA_TRY(cudaGetLastError());
-            c->last_launches++;
-            return 0;
-        }
-    }
     conv_strip_kernel<C><<<grid, C::NTHREADS, C::SMEM_BYTES, c->stream>>>(p);
     CUDA_TRY(cudaGetLastError());
     c->last_launches++;
     return 0;
 }
 
+// Output selection of one forward pass: exactly one of f32 / u8 (u8_ch = 4 RGBA or 3 RGB); top / bottom = halo rows of a band
+// (rows of the input whose outputs are not produced; 0 for whole images).
+struct OutSpec {
+    float* f32 = nullptr;
+    uint8_t* u8 = nullptr;
+    int u8_ch = 4;
+    int top = 0, bottom = 0;
+};
+
+// Middle levels on the fused launch?  It walks 124-pixel strips where the split launches walk 128-pixel strips, so narrow
+// images can pay for a nearly empty extra strip; per strip the fused launch costs FUSED_STRIP_COST of the two split launches
+// (same-box measurements, profiles/README.md).
+#ifndef RSR_FUSED_STRIP_COST
+#define RSR_FUSED_STRIP_COST 0.75
+#endif
+static bool use_fused(const rsr_ctx* c, int w) {
+    if (c->plan == 1) return true;
+    if (c->plan == 2) return false;
+    const int nf = (w + FusedCfg::STRIP - 1) / FusedCfg::STRIP, ns = (w + 127) / 128;
+    return nf * RSR_FUSED_STRIP_COST <= ns;
+}
+
 // The whole forward pass on device-resident input.  in: f32 [n][h][w][3] or u8 [n][h][w][ch].
-static int forward_device(rsr_ctx* c, const void* d_in, bool u8, int in_ch, int n, int w, int h, float* d_out_f32,
-                          uint8_t* d_out_u8) {
-    if (!c) return fail(RSR_E_BAD_ARG, "ctx is null");
-    if (!d_in || (!d_out_f32 && !d_out_u8)) return fail(RSR_E_BAD_ARG, "null buffer");
-    if (d_out_f32 && d_out_u8) return fail(RSR_E_BAD_ARG, "exactly one of the f32 / RGBA outputs may be requested");
-    if (n < 1 || w < 1 || h < 1) return fail(RSR_E_BAD_ARG, "bad dimensions n=%d w=%d h=%d", n, w, h);
-    if (u8 && in_ch != 3 && in_ch != 4) return fail(RSR_E_BAD_ARG, "in_channels must be 3 or 4 (got %d)", in_ch);
-    CUDA_TRY(cudaSetDevice(c->device));
+template <int PREC, int F>
+static int forward_impl(rsr_ctx* c, const void* d_in, bool u8, int in_ch, int n, int w, int h, const OutSpec& o) {
+    using N = Net<PREC, F>;
+    constexpr int NGE = N::NGE;
     const size_t npx = (size_t)n * w * h;
     if (int rc = ensure(c->xcol, npx * 64)) return rc;
     if (int rc = ensure(c->xf4, npx * 16)) return rc;
@@ -656,15 +701,18 @@ static int forward_device(rsr_ctx* c, const void* d_in, bool u8, int in_ch, int 
     if (int rc = ensure(c->actB, npx * 128)) return rc;
     if (int rc = ensure(c->partA, npx * 128)) return rc;
     if (int rc = ensure(c->partB, npx * 128)) return rc;
+    const bool fused = NGE == 1 && use_fused(c, w);
+    if (fused || NGE == 2) { if (int rc = ensure(c->partC, npx * 128)) return rc; }
+    c->fused_last = fused;
 
-    __nv_bfloat16* xcol = (__nv_bfloat16*)c->xcol.p;
-    __nv_bfloat16* f_act = (__nv_bfloat16*)c->actA.p;   // f, later l2
-    __nv_bfloat16* l1_act = (__nv_bfloat16*)c->actB.p;  // l1, later l3
-    __nv_bfloat16* l2_act = f_act;
-    __nv_bfloat16* l3_act = l1_act;                     // (the fused middle launch puts l3 into f's buffer instead)
+    uint8_t* xcol = (uint8_t*)c->xcol.p;
+    uint8_t* f_act = (uint8_t*)c->actA.p;   // f, later l2
+    uint8_t* l1_act = (uint8_t*)c->actB.p;  // l1, later l3
+    uint8_t* l2_act = f_act;
+    uint8_t* l3_act = l1_act;               // (the fused middle launch puts l3 into f's buffer instead)
     float* P2 = (float*)c->partA.p;  // conv2(f): fp32 partial of l2_conv; later E (expand partial)
     float* P3 = (float*)c->partB.p;  // conv3(f) (+conv6(l1)): fp32 partial of l3_conv, updated in place
-    float* E = P2;                   // conv7(l1) (+conv9(l2)), updated in place (aliasing)
+    float* E[2] = {P2, (float*)c->partC.p};   // conv7(l1) (+conv9(l2)) per 32-column group, updated in place (aliasing)
     const float* V = c->vecs;
     const float *f_bias = V, *f_slope = V + 32, *l1_bias = V + 64, *l1_slope = V + 96, *l2_bias = V + 128,
                 *l2_slope = V + 160, *l3_bias = V + 192, *l3_slope = V + 224, *e_bias = V + 256;
@@ -672,9 +720,10 @@ static int forward_device(rsr_ctx* c, const void* d_in, bool u8, int in_ch, int 
     c->last_launches = 0;
     CUDA_TRY(cudaEventRecord(c->ev[0], c->stream));
     {
-        const int blocks = (int)std::min<size_t>((npx + 255) / 256, (size_t)c->num_sms * 16);
-        if (u8) pack_input_kernel<true><<<blocks, 256, 0, c->stream>>>(d_in, in_ch, w, h, n, xcol, (float4*)c->xf4.p);
-        else    pack_input_kernel<false><<<blocks, 256, 0, c->stream>>>(d_in, 3, w, h, n, xcol, (float4*)c->xf4.p);
+        const long long nseg = (long long)n * h * ((w + 27) / 28);
+        const int blocks = (int)std::min<long long>((nseg + 7) / 8, (long long)c->num_sms * 16);
+        if (u8) pack_input_kernel<true><<<blocks, 256, 0, c->stream>>>(d_in, in_ch, w, h, n, (__nv_bfloat16*)xcol, (float4*)c->xf4.p);
+        else    pack_input_kernel<false><<<blocks, 256, 0, c->stream>>>(d_in, 3, w, h, n, (__nv_bfloat16*)xcol, (float4*)c->xf4.p);
         CUDA_TRY(cudaGetLastError());
         c->last_launches++;
     }
@@ -682,45 +731,48 @@ static int forward_device(rsr_ctx* c, const void* d_in, bool u8, int in_ch, int 
     if (c->stop_after == 0) return 0;
 
     ConvParams p{};
-    p.W = w; p.H = h; p.NIMG = n; p.row_begin = 0; p.row_end = h; p.factor = c->factor; p.fault = c->fault;
+    p.W = w; p.H = h; p.NIMG = n; p.row_begin = 0; p.row_end = h; p.fault = c->fault;
     p.n_cb = 1;
     p.xf4 = (const float4*)c->xf4.p;
     const EpiGroup none{EPI_NONE, 0, nullptr, nullptr, 0, 0};
-    auto in_map = [&](CUtensorMap* m, const void* base, int boxw) { return make_map_act(c, m, base, 64, w, h, n, boxw); };
+    auto set_groups = [&](std::initializer_list<EpiGroup> g) {
+        int i = 0;
+        for (const EpiGroup& e : g) p.grp[i++] = e;
+        for (; i < 8; ++i) p.grp[i] = none;
+    };
+    auto in_map = [&](CUtensorMap* m, const void* base, int boxw) { return make_map_act(c, m, base, 128, w, h, n, boxw); };
     auto pair = [&](int kindex) { return (c->pair_mask >> kindex & 1) != 0; };
     auto part_map = [&](CUtensorMap* m, const void* base, int boxw) { return make_map_part(c, m, base, w, h, n, boxw); };
 
     // conv0: xcol -> f = BeLU(conv0(x) + f_bias)                       network.rs:33-35
-    if (int rc = make_map_act(c, &p.tmA, xcol, 32, w, h, n, Cfg0::BOXW)) return rc;
-    auto fold = [&](int kindex) { return (c->fold_mask >> kindex & 1) != 0; };
-    if (int rc = make_map_w(c, &p.tmB, fold(1) ? c->w0f : c->w0, 32, 5 * 32, pair(1) ? 16 : Cfg0::TPS * 32)) return rc;
+    if (int rc = make_map_act(c, &p.tmA, xcol, 64, w, h, n, N::C0::BOXW)) return rc;
+    if (int rc = make_map_w(c, &p.tmB, c->w0, 64, 5 * 32, N::C0::TPS * 32)) return rc;
     if (int rc = in_map(&p.tmOut[0], f_act, 32)) return rc;
-    p.grp[0] = EpiGroup{EPI_ACT, 0, f_bias, f_slope, 0, 0};
-    p.grp[1] = none; p.grp[2] = none;
-    if (int rc = launch_conv<Cfg0>(c, p, 1)) return rc;
+    set_groups({EpiGroup{EPI_ACT, 0, f_bias, f_slope, 0, 0}});
+    if (int rc = launch_conv<typename N::C0>(c, p, 1)) return rc;
     CUDA_TRY(cudaEventRecord(c->ev[2], c->stream));
     if (c->stop_after == 1) return 0;
 
     // f -> l1 = BeLU(conv1(f) + l1_bias); P2 = conv2(f); P3 = conv3(f)  network.rs:60-62,50,54
-    if (int rc = in_map(&p.tmA, f_act, Cfg1::BOXW)) return rc;
-    if (int rc = make_map_w(c, &p.tmB, c->w1, 64, 25 * 96, pair(2) ? 48 : Cfg1::TPS * 96)) return rc;
+    if (int rc = in_map(&p.tmA, f_act, N::C1::BOXW)) return rc;
+    if (int rc = make_map_w(c, &p.tmB, c->w1, 128, 25 * 96, pair(2) ? 48 : N::C1::TPS * 96)) return rc;
     if (int rc = in_map(&p.tmOut[0], l1_act, 32)) return rc;
     if (int rc = part_map(&p.tmOut[1], P2, 32)) return rc;
     if (int rc = part_map(&p.tmOut[2], P3, 32)) return rc;
-    p.grp[0] = EpiGroup{EPI_ACT, 0, l1_bias, l1_slope, 0, 0};
-    p.grp[1] = EpiGroup{EPI_RAW, 0, nullptr, nullptr, 0, 0};
-    p.grp[2] = EpiGroup{EPI_RAW, 0, nullptr, nullptr, 0, 0};
-    if (int rc = launch_conv<Cfg1>(c, p, 2)) return rc;
+    set_groups({EpiGroup{EPI_ACT, 0, l1_bias, l1_slope, 0, 0}, EpiGroup{EPI_RAW, 0, nullptr, nullptr, 0, 0},
+                EpiGroup{EPI_RAW, 0, nullptr, nullptr, 0, 0}});
+    if (pair(2)) { if (int rc = launch_conv_pair<typename N::P1>(c, p, 2)) return rc; }
+    else         { if (int rc = launch_conv<typename N::C1>(c, p, 2)) return rc; }
     CUDA_TRY(cudaEventRecord(c->ev[3], c->stream));
     if (c->stop_after == 2) return 0;
 
-    if (c->fused_mid) {
+    if constexpr (NGE == 1) {
+    if (fused) {
         // l1, P2, P3 -> l3, E in one launch; l2 lives in shared memory only (conv_fused.cuh)   :65-70,51-52,55-56
         // l3 goes to the buffer of the (dead) f; E to a buffer of its own: the fused launch reads P2 rows of
         // neighbouring work items (l2 halo rows), so E may not overwrite P2 here.
-        if (int rc = ensure(c->partC, npx * 128)) return rc;
         l3_act = f_act;
-        E = (float*)c->partC.p;
+        E[0] = (float*)c->partC.p;
         FusedParams q{};
         q.W = w; q.H = h; q.NIMG = n; q.fault = c->fault;
         q.n_strips = (w + FusedCfg::STRIP - 1) / FusedCfg::STRIP;
@@ -729,16 +781,16 @@ static int forward_device(rsr_ctx* c, const void* d_in, bool u8, int in_ch, int 
         // the fused launch runs on CTA pairs when launch index 3 is in the pair mask (half-tap weight boxes);
         // the debug hooks exist in the single-CTA debug instantiation only
         const bool fpair = pair(3) && (c->fused_dbg & 7) == 0;
-        if (int rc = make_map_w(c, &q.tmB1, c->w2, 64, 9 * 96, fpair ? 48 : 96)) return rc;
-        if (int rc = make_map_w(c, &q.tmB2, c->w3, 64, 9 * 64, fpair ? 32 : 64)) return rc;
+        if (int rc = make_map_w(c, &q.tmB1, c->w2, 128, 9 * 96, fpair ? 48 : 96)) return rc;
+        if (int rc = make_map_w(c, &q.tmB2, c->w3, 128, 9 * 64, fpair ? 32 : 64)) return rc;
         if (int rc = part_map(&q.tmP2, P2, 128)) return rc;
         if (int rc = part_map(&q.tmP3, P3, 128)) return rc;
         if (int rc = in_map(&q.tmL3[0], l3_act, 32)) return rc;
         if (int rc = in_map(&q.tmL3[1], l3_act, 31)) return rc;
         if (int rc = in_map(&q.tmL3[2], l3_act, 29)) return rc;
-        if (int rc = part_map(&q.tmE[0], E, 32)) return rc;
-        if (int rc = part_map(&q.tmE[1], E, 31)) return rc;
-        if (int rc = part_map(&q.tmE[2], E, 29)) return rc;
+        if (int rc = part_map(&q.tmE[0], E[0], 32)) return rc;
+        if (int rc = part_map(&q.tmE[1], E[0], 31)) return rc;
+        if (int rc = part_map(&q.tmE[2], E[0], 29)) return rc;
         q.g_l2 = EpiGroup{EPI_ACT, 1, l2_bias, l2_slope, 0, 0};
         q.g_l3 = EpiGroup{EPI_ACT, 1, l3_bias, l3_slope, 0, 0};
         q.dbg_flags = c->fused_dbg & 1;
@@ -760,18 +812,18 @@ static int forward_device(rsr_ctx* c, const void* d_in, bool u8, int in_ch, int 
             cudaLaunchConfig_t cfg{};
             cfg.gridDim = dim3(2 * ncl);
             cfg.blockDim = dim3(FusedCfg::NTHREADS);
-            cfg.dynamicSmemBytes = FusedCfgT<true>::SMEM_BYTES;
+            cfg.dynamicSmemBytes = FusedCfgT<true, PREC>::SMEM_BYTES;
             cfg.stream = c->stream;
             cudaLaunchAttribute at[1];
             at[0].id = cudaLaunchAttributeClusterDimension;
             at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
             cfg.attrs = at;
             cfg.numAttrs = 1;
-            CUDA_TRY(cudaLaunchKernelEx(&cfg, conv_fused_mid_kernel<false, true>, q));
+            CUDA_TRY(cudaLaunchKernelEx(&cfg, conv_fused_mid_kernel<false, true, PREC>, q));
         } else {
             const int grid = (int)std::min<long long>(q.total_rowtiles, c->num_sms);
-            if (c->fused_dbg & 7) conv_fused_mid_kernel<true, false><<<grid, FusedCfg::NTHREADS, FusedCfg::SMEM_BYTES, c->stream>>>(q);
-            else conv_fused_mid_kernel<false, false><<<grid, FusedCfg::NTHREADS, FusedCfg::SMEM_BYTES, c->stream>>>(q);
+            if (c->fused_dbg & 7) conv_fused_mid_kernel<true, false, PREC><<<grid, FusedCfg::NTHREADS, FusedCfgT<false, PREC>::SMEM_BYTES, c->stream>>>(q);
+            else conv_fused_mid_kernel<false, false, PREC><<<grid, FusedCfg::NTHREADS, FusedCfgT<false, PREC>::SMEM_BYTES, c->stream>>>(q);
         }
         CUDA_TRY(cudaGetLastError());
         c->last_launches++;
@@ -779,101 +831,133 @@ static int forward_device(rsr_ctx* c, const void* d_in, bool u8, int in_ch, int 
         CUDA_TRY(cudaEventRecord(c->ev[4], c->stream));
         CUDA_TRY(cudaEventRecord(c->ev[5], c->stream));
         if (c->stop_after == 3 || c->stop_after == 4) return 0;
-    } else {
+    }
+    }
+    if (!fused) {
         // l1 -> l2 = BeLU(P2 + conv5(l1) + l2_bias); P3 += conv6(l1); E = conv7(l1)   :65-67,51,55
-        // (l2 overwrites f, E overwrites P2: both are dead; a thread block only overwrites pixels whose
+        // (l2 overwrites f, E[0] overwrites P2: both are dead; a thread block only overwrites pixels whose
         //  partial tile it has already consumed — see DESIGN.md "aliasing")
-        if (int rc = in_map(&p.tmA, l1_act, Cfg2::BOXW)) return rc;
-        if (int rc = make_map_w(c, &p.tmB, c->w2, 64, 9 * 96, pair(3) ? 48 : Cfg2::TPS * 96)) return rc;
+        if (int rc = in_map(&p.tmA, l1_act, N::C2::BOXW)) return rc;
+        if (int rc = make_map_w(c, &p.tmB, c->w2, 128, 9 * N::C2::NCOL, N::C2::TPS * N::C2::NCOL)) return rc;
         if (int rc = part_map(&p.tmPin[0], P2, 128)) return rc;
         if (int rc = part_map(&p.tmPin[1], P3, 128)) return rc;
         if (int rc = in_map(&p.tmOut[0], l2_act, 32)) return rc;
         if (int rc = part_map(&p.tmOut[1], P3, 32)) return rc;
-        if (int rc = part_map(&p.tmOut[2], E, 32)) return rc;
-        p.grp[0] = EpiGroup{EPI_ACT, 1, l2_bias, l2_slope, 0, 0};
-        p.grp[1] = EpiGroup{EPI_RAW, 1, nullptr, nullptr, 0, 0};
-        p.grp[2] = EpiGroup{EPI_RAW, 0, nullptr, nullptr, 0, 0};
-        if (int rc = launch_conv<Cfg2>(c, p, 3)) return rc;
+        for (int k = 0; k < NGE; ++k)
+            if (int rc = part_map(&p.tmOut[2 + k], E[k], 32)) return rc;
+        set_groups({EpiGroup{EPI_ACT, 1, l2_bias, l2_slope, 0, 0}, EpiGroup{EPI_RAW, 1, nullptr, nullptr, 0, 0},
+                    EpiGroup{EPI_RAW, 0, nullptr, nullptr, 0, 0}, NGE == 2 ? EpiGroup{EPI_RAW, 0, nullptr, nullptr, 0, 0} : none});
+        if (int rc = launch_conv<typename N::C2>(c, p, 3)) return rc;
         CUDA_TRY(cudaEventRecord(c->ev[4], c->stream));
         if (c->stop_after == 3) return 0;
 
         // l2 -> l3 = BeLU(P3 + conv8(l2) + l3_bias); E += conv9(l2)                  :69-70,52,56
-        if (int rc = in_map(&p.tmA, l2_act, Cfg3::BOXW)) return rc;
-        if (int rc = make_map_w(c, &p.tmB, c->w3, 64, 9 * 64, pair(4) ? 32 : Cfg3::TPS * 64)) return rc;
+        if (int rc = in_map(&p.tmA, l2_act, N::C3::BOXW)) return rc;
+        if (int rc = make_map_w(c, &p.tmB, c->w3, 128, 9 * N::C3::NCOL, N::C3::TPS * N::C3::NCOL)) return rc;
         if (int rc = part_map(&p.tmPin[0], P3, 128)) return rc;
-        if (int rc = part_map(&p.tmPin[1], E, 128)) return rc;
         if (int rc = in_map(&p.tmOut[0], l3_act, 32)) return rc;
-        if (int rc = part_map(&p.tmOut[1], E, 32)) return rc;
-        p.grp[0] = EpiGroup{EPI_ACT, 1, l3_bias, l3_slope, 0, 0};
-        p.grp[1] = EpiGroup{EPI_RAW, 1, nullptr, nullptr, 0, 0};
-        p.grp[2] = none;
-        if (int rc = launch_conv<Cfg3>(c, p, 4)) return rc;
+        for (int k = 0; k < NGE; ++k) {
+            if (int rc = part_map(&p.tmPin[1 + k], E[k], 128)) return rc;
+            if (int rc = part_map(&p.tmOut[1 + k], E[k], 32)) return rc;
+        }
+        set_groups({EpiGroup{EPI_ACT, 1, l3_bias, l3_slope, 0, 0}, EpiGroup{EPI_RAW, 1, nullptr, nullptr, 0, 0},
+                    NGE == 2 ? EpiGroup{EPI_RAW, 1, nullptr, nullptr, 0, 0} : none});
+        if (int rc = launch_conv<typename N::C3>(c, p, 4)) return rc;
         CUDA_TRY(cudaEventRecord(c->ev[5], c->stream));
         if (c->stop_after == 4) return 0;
-
     }
 
     // l3 -> output = Expand(E + conv10(l3) + expand_bias) + LinearInterp(x)          :72,38-39,27
-    if (int rc = in_map(&p.tmA, l3_act, Cfg4::BOXW)) return rc;
-    if (int rc = make_map_w(c, &p.tmB, fold(5) ? c->w4f : c->w4, 64, 9 * 32, pair(5) ? 16 : Cfg4::TPS * 32)) return rc;
-    if (int rc = part_map(&p.tmPin[0], E, 128)) return rc;
-    p.grp[0] = EpiGroup{EPI_SHUFFLE, 1, e_bias, nullptr, 0, 0};
-    p.grp[1] = none; p.grp[2] = none;
-    p.out_f32 = d_out_f32;
-    p.out_u8 = d_out_u8;
-    p.out_vec_ok = (w % 4 == 0) && ((reinterpret_cast<uintptr_t>(d_out_f32) & 15) == 0);
-    if (int rc = launch_conv<Cfg4>(c, p, 5)) return rc;
+    if (int rc = in_map(&p.tmA, l3_act, N::C4::BOXW)) return rc;
+    if (int rc = make_map_w(c, &p.tmB, c->w4, 128, 9 * N::C4::NCOL, N::C4::TPS * N::C4::NCOL)) return rc;
+    for (int k = 0; k < NGE; ++k)
+        if (int rc = part_map(&p.tmPin[k], E[k], 128)) return rc;
+    set_groups({EpiGroup{EPI_SHUFFLE, 1, e_bias, nullptr, 0, 0}, NGE == 2 ? EpiGroup{EPI_SHUFFLE, 1, e_bias + 32, nullptr, 0, 0} : none});
+    p.row_begin = o.top; p.row_end = h - o.bottom;      // band mode: the halo rows' outputs are not produced
+    p.out_row0 = o.top; p.out_rows = h - o.top - o.bottom;
+    p.out_f32 = o.f32;
+    p.out_u8 = o.u8;
+    p.out_u8_ch = o.u8_ch;
+    p.out_vec_ok = ((w * F) % 4 == 0) && ((reinterpret_cast<uintptr_t>(o.f32 ? (void*)o.f32 : (void*)o.u8) & 15) == 0);
+    if (int rc = launch_conv<typename N::C4>(c, p, 5)) return rc;
     CUDA_TRY(cudaEventRecord(c->ev[6], c->stream));
     c->timed = true;
     return 0;
 }
 
+struct Forward {
+    rsr_ctx* c; const void* d_in; bool u8; int in_ch, n, w, h; const OutSpec& o;
+    template <int PREC, int F> int operator()() const { return forward_impl<PREC, F>(c, d_in, u8, in_ch, n, w, h, o); }
+};
+static int forward_device(rsr_ctx* c, const void* d_in, bool u8, int in_ch, int n, int w, int h, const OutSpec& o) {
+    if (!c) return fail(RSR_E_BAD_ARG, "ctx is null");
+    if (!d_in || (!o.f32 && !o.u8)) return fail(RSR_E_BAD_ARG, "null buffer");
+    if (o.f32 && o.u8) return fail(RSR_E_BAD_ARG, "exactly one of the f32 / u8 outputs may be requested");
+    if (n < 1 || w < 1 || h < 1) return fail(RSR_E_BAD_ARG, "bad dimensions n=%d w=%d h=%d", n, w, h);
+    if (u8 && in_ch != 3 && in_ch != 4) return fail(RSR_E_BAD_ARG, "in_channels must be 3 or 4 (got %d)", in_ch);
+    if (o.u8 && o.u8_ch != 3 && o.u8_ch != 4) return fail(RSR_E_BAD_ARG, "out_channels must be 3 or 4 (got %d)", o.u8_ch);
+    if (o.top < 0 || o.bottom < 0 || h - o.top - o.bottom < 1 || ((o.top || o.bottom) && n != 1))
+        return fail(RSR_E_BAD_ARG, "bad band: rows_in=%d top_halo=%d bottom_halo=%d", h, o.top, o.bottom);
+    CUDA_TRY(cudaSetDevice(c->device));
+    return dispatch(c->prec, c->factor, Forward{c, d_in, u8, in_ch, n, w, h, o});
+}
+
+static OutSpec out_spec(float* f32, uint8_t* u8, int u8_ch, int top = 0, int bottom = 0) {
+    OutSpec o;
+    o.f32 = f32; o.u8 = u8; o.u8_ch = u8_ch; o.top = top; o.bottom = bottom;
+    return o;
+}
 extern "C" int rsr_upscale_device_f32(rsr_ctx* c, const float* d_in, int n, int w, int h, float* d_out_f32,
                                       uint8_t* d_out_rgba) {
-    return forward_device(c, d_in, false, 3, n, w, h, d_out_f32, d_out_rgba);
+    return forward_device(c, d_in, false, 3, n, w, h, out_spec(d_out_f32, d_out_rgba, 4));
 }
 extern "C" int rsr_upscale_device_u8(rsr_ctx* c, const uint8_t* d_in, int n, int w, int h, int in_channels,
                                      float* d_out_f32, uint8_t* d_out_rgba) {
-    return forward_device(c, d_in, true, in_channels, n, w, h, d_out_f32, d_out_rgba);
+    return forward_device(c, d_in, true, in_channels, n, w, h, out_spec(d_out_f32, d_out_rgba, 4));
+}
+extern "C" int rsr_upscale_device_u8_rgb(rsr_ctx* c, const uint8_t* d_in, int n, int w, int h, int in_channels, uint8_t* d_out_rgb) {
+    return forward_device(c, d_in, true, in_channels, n, w, h, out_spec(nullptr, d_out_rgb, 3));
+}
+extern "C" int rsr_upscale_band_device_f32(rsr_ctx* c, const float* d_in_rows, int w, int rows_in, int top_halo, int bottom_halo,
+                                           float* d_out_rows) {
+    return forward_device(c, d_in_rows, false, 3, 1, w, rows_in, out_spec(d_out_rows, nullptr, 4, top_halo, bottom_halo));
+}
+extern "C" int rsr_upscale_band_device_u8(rsr_ctx* c, const uint8_t* d_in_rows, int w, int rows_in, int top_halo, int bottom_halo,
+                                          int in_channels, uint8_t* d_out_rows, int out_channels) {
+    return forward_device(c, d_in_rows, true, in_channels, 1, w, rows_in, out_spec(nullptr, d_out_rows, out_channels, top_halo, bottom_halo));
 }
 
-// Host-buffer entry points: H2D, forward, D2H on the context's stream, then synchronise.
-static int upscale_host(rsr_ctx* c, const void* in, bool u8, int in_ch, int n, int w, int h, float* out_f32,
-                        uint8_t* out_u8, int out_row_begin, int out_rows) {
+// Host-buffer entry points: H2D, forward, D2H on the context's stream, then synchronise.  out_ch: 0 = f32 RGB, 3 / 4 = u8.
+static int upscale_host(rsr_ctx* c, const void* in, bool u8, int in_ch, int n, int w, int h, void* out, int out_ch,
+                        int top = 0, int bottom = 0) {
     if (!c) return fail(RSR_E_BAD_ARG, "ctx is null");
-    if (!in || (!out_f32 && !out_u8)) return fail(RSR_E_BAD_ARG, "null buffer");
+    if (!in || !out) return fail(RSR_E_BAD_ARG, "null buffer");
     if (n < 1 || w < 1 || h < 1) return fail(RSR_E_BAD_ARG, "bad dimensions n=%d w=%d h=%d", n, w, h);
     if (u8 && in_ch != 3 && in_ch != 4) return fail(RSR_E_BAD_ARG, "in_channels must be 3 or 4 (got %d)", in_ch);
+    if (top < 0 || bottom < 0 || h - top - bottom < 1)
+        return fail(RSR_E_BAD_ARG, "bad band: rows_in=%d top_halo=%d bottom_halo=%d", h, top, bottom);
     CUDA_TRY(cudaSetDevice(c->device));
     const int F = c->factor;
     const size_t npx = (size_t)n * w * h;
     const size_t in_bytes = u8 ? npx * in_ch : npx * 3 * sizeof(float);
     if (int rc = ensure(c->in_stage, in_bytes)) return rc;
     CUDA_TRY(cudaMemcpyAsync(c->in_stage.p, in, in_bytes, cudaMemcpyHostToDevice, c->stream));
-    const size_t opx = npx * F * F;
-    float* d_f32 = nullptr;
-    uint8_t* d_u8 = nullptr;
-    if (out_f32) { if (int rc = ensure(c->out_f32, opx * 3 * sizeof(float))) return rc; d_f32 = (float*)c->out_f32.p; }
-    if (out_u8) { if (int rc = ensure(c->out_u8, opx * 4)) return rc; d_u8 = (uint8_t*)c->out_u8.p; }
-    if (int rc = forward_device(c, c->in_stage.p, u8, in_ch, n, w, h, d_f32, d_u8)) return rc;
-    if (int rc = rsr_synchronize(c)) return rc;   // surfaces a kernel fault (with its fault word) before the copies
-    // band mode copies a row window of a single image; otherwise everything
-    const size_t orow_px = (size_t)w * F;
-    if (out_f32)
-        CUDA_TRY(cudaMemcpyAsync(out_f32, d_f32 + (size_t)out_row_begin * orow_px * 3,
-                                 (out_rows < 0 ? opx : (size_t)out_rows * orow_px) * 3 * sizeof(float),
-                                 cudaMemcpyDeviceToHost, c->stream));
-    if (out_u8)
-        CUDA_TRY(cudaMemcpyAsync(out_u8, d_u8 + (size_t)out_row_begin * orow_px * 4,
-                                 (out_rows < 0 ? opx : (size_t)out_rows * orow_px) * 4, cudaMemcpyDeviceToHost,
-                                 c->stream));
+    const size_t opx = (size_t)n * w * (h - top - bottom) * F * F;
+    const size_t out_bytes = opx * (out_ch ? (size_t)out_ch : 3 * sizeof(float));
+    DevBuf& ob = out_ch ? c->out_u8 : c->out_f32;
+    if (int rc = ensure(ob, out_bytes)) return rc;
+    if (int rc = forward_device(c, c->in_stage.p, u8, in_ch, n, w, h,
+                                out_spec(out_ch ? nullptr : (float*)ob.p, out_ch ? (uint8_t*)ob.p : nullptr, out_ch ? out_ch : 4, top, bottom)))
+        return rc;
+    if (int rc = rsr_synchronize(c)) return rc;   // surfaces a kernel fault (with its fault word) before the copy
+    CUDA_TRY(cudaMemcpyAsync(out, ob.p, out_bytes, cudaMemcpyDeviceToHost, c->stream));
     return rsr_synchronize(c);
 }
 
 // ---- pipelined host API ---------------------------------------------------------------------
-static int submit_host(rsr_ctx* c, const void* in, bool u8, int in_ch, int w, int h, float* out_f32, uint8_t* out_u8) {
+static int submit_host(rsr_ctx* c, const void* in, bool u8, int in_ch, int w, int h, void* out, int out_ch) {
     if (!c) return fail(RSR_E_BAD_ARG, "ctx is null");
-    if (!in || (!out_f32 && !out_u8)) return fail(RSR_E_BAD_ARG, "null buffer");
+    if (!in || !out) return fail(RSR_E_BAD_ARG, "null buffer");
     if (w < 1 || h < 1) return fail(RSR_E_BAD_ARG, "bad dimensions w=%d h=%d", w, h);
     if (u8 && in_ch != 3 && in_ch != 4) return fail(RSR_E_BAD_ARG, "in_channels must be 3 or 4 (got %d)", in_ch);
     CUDA_TRY(cudaSetDevice(c->device));
@@ -882,7 +966,7 @@ static int submit_host(rsr_ctx* c, const void* in, bool u8, int in_ch, int w, in
     const int F = c->factor;
     const size_t npx = (size_t)w * h, opx = npx * F * F;
     const size_t in_bytes = u8 ? npx * in_ch : npx * 3 * sizeof(float);
-    const size_t out_bytes = out_f32 ? opx * 3 * sizeof(float) : opx * 4;
+    const size_t out_bytes = opx * (out_ch ? (size_t)out_ch : 3 * sizeof(float));
     if (in_bytes > sl.in.cap || out_bytes > sl.out.cap) {
         // growing a slot re-allocates: drain whatever still uses it first
         if (sl.used) CUDA_TRY(cudaEventSynchronize(sl.ev_out));
@@ -896,21 +980,25 @@ static int submit_host(rsr_ctx* c, const void* in, bool u8, int in_ch, int w, in
     CUDA_TRY(cudaStreamWaitEvent(c->stream, sl.ev_in, 0));
     // the forward pass may overwrite the slot's output only after its previous D2H has finished
     if (sl.used) CUDA_TRY(cudaStreamWaitEvent(c->stream, sl.ev_out, 0));
-    if (int rc = forward_device(c, sl.in.p, u8, in_ch, 1, w, h, out_f32 ? (float*)sl.out.p : nullptr,
-                                out_u8 ? (uint8_t*)sl.out.p : nullptr)) return rc;
+    if (int rc = forward_device(c, sl.in.p, u8, in_ch, 1, w, h,
+                                out_spec(out_ch ? nullptr : (float*)sl.out.p, out_ch ? (uint8_t*)sl.out.p : nullptr, out_ch ? out_ch : 4)))
+        return rc;
     CUDA_TRY(cudaEventRecord(sl.ev_done, c->stream));
     CUDA_TRY(cudaStreamWaitEvent(c->s_d2h, sl.ev_done, 0));
-    CUDA_TRY(cudaMemcpyAsync(out_f32 ? (void*)out_f32 : (void*)out_u8, sl.out.p, out_bytes, cudaMemcpyDeviceToHost, c->s_d2h));
+    CUDA_TRY(cudaMemcpyAsync(out, sl.out.p, out_bytes, cudaMemcpyDeviceToHost, c->s_d2h));
     CUDA_TRY(cudaEventRecord(sl.ev_out, c->s_d2h));
     sl.used = true;
     c->next_ticket++;
     return (int)(ticket & 0x3fffffff);
 }
 extern "C" int rsr_submit_u8(rsr_ctx* c, const uint8_t* in, int w, int h, int in_channels, uint8_t* out_rgba) {
-    return submit_host(c, in, true, in_channels, w, h, nullptr, out_rgba);
+    return submit_host(c, in, true, in_channels, w, h, out_rgba, 4);
+}
+extern "C" int rsr_submit_u8_rgb(rsr_ctx* c, const uint8_t* in, int w, int h, int in_channels, uint8_t* out_rgb) {
+    return submit_host(c, in, true, in_channels, w, h, out_rgb, 3);
 }
 extern "C" int rsr_submit_f32(rsr_ctx* c, const float* in, int w, int h, float* out) {
-    return submit_host(c, in, false, 3, w, h, out, nullptr);
+    return submit_host(c, in, false, 3, w, h, out, 0);
 }
 extern "C" int rsr_wait(rsr_ctx* c, int ticket) {
     if (!c) return fail(RSR_E_BAD_ARG, "ctx is null");
@@ -919,7 +1007,7 @@ extern "C" int rsr_wait(rsr_ctx* c, int ticket) {
     const long long t = newest - ((newest - (long long)ticket) & 0x3fffffff);
     if (ticket < 0 || ticket > 0x3fffffff || t < 0) return fail(RSR_E_BAD_ARG, "unknown ticket %d (%lld issued so far)", ticket, newest + 1);
     CUDA_TRY(cudaSetDevice(c->device));
-    // Frame t used slot t % NSLOT.  If the slot has been re-used since, its event belongs to a LATER frame of the same slot;
+    // Frame t used slot t % 3.  If the slot has been re-used since, its event belongs to a LATER frame of the same slot;
     // device->host copies are ordered on one stream, so that event completing implies frame t's copy has completed too
     // (conservative, never early).
     cudaError_t e = cudaEventSynchronize(c->slot[t % 3].ev_out);
@@ -936,34 +1024,28 @@ extern "C" int rsr_wait_all(rsr_ctx* c) {
 }
 
 extern "C" int rsr_upscale_f32(rsr_ctx* c, const float* in, int w, int h, float* out) {
-    return upscale_host(c, in, false, 3, 1, w, h, out, nullptr, 0, -1);
+    return upscale_host(c, in, false, 3, 1, w, h, out, 0);
 }
 extern "C" int rsr_upscale_u8(rsr_ctx* c, const uint8_t* in, int w, int h, int in_channels, uint8_t* out_rgba) {
-    return upscale_host(c, in, true, in_channels, 1, w, h, nullptr, out_rgba, 0, -1);
+    return upscale_host(c, in, true, in_channels, 1, w, h, out_rgba, 4);
+}
+extern "C" int rsr_upscale_u8_rgb(rsr_ctx* c, const uint8_t* in, int w, int h, int in_channels, uint8_t* out_rgb) {
+    return upscale_host(c, in, true, in_channels, 1, w, h, out_rgb, 3);
 }
 extern "C" int rsr_upscale_batch_f32(rsr_ctx* c, const float* in, int n, int w, int h, float* out) {
-    return upscale_host(c, in, false, 3, n, w, h, out, nullptr, 0, -1);
+    return upscale_host(c, in, false, 3, n, w, h, out, 0);
 }
 extern "C" int rsr_upscale_batch_u8(rsr_ctx* c, const uint8_t* in, int n, int w, int h, int in_channels,
                                     uint8_t* out_rgba) {
-    return upscale_host(c, in, true, in_channels, n, w, h, nullptr, out_rgba, 0, -1);
+    return upscale_host(c, in, true, in_channels, n, w, h, out_rgba, 4);
 }
 extern "C" int rsr_upscale_band_f32(rsr_ctx* c, const float* in_rows, int w, int rows_in, int top_halo,
                                     int bottom_halo, float* out_rows) {
-    if (top_halo < 0 || bottom_halo < 0 || rows_in - top_halo - bottom_halo < 1)
-        return fail(RSR_E_BAD_ARG, "bad band: rows_in=%d top_halo=%d bottom_halo=%d", rows_in, top_halo, bottom_halo);
-    const int F = c ? c->factor : 3;
-    return upscale_host(c, in_rows, false, 3, 1, w, rows_in, out_rows, nullptr, top_halo * F,
-                        (rows_in - top_halo - bottom_halo) * F);
+    return upscale_host(c, in_rows, false, 3, 1, w, rows_in, out_rows, 0, top_halo, bottom_halo);
 }
-
 extern "C" int rsr_upscale_band_u8(rsr_ctx* c, const uint8_t* in_rows, int w, int rows_in, int top_halo, int bottom_halo,
                                    int in_channels, uint8_t* out_rows_rgba) {
-    if (top_halo < 0 || bottom_halo < 0 || rows_in - top_halo - bottom_halo < 1)
-        return fail(RSR_E_BAD_ARG, "bad band: rows_in=%d top_halo=%d bottom_halo=%d", rows_in, top_halo, bottom_halo);
-    const int F = c ? c->factor : 3;
-    return upscale_host(c, in_rows, true, in_channels, 1, w, rows_in, nullptr, out_rows_rgba, top_halo * F,
-                        (rows_in - top_halo - bottom_halo) * F);
+    return upscale_host(c, in_rows, true, in_channels, 1, w, rows_in, out_rows_rgba, 4, top_halo, bottom_halo);
 }
 
 extern "C" int rsr_last_kernel_times(rsr_ctx* c, float* ms, int cap) {
@@ -978,15 +1060,15 @@ extern "C" int rsr_last_launch_count(rsr_ctx* c) { return c ? c->last_launches :
 extern "C" const char* rsr_plan(rsr_ctx* c) {
     static thread_local std::string s;
     if (!c) return "";
-    s = c->fused_mid ? "5 launches: pack, conv0, conv1|2|3, conv5|6|7+conv8|9 fused, conv10+expand" 
-                     : "6 launches: pack, conv0, conv1|2|3, conv5|6|7, conv8|9, conv10+expand";
+    const bool fused = c->plan == 1 || (c->plan == 0 && (c->last_launches == 0 || c->fused_last));
+    s = fused ? "5 launches: pack, conv0, conv1|2|3, conv5|6|7+conv8|9 fused, conv10+expand"
+              : "6 launches: pack, conv0, conv1|2|3, conv5|6|7, conv8|9, conv10+expand";
+    if (c->plan == 0) s += " (middle levels by image width)";
+    s += c->prec == PREC_F16MX ? "; operands fp16 + mxfp8 (2 MMAs per K chunk)" : "; operands bf16x3 (3 MMAs per K chunk)";
     s += "; CTA pairs (cta_group::2):";
     bool any = false;
-    for (int k = 1; k < K_COUNT; ++k)
-        if ((c->pair_mask >> k & 1) && !(c->fused_mid && k == K_L2)) {   // (the fused plan has no launch of its own for conv8|9)
-            s += std::string(any ? "," : " ") + (c->fused_mid && k == K_L1 ? "conv5|6|7+conv8|9 fused" : kKernelNames[k]);
-            any = true;
-        }
+    if (c->pair_mask & 4) { s += " conv1|2|3"; any = true; }
+    if ((c->pair_mask & 8) && fused) { s += std::string(any ? "," : " ") + "conv5|6|7+conv8|9 fused"; any = true; }
     if (!any) s += " none";
     return s.c_str();
 }
@@ -996,6 +1078,19 @@ extern "C" int rsr_debug_stop_after(rsr_ctx* c, int k) {
     if (!c) return fail(RSR_E_BAD_ARG, "ctx is null");
     c->stop_after = k;
     return 0;
+}
+// one stored activation row (128 B, conv_strip.cuh storage formats) -> 32 floats
+static void unpack_act_row(const uint8_t* row, int prec, float* out) {
+    if (prec == PREC_F16MX) {
+        const __half* h = reinterpret_cast<const __half*>(row);
+        for (int ch = 0; ch < 32; ++ch) {
+            const __nv_fp8_storage_t lo = row[64 + (ch >> 4) * 32 + (ch & 15)];
+            out[ch] = __half2float(h[ch]) + __half2float(__half(__nv_cvt_fp8_to_halfraw(lo, __NV_E4M3))) / F16MX_SCALE;
+        }
+    } else {
+        const __nv_bfloat16* q = reinterpret_cast<const __nv_bfloat16*>(row);
+        for (int ch = 0; ch < 32; ++ch) out[ch] = __bfloat162float(q[ch]) + __bfloat162float(q[32 + ch]);
+    }
 }
 extern "C" int rsr_debug_read_node(rsr_ctx* c, int which, float* out, size_t npx) {
     if (!c || !out) return fail(RSR_E_BAD_ARG, "null argument");
@@ -1007,11 +1102,9 @@ extern "C" int rsr_debug_read_node(rsr_ctx* c, int which, float* out, size_t npx
         CUDA_TRY(cudaMemcpy(out, b->p, npx * 128, cudaMemcpyDeviceToHost));
         return 0;
     }
-    std::vector<__nv_bfloat16> tmp(npx * 64);
+    std::vector<uint8_t> tmp(npx * 128);
     CUDA_TRY(cudaMemcpy(tmp.data(), b->p, npx * 128, cudaMemcpyDeviceToHost));
-    for (size_t i = 0; i < npx; ++i)
-        for (int ch = 0; ch < 32; ++ch)
-            out[i * 32 + ch] = __bfloat162float(tmp[i * 64 + ch]) + __bfloat162float(tmp[i * 64 + 32 + ch]);
+    for (size_t i = 0; i < npx; ++i) unpack_act_row(&tmp[i * 128], c->prec, out + i * 32);
     return 0;
 }
 
@@ -1049,6 +1142,42 @@ extern "C" int rsr_debug_read_profile(rsr_ctx* c, int kindex, long long* out, in
     const int rows = c->prof_grid[kindex] < cap_rows ? c->prof_grid[kindex] : cap_rows;
     CUDA_TRY(cudaMemcpy(out, c->prof + (size_t)kindex * 256 * 16, sizeof(long long) * rows * 16, cudaMemcpyDeviceToHost));
     return rows;
+}
+
+// ------------------------------------------------------------------------------- .rsr codec
+// bytevec `<Vec<f32>>::encode::<u32>` / `decode::<u32>` (call sites main.rs:138-152,194,213):
+// u32 LE N | N x u32 LE element sizes (all 4) | N x f32 LE.  Pure host code, no context.
+extern "C" size_t rsr_rsr_encoded_size(size_t n_params) { return 4 + 8 * n_params; }
+extern "C" long long rsr_rsr_encode(const float* params, size_t n_params, uint8_t* out, size_t cap) {
+    if (!params || !out) return fail(RSR_E_BAD_ARG, "null argument");
+    if (n_params > 0xffffffffull) return fail(RSR_E_BAD_ARG, "too many parameters for a u32 length prefix");
+    const size_t need = rsr_rsr_encoded_size(n_params);
+    if (cap < need) return fail(RSR_E_BAD_ARG, "output buffer too small (%zu < %zu)", cap, need);
+    auto put32 = [](uint8_t* q, uint32_t v) { q[0] = (uint8_t)v; q[1] = (uint8_t)(v >> 8); q[2] = (uint8_t)(v >> 16); q[3] = (uint8_t)(v >> 24); };
+    put32(out, (uint32_t)n_params);
+    for (size_t i = 0; i < n_params; ++i) put32(out + 4 + 4 * i, 4);
+    for (size_t i = 0; i < n_params; ++i) {
+        uint32_t bits;
+        memcpy(&bits, params + i, 4);
+        put32(out + 4 + 4 * n_params + 4 * i, bits);
+    }
+    return (long long)need;
+}
+// Returns the number of parameters (writing at most `cap` of them to `params`, which may be NULL to query the count).
+extern "C" long long rsr_rsr_decode(const uint8_t* data, size_t len, float* params, size_t cap) {
+    if (!data) return fail(RSR_E_BAD_ARG, "null argument");
+    auto get32 = [](const uint8_t* q) { return (uint32_t)q[0] | (uint32_t)q[1] << 8 | (uint32_t)q[2] << 16 | (uint32_t)q[3] << 24; };
+    if (len < 4) return fail(RSR_E_BAD_ARG, "Parameter file is malformed: shorter than its length prefix");
+    const size_t n = get32(data);
+    if (len != 4 + 8 * n) return fail(RSR_E_BAD_ARG, "Parameter file is malformed: %zu bytes for %zu parameters", len, n);
+    for (size_t i = 0; i < n; ++i)
+        if (get32(data + 4 + 4 * i) != 4) return fail(RSR_E_BAD_ARG, "Parameter file is malformed: element %zu has size %u", i, get32(data + 4 + 4 * i));
+    if (params)
+        for (size_t i = 0; i < n && i < cap; ++i) {
+            const uint32_t bits = get32(data + 4 + 4 * n + 4 * i);
+            memcpy(params + i, &bits, 4);
+        }
+    return (long long)n;
 }
 
 // ------------------------------------------------------------------ parameter-free CLI modes
@@ -1173,10 +1302,10 @@ extern "C" int rsr_downsample_u8(int device, const uint8_t* in, int w, int h, in
 // ([cb][H][W][32 hi | 32 mid]) and accumulated in TMEM (ConvParams::n_cb), the output is fp32 [H][W][Cout]
 // written 32 channels at a time by the RAW epilogue through a tensor map with a channel coordinate.
 //                        KH KW  RB NG R NR TPS NBS NPIN NOUT SHUF
-using CvN32  = ConvCfg<3, 3, 128, 1, 2, 6, 3, 3, 0, 2, false>;
-using CvN64  = ConvCfg<3, 3, 128, 2, 2, 6, 2, 3, 0, 2, false>;
-using CvN128 = ConvCfg<3, 3, 128, 4, 2, 6, 1, 4, 0, 2, false>;
-using CvN256 = ConvCfg<3, 3, 128, 8, 1, 5, 1, 3, 0, 2, false>;
+using CvN32  = ConvCfg<3, 3, 128, 1, 2, 6, 3, 3, 0, 2, 0>;
+using CvN64  = ConvCfg<3, 3, 128, 2, 2, 6, 2, 3, 0, 2, 0>;
+using CvN128 = ConvCfg<3, 3, 128, 4, 2, 6, 1, 4, 0, 2, 0>;
+using CvN256 = ConvCfg<3, 3, 128, 8, 1, 5, 1, 3, 0, 2, 0>;
 
 __global__ void __launch_bounds__(256) pack_planes_kernel(const float* __restrict__ x, int W, int H, int Ci,
                                                            __nv_bfloat16* __restrict__ planes) {
@@ -1214,7 +1343,7 @@ template <class C>
 static int conv2d_block(PFN_cuTensorMapEncodeTiled_v12000 enc, int num_sms, cudaStream_t st, const __nv_bfloat16* planes,
                         const __nv_bfloat16* wpack, float* d_out, int W, int H, int Ci, int Co, int co0, int* fault) {
     ConvParams p{};
-    p.W = W; p.H = H; p.NIMG = 1; p.row_begin = 0; p.row_end = H; p.factor = 3; p.fault = fault;
+    p.W = W; p.H = H; p.NIMG = 1; p.row_begin = 0; p.row_end = H; p.fault = fault;
     p.n_cb = Ci / 32;
     {
         cuuint64_t dims[4] = {64, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)p.n_cb};

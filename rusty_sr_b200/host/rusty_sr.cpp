@@ -18,21 +18,23 @@
 #include "../../include/rsr_b200.h"
 #include "png_io.hpp"
 
-static const int FACTOR = 3;  // main.rs:31
+static int FACTOR = 3;  // main.rs:31 (`const FACTOR: usize = 3; // TODO expose as an option`): --factor exposes it
 
-// bytevec decode::<u32> of Vec<f32>: u32 N | N x u32 sizes (all 4) | N x f32   
+// bytevec decode::<u32> of Vec<f32> (main.rs:138,146-152) through the library's codec (rsr_rsr_decode)
 static std::vector<float> decode_rsr(const std::vector<uint8_t>& d) {
-    auto bad = [] { return std::runtime_error("ByteVec conversion failed"); };  // main.rs:138 .expect(..)
-    if (d.size() < 4) throw bad();
-    const uint32_t n = (uint32_t)d[0] | (uint32_t)d[1] << 8 | (uint32_t)d[2] << 16 | (uint32_t)d[3] << 24;
-    if (d.size() != 4 + 8 * (size_t)n) throw bad();
-    for (uint32_t i = 0; i < n; ++i) {
-        const uint8_t* p = &d[4 + 4 * (size_t)i];
-        if (((uint32_t)p[0] | (uint32_t)p[1] << 8 | (uint32_t)p[2] << 16 | (uint32_t)p[3] << 24) != 4) throw bad();
-    }
-    std::vector<float> out(n);
-    memcpy(out.data(), &d[4 + 4 * (size_t)n], 4 * (size_t)n);
+    const long long n = rsr_rsr_decode(d.data(), d.size(), nullptr, 0);
+    if (n < 0) throw std::runtime_error("ByteVec conversion failed");  // main.rs:138 .expect(..)
+    std::vector<float> out((size_t)n);
+    rsr_rsr_decode(d.data(), d.size(), out.data(), out.size());
     return out;
+}
+// bytevec encode::<u32> (main.rs:213: the checkpoint writer of the training loop)
+static void write_rsr(const std::string& path, const std::vector<float>& params) {
+    std::vector<uint8_t> blob(rsr_rsr_encoded_size(params.size()));
+    if (rsr_rsr_encode(params.data(), params.size(), blob.data(), blob.size()) < 0) throw std::runtime_error(rsr_last_error());
+    FILE* f = fopen(path.c_str(), "wb");
+    if (!f || fwrite(blob.data(), 1, blob.size(), f) != blob.size()) { if (f) fclose(f); throw std::runtime_error("Error writing parameter file"); }
+    fclose(f);
 }
 
 static std::vector<uint8_t> read_file(const std::string& path, const char* what) {
@@ -62,7 +64,7 @@ static int usage(const char* msg) {
 
 int main(int argc, char** argv) {
     std::vector<std::string> pos;
-    std::string parameters, custom;
+    std::string parameters, custom, export_params;
     bool downsample = false;
     int device = 0;
     for (int i = 1; i < argc; ++i) {
@@ -75,6 +77,8 @@ int main(int argc, char** argv) {
         else if (a == "-c" || a == "--custom") custom = value("--custom");
         else if (a == "-d" || a == "--downsample") downsample = true;
         else if (a == "--device") device = atoi(value("--device").c_str());
+        else if (a == "--factor") FACTOR = atoi(value("--factor").c_str());             // extension (reference: compile-time 3)
+        else if (a == "--export-params") export_params = value("--export-params");       // extension: re-encode the selected .rsr
         else if (a == "--png-roundtrip") {  // test hook for the PNG codec: decode INPUT, re-encode as RGBA
             if (i + 2 >= argc) return usage("--png-roundtrip IN OUT");
             try {
@@ -87,6 +91,7 @@ int main(int argc, char** argv) {
         else pos.push_back(a);
     }
     if (pos.size() != 2) return usage("INPUT_FILE and OUTPUT_FILE are required");
+    if (FACTOR < 1 || FACTOR > 4) return usage("--factor must be 1..4");
     // clap conflicts_with (main.rs:58-70)
     if (!custom.empty() && !parameters.empty()) return usage("--custom conflicts with --parameters");
     if (downsample && (!custom.empty() || !parameters.empty())) return usage("--downsample conflicts with --parameters / --custom");
@@ -122,6 +127,7 @@ int main(int argc, char** argv) {
             params = decode_rsr(read_file(resource_dir(argv[0]) + "/" + name + ".rsr", "built-in parameter blob not found (set RUSTY_SR_RES)"));
         }
         fflush(stdout);
+        if (!export_params.empty()) write_rsr(export_params, params);
         // main.rs:162 assert_eq!(params.len(), graph.num_params(), ...)
         if (params.size() != rsr_num_params(FACTOR))
             throw std::runtime_error("Parameters selected do not have the size required by the neural net. Ensure that the "

@@ -15,11 +15,14 @@ from conftest import load_png, noise_image
 from oracle import oracle as O
 
 
+PREC_FLAGS = R.RSR_FLAG_BF16X3 if "bf16x3" in sys.argv[1:] else 0   # operand format under test (default: fp16 + mxfp8)
+
+
 def stage_check(params, x, label):
     H, W = x.shape[:2]
     npx = H * W
     ref, taps = O.forward(params, x, 3, np.float64, taps=True)
-    up = R.Upscaler(params)
+    up = R.Upscaler(params, flags=R.RSR_FLAG_SPLIT_MID | PREC_FLAGS)   # the split plan leaves every node in HBM
     # (stop_after, node buffer, oracle tensor)
     l3_part = None
     plan = [
@@ -67,7 +70,7 @@ def fused_check(params, x, label):
     H, W = x.shape[:2]
     ref, taps = O.forward(params, x, 3, np.float64, taps=True)
     try:
-        up = R.Upscaler(params, flags=R.RSR_FLAG_FUSED_MID)
+        up = R.Upscaler(params, flags=R.RSR_FLAG_FUSED_MID | PREC_FLAGS)
         up.debug_stop_after(3)
         up.forward(x)
         l3 = up.debug_read_node(0, H * W).reshape(H, W, 32)
@@ -83,7 +86,7 @@ def fused_check(params, x, label):
         launches = up.last_launch_count()
         times = up.last_kernel_times_ms()
         up.close()
-        split = R.Upscaler(params, flags=R.RSR_FLAG_SPLIT_MID)
+        split = R.Upscaler(params, flags=R.RSR_FLAG_SPLIT_MID | PREC_FLAGS)
         out_s = split.forward(x)
         split.close()
     except Exception as e:  # noqa

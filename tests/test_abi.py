@@ -57,8 +57,12 @@ def test_bad_arguments():
     assert not L.rsr_create(None, 0, 3, 0, 0)
     assert L.rsr_last_error_code() == _lib.RSR_E_BAD_ARG
     p = np.zeros(R.num_params(4), np.float32)
-    assert not L.rsr_create(p.ctypes.data_as(ctypes.POINTER(ctypes.c_float)), p.size, 4, 0, 0)
+    pp = p.ctypes.data_as(ctypes.POINTER(ctypes.c_float))
+    assert not L.rsr_create(pp, p.size, 5, 0, 0)                       # factors 1..4 only
+    assert L.rsr_last_error_code() == _lib.RSR_E_BAD_ARG
+    assert not L.rsr_create(pp, p.size, 4, 0, _lib.RSR_FLAG_FUSED_MID)  # the fused middle launch holds 32 expand channels
     assert L.rsr_last_error_code() == _lib.RSR_E_UNSUPPORTED
+    assert [L.rsr_num_params(f) for f in (1, 2, 3, 4)] == [R.num_params(f) for f in (1, 2, 3, 4)]
     assert L.rsr_upscale_f32(None, None, 1, 1, None) == _lib.RSR_E_BAD_ARG
     assert L.rsr_synchronize(None) == _lib.RSR_E_BAD_ARG
 
@@ -83,6 +87,19 @@ def test_rsr_codec_round_trip_and_errors():
     # agrees with the oracle's decoder
     from oracle import oracle as O
     assert np.array_equal(O.decode_rsr(data), p)
+    # and with the codec of the C ABI (rsr_rsr_encode / rsr_rsr_decode: what the compiled host uses; main.rs:138,213)
+    L = _lib.load()
+    buf = np.frombuffer(data, np.uint8)
+    assert L.rsr_rsr_decode(buf.ctypes.data, buf.size, None, 0) == p.size
+    q = np.zeros(p.size, np.float32)
+    assert L.rsr_rsr_decode(buf.ctypes.data, buf.size, q.ctypes.data, q.size) == p.size and np.array_equal(q, p)
+    out = np.zeros(L.rsr_rsr_encoded_size(p.size), np.uint8)
+    assert out.size == len(data) and L.rsr_rsr_encode(p.ctypes.data, p.size, out.ctypes.data, out.size) == len(data)
+    assert out.tobytes() == data
+    assert L.rsr_rsr_encode(p.ctypes.data, p.size, out.ctypes.data, out.size - 1) == _lib.RSR_E_BAD_ARG
+    for bad in (data[:-1], data + b"\x00", b"\x05\x00\x00\x00"):
+        b = np.frombuffer(bad, np.uint8)
+        assert L.rsr_rsr_decode(b.ctypes.data, b.size, None, 0) == _lib.RSR_E_BAD_ARG
 
 
 def test_product_package_never_touches_the_oracle():

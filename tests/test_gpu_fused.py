@@ -4,11 +4,10 @@ as the split plan (tests/test_gpu_parity.py), plus agreement between the two pla
 import numpy as np
 import pytest
 
-from conftest import load_png, noise_image, synthetic_kat_image
+from conftest import Plans, load_png, noise_image, synthetic_kat_image
 from oracle import oracle as O
 
 pytestmark = pytest.mark.gpu
-TOL = 2e-4   # asserted; the contract is 1e-3 (linear light)
 
 
 @pytest.fixture(scope="module")
@@ -17,10 +16,11 @@ def R():
     return R
 
 
-@pytest.fixture(scope="module")
-def pair(R, weights):
-    f = {k: R.Upscaler(weights[k], flags=R.RSR_FLAG_FUSED_MID) for k in weights}
-    s = {k: R.Upscaler(weights[k], flags=R.RSR_FLAG_SPLIT_MID) for k in weights}
+@pytest.fixture(scope="module", params=["f16mx", "bf16x3"])
+def pair(request, R, weights):
+    pf = R.RSR_FLAG_BF16X3 if request.param == "bf16x3" else 0
+    f = Plans({k: R.Upscaler(weights[k], flags=R.RSR_FLAG_FUSED_MID | pf) for k in weights}, request.param)
+    s = Plans({k: R.Upscaler(weights[k], flags=R.RSR_FLAG_SPLIT_MID | pf) for k in weights}, request.param)
     yield f, s
     for d in (f, s):
         for u in d.values():
@@ -51,9 +51,11 @@ def test_fused_parity(pair, weights, wname, case):
     ref = O.forward(weights[wname], x, 3, np.float64)
     out = f[wname].forward(x)
     srgb, lin = errs(out, ref)
-    assert lin < TOL and srgb < TOL, (srgb, lin)
-    # the two plans differ only in fp32 summation order
-    assert np.abs(out - s[wname].forward(x)).max() < 2e-5
+    tol = f.tol_noise if case == "noise256" else f.tol_natural
+    assert lin < tol and srgb < tol, (srgb, lin)
+    # the two plans differ only in fp32 summation order (fp16 + fp8 operands: an fp32-level difference in l2 can also flip the
+    # rounding of an fp8 correction operand, worth ~2^-16 of the value)
+    assert np.abs(out - s[wname].forward(x)).max() < (2e-5 if f.prec == "bf16x3" else 1e-4)
 
 
 @pytest.mark.parametrize("shape", [(1, 1), (1, 9), (9, 1), (7, 5), (2, 123), (3, 124), (5, 125), (4, 126), (3, 127),
@@ -66,7 +68,7 @@ def test_fused_odd_sizes(pair, weights, shape):
     x = noise_image(H, W, 100 + H * 1000 + W)
     ref = O.forward(weights["anime"], x, 3, np.float64)
     srgb, lin = errs(f["anime"].forward(x), ref)
-    assert lin < TOL and srgb < TOL, (shape, srgb, lin)
+    assert lin < f.tol_noise and srgb < f.tol_noise, (shape, srgb, lin)
 
 
 def test_fused_golden_u8(pair):
@@ -74,7 +76,7 @@ def test_fused_golden_u8(pair):
     lr, hr = load_png("cartoon_lr"), load_png("cartoon_rsa")
     img = f["anime"].forward_u8(lr)
     d = np.abs(img.astype(int) - hr.astype(int))
-    assert d.max() <= 1 and (d == 0).mean() >= 0.999 and (img[..., 3] == 255).all()
+    assert d.max() <= 1 and (d == 0).mean() >= f.tie_frac and (img[..., 3] == 255).all()
 
 
 def test_fused_batch_and_bands_bit_identical(pair):
@@ -104,7 +106,7 @@ def test_fused_1080p(pair, weights):
     y0, y1 = 500, 564
     ref = O.forward(weights["imagenet"], x[y0 - 7:y1 + 7], 3, np.float64)[21:-21]
     srgb, lin = errs(out[3 * y0:3 * y1], ref)
-    assert lin < TOL and srgb < TOL, (srgb, lin)
-    assert np.abs(out - s["imagenet"].forward(x)).max() < 2e-5
+    assert lin < f.tol_noise and srgb < f.tol_noise, (srgb, lin)
+    assert np.abs(out - s["imagenet"].forward(x)).max() < (2e-5 if f.prec == "bf16x3" else 1e-4)
     # repeated calls are deterministic
     assert np.array_equal(out, f["imagenet"].forward(x))
