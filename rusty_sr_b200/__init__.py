@@ -188,6 +188,10 @@ class Upscaler:
                                                 ctypes.c_void_p(d_out_rgba or None))
         _lib.check(rc)
 
+    def forward_device_u8_rgb(self, d_in: int, n: int, w: int, h: int, in_channels: int, d_out_rgb: int) -> None:
+        """Device-resident u8 [n][h][w][in_channels] -> u8 RGB [n][fh][fw][3] (rsr_upscale_device_u8_rgb); not synchronised."""
+        _lib.check(self._L.rsr_upscale_device_u8_rgb(self._h, ctypes.c_void_p(d_in), n, w, h, in_channels, ctypes.c_void_p(d_out_rgb)))
+
     def forward_band_device(self, d_in_rows: int, w: int, rows_in: int, top_halo: int, bottom_halo: int, d_out: int,
                             u8_channels: int = 0, out_channels: int = 0) -> None:
         """Device-resident band (rsr_upscale_band_device_*): u8_channels = 0 -> f32 in / f32 out, else u8 in / u8 out with

@@ -11,11 +11,11 @@
 //
 // How: a CTA walks down a 124-pixel-wide column strip, one image row per step.
 //   S1(y): tcgen05.mma M=128 N=96 over the 3x3 taps of l1 rows y-1..y+1 -> TMEM slot T[y] = [l2pre | P3acc | Eacc].
-//   E1(y): 4 warps: l2pre (+ P2 tile) -> bias, BeLU, split -> row y of a 3-slot l2 ring in shared memory, written
+//   E1(y): 8 warps: l2pre (+ P2 tile) -> bias, BeLU, split -> row y of a 3-slot l2 ring in shared memory, written
 //          in exactly the swizzled layout a TMA load would have produced (zero outside the image = Padding::Same).
 //   S2(y): tcgen05.mma N=64 over the taps of l2 rows y-1..y+1, ACCUMULATING onto T[y][32:96] (conv8 onto the
 //          conv6 partial, conv9 onto the conv7 partial) — the partial sums never leave TMEM.
-//   E2(y): 4 more warps: T[y][32:64] (+ P3 tile) -> bias, BeLU, split -> TMA store l3;  T[y][64:96] -> TMA store E.
+//   E2(y): 8 more warps: T[y][32:64] (+ P3 tile) -> bias, BeLU, split -> l3 (global);  T[y][64:96] -> E (global).
 // 128 l1 pixels give 126 l2 pixels give 124 output pixels per strip, so a strip recomputes 2 of 126 l2 columns;
 // a work item also recomputes one l2 row above and below its row range.  MMA row (= TMEM lane) m stands for
 // pixel x0 - 1 + m in BOTH levels — S2 accumulates onto S1's columns, so the lanes must agree: S1 reads l1 ring
@@ -23,9 +23,14 @@
 // 125..127 see out-of-window pixels and are discarded).  The MMA warp issues S1 three rows ahead of S2 so that
 // E1 runs under the MMAs.
 //
-// Warp roles (13 warps): 0 l1-row producer (TMA), 1 MMA issuer, 2 TMEM allocator + P2 producer, 3 weight
-// producer (one tap per stage, 5-stage ring), 4-7 E1, 8-11 E2, 12 P3 producer.  All hand-offs are mbarriers
-// and every wait is bounded (ptx.cuh mbar_wait).
+// Warp roles (21 warps): 0 l1-row producer (TMA), 1 MMA issuer, 2 TMEM allocator + P2 producer, 3 weight
+// producer, 4-11 E1, 12-19 E2, 20 P3 producer.  All hand-offs are mbarriers and every wait is bounded (ptx.cuh
+// mbar_wait).  The epilogues are the critical path of this kernel (r02 ablations: without their math it runs 250 us
+// instead of 450): each pixel's 32 channels are therefore split over TWO warps per TMEM lane quarter (16 channels =
+// one K chunk = 64 contiguous bytes of the pixel row each); every E2 warp stages its half rows of l3 and of E in two
+// 2 KB tiles of its own and stores them with TMA (64-byte-wide boxes), so the bulk-store wait before a tile is re-written
+// is always for a store issued a whole row earlier.  (Storing straight from registers was tried: the 16-byte-per-lane
+// strided stores cost 63 us of load/store-unit time, profiles/r02 A/B.)
 //
 // CTA-pair variant (template parameter PAIR; tcgen05 cta_group::2 as in conv_pair.cuh): the kernel is bound by the
 // shared-memory port — with one row per step every weight tap is re-streamed into shared memory and re-read by
@@ -44,11 +49,12 @@ struct FusedParams {
     CUtensorMap tmB2;     // conv8|9 weights:   rank 2 (64, 9 * 64), box (64, 64)
     CUtensorMap tmP2;     // conv2(f): rank 4 (32, W, H, NIMG) fp32, box (32, 128, 1, 1)
     CUtensorMap tmP3;     // conv3(f): same
-    CUtensorMap tmL3[3];  // l3 out: bf16 boxes of 32, 31 (first slice of a strip) and 29 pixels (last slice)
-    CUtensorMap tmE[3];   // E out: fp32 boxes of 32, 31 and 29 pixels
+    CUtensorMap tmL3[3];  // l3 out: half rows (32 x 2 B = one K chunk), boxes of 32, 31 (first slice of a strip) and 29 pixels (last slice), SWIZZLE_64B
+    CUtensorMap tmE[3];   // E out: half rows (16 fp32), same boxes
     int W, H, NIMG, n_strips;
     long long total_rowtiles;   // NIMG * n_strips * H
-    EpiGroup g_l2, g_l3;        // bias / slope of the two activations (kind = EPI_ACT)
+    // bias / BeLU slope of the two activations, in the kernel parameter (constant) bank: network.rs:51-52,55-56
+    float l2_bias[32], l2_slope[32], l3_bias[32], l3_slope[32];
     int* fault;
     // test hooks (rsr_debug_fused): fp32 [NIMG][H][W][32] dumps of l2 (as written to the ring) and of the raw
     // accumulator columns 32..63 (conv6(l1) + conv8(l2)); dbg_flags bit 0 = skip the S2 MMAs
@@ -97,7 +103,7 @@ enum : int {
 #define RSR_FUSED_PAIR_NB 3
 #endif
 #ifndef RSR_FUSED_PAIR_NR1
-#define RSR_FUSED_PAIR_NR1 4
+#define RSR_FUSED_PAIR_NR1 3   // the 3-row window only: the next row loads behind the first tap row of S1 (no loss vs 4, r02 A/B); frees 16 KB
 #endif
 template <bool PAIR_, int PREC_ = PREC_BF16X3>
 struct FusedCfgT {
@@ -106,12 +112,12 @@ struct FusedCfgT {
     static constexpr int STRIP = 124;          // output pixels per strip
     static constexpr int L2W = 126;            // valid l2 pixels per strip row
     static constexpr int SLOT = 128 * 128;     // one row slot: 128 pixels x 128 B
-    static constexpr int NR1 = PAIR ? RSR_FUSED_PAIR_NR1 : 4;     // l1 ring (3-row window + rows in flight)
+    static constexpr int NR1 = PAIR ? RSR_FUSED_PAIR_NR1 : 3;     // l1 ring (the 3-row window of S1)
     static constexpr int NR2 = 3;              // l2 ring
     static constexpr int TPS = PAIR ? RSR_FUSED_PAIR_TPS : 1;     // taps per weight stage (each tcgen05.commit that
                                                // releases a stage costs tensor-pipe time: fewer, larger stages)
     static constexpr int NSTG = 9 / TPS;       // stages per S1 / S2
-    static constexpr int NB = PAIR ? RSR_FUSED_PAIR_NB : 5;       // weight stages in the ring
+    static constexpr int NB = PAIR ? RSR_FUSED_PAIR_NB : 4;       // weight stages in the ring
     static constexpr int H1 = PAIR ? 48 : 96;  // weight rows per conv5|6|7 tap in this CTA
     static constexpr int H2 = PAIR ? 32 : 64;  // weight rows per conv8|9 tap in this CTA
     static constexpr int TAP1 = H1 * 128, TAP2 = H2 * 128;        // bytes of one tap in this CTA
@@ -121,14 +127,15 @@ struct FusedCfgT {
     static constexpr int TCOLS = 96;
     static constexpr int SF_COL = NT * TCOLS;  // PREC_F16MX: scale-factor columns 480..511 of the 512 allocated
     static constexpr int LOOKAHEAD = 4;        // S1 rows issued before the first S2 of a work item
-    static constexpr int NTHREADS = 13 * 32;
-    static constexpr int NARR = PAIR ? 8 : 4;  // epilogue-warp arrivals on l2_full / t_empty (both CTAs of a pair)
+    static constexpr int NTHREADS = 21 * 32;
+    static constexpr int NEW = 8;              // warps per epilogue level: 2 per TMEM lane quarter (16 channels each)
+    static constexpr int NARR = PAIR ? 2 * NEW : NEW;  // epilogue-warp arrivals on l2_full / t_empty (both CTAs of a pair)
     static constexpr int OFF_L2 = NR1 * SLOT;
     static constexpr int OFF_B = OFF_L2 + NR2 * SLOT;
     static constexpr int OFF_P2 = OFF_B + NB * BST;
     static constexpr int OFF_P3 = OFF_P2 + SLOT;
-    static constexpr int OFF_O = OFF_P3 + SLOT;
-    static constexpr int OFF_BAR = OFF_O + 4 * 4096;
+    static constexpr int OFF_O = OFF_P3 + SLOT;            // E2 staging: per warp a 2 KB half tile of l3 and one of E
+    static constexpr int OFF_BAR = OFF_O + NEW * 4096;
     // a_full/a_empty[NR1] b_full/b_empty[NB] p2_full p2_empty p3_full p3_empty t1_full[NT] l2_full/l2_empty[NR2]
     // t2_full[NT] t_empty[NT]
     static constexpr int NBAR = 2 * NR1 + 2 * NB + 4 + NT + 2 * NR2 + NT + NT;
@@ -235,8 +242,8 @@ __global__ void __launch_bounds__(FusedCfg::NTHREADS, 1) conv_fused_mid_kernel(c
     if (threadIdx.x == 0) {
         for (int i = 0; i < C::NR1; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
         for (int i = 0; i < C::NB; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
-        mbar_init(p2_full, 1); mbar_init(p2_empty, 4);
-        mbar_init(p3_full, 1); mbar_init(p3_empty, 4);
+        mbar_init(p2_full, 1); mbar_init(p2_empty, C::NEW);
+        mbar_init(p3_full, 1); mbar_init(p3_empty, C::NEW);
         for (int i = 0; i < C::NT; ++i) { mbar_init(&t1_full[i], 1); mbar_init(&t2_full[i], 1); mbar_init(&t_empty[i], C::NARR); }
         for (int i = 0; i < C::NR2; ++i) { mbar_init(&l2_full[i], C::NARR); mbar_init(&l2_empty[i], 1); }
         fence_mbar_init();
@@ -350,7 +357,7 @@ __global__ void __launch_bounds__(FusedCfg::NTHREADS, 1) conv_fused_mid_kernel(c
             }
         }
         FPROF_FLUSH(FP_P2_EMPTY, 1);
-    } else if (warp == 12) {
+    } else if (warp == 20) {
         // ===== P3 tile producer: one tile per S2 row (pixels x0-1 .. x0+126 of row y_b+r: tile row = TMEM lane) =====
         uint32_t u = 0;
         while (fitem_next<PAIR>(p, cur, end, rank, w)) {
@@ -410,7 +417,10 @@ __global__ void __launch_bounds__(FusedCfg::NTHREADS, 1) conv_fused_mid_kernel(c
                         const uint32_t b_e = sB_e + bst * (C::BST >> 4) + tt * (C::TAP1 >> 4);
                         const uint32_t a_e = arow[ta] + tb * (128 >> 4);
                         #pragma unroll
-                        for (int k = 0; k < 2; ++k) MM::chunk(d, a_e, b_e, k, MM_M, 96, sf, (t | k) != 0 ? 1u : 0u);
+                        for (int k = 0; k < 2; ++k) {
+                            if (ABL_NO_MMA) continue;
+                            MM::chunk(d, a_e, b_e, k, MM_M, 96, sf, (t | k) != 0 ? 1u : 0u);
+                        }
                         if (t == 2) commit(&a_empty[(a_item + q) % C::NR1]);   // top window row is dead
                     }
                     commit(&b_empty[bst]);
@@ -456,7 +466,7 @@ __global__ void __launch_bounds__(FusedCfg::NTHREADS, 1) conv_fused_mid_kernel(c
                         const uint32_t a_e = lrow[ta] + (tb - 1) * (128 >> 4);   // lane m reads ring pixels m-1..m+1
                         #pragma unroll
                         for (int k = 0; k < 2; ++k) {
-                            if (DBG && (p.dbg_flags & 1)) continue;
+                            if ((DBG && (p.dbg_flags & 1)) || ABL_NO_MMA) continue;
                             MM::chunk(d, a_e, b_e, k, MM_M, 64, sf, 1);
                         }
                         if (t == 2) commit(&l2_empty[(c1_item + r) % C::NR2]);
@@ -492,11 +502,13 @@ __global__ void __launch_bounds__(FusedCfg::NTHREADS, 1) conv_fused_mid_kernel(c
         FPROF_FLUSH(FP_T_EMPTY, FP_MMA_TOTAL - FP_T_EMPTY + 1);
         FPROF_FLUSH(FP_ROWS, 1);
         }  // leader
-    } else if (warp >= 4 && warp < 8) {
-        // ===== E1: l2pre (+ P2) -> l2 row in the shared-memory ring =====
-        const int ew = warp - 4;
+    } else if (warp >= 4 && warp < 12) {
+        // ===== E1: l2pre (+ P2) -> l2 row in the shared-memory ring; this warp: lane quarter ew, channels 16*half .. +15 =====
+        const int ew = warp & 3, half = (warp - 4) >> 2;
         const int m = ew * 32 + lane;            // MMA row = l2 ring pixel index
         const uint32_t sL_u = smem_u32(sL), sP2_u = smem_u32(sP2);
+        const float* bias = p.l2_bias + 16 * half;
+        const float* slope = p.l2_slope + 16 * half;
         uint32_t c = 0;
         const long long prof_t0 = FPROF_ON ? clock64() : 0;
         while (fitem_next<PAIR>(p, cur, end, rank, w)) {
@@ -505,44 +517,41 @@ __global__ void __launch_bounds__(FusedCfg::NTHREADS, 1) conv_fused_mid_kernel(c
                 const int y = w.y_b - 1 + q, px = w.x0 - 1 + m;
                 FWP(&t1_full[ts], (c / C::NT) & 1, 30, FP_E1_T1_FULL);
                 tc_fence_after();
-                uint32_t raw[32];
-                tmem_ld_32x32(tmem_base + ((uint32_t)(ew * 32) << 16) + ts * C::TCOLS, raw);
+                uint32_t raw[16];
+                tmem_ld_32x16(tmem_base + ((uint32_t)(ew * 32) << 16) + ts * C::TCOLS + 16 * half, raw);
                 tmem_ld_wait();
-                float v[32];
+                float v[16];
                 #pragma unroll
-                for (int k = 0; k < 32; ++k) v[k] = __uint_as_float(raw[k]);
+                for (int k = 0; k < 16; ++k) v[k] = __uint_as_float(raw[k]);
                 FWP(p2_full, c & 1, 31, FP_E1_P2_FULL);
-                epi_add_partial_tile(v, sP2_u, m);
+                epi_add_partial_half(v, sP2_u, m, half);
                 __syncwarp();
                 if (lane == 0) mbar_arrive(p2_empty);
-                {
-                    const float4* b4 = reinterpret_cast<const float4*>(p.g_l2.bias);
-                    const float4* s4 = reinterpret_cast<const float4*>(p.g_l2.slope);
+                if (!ABL_NO_E1_MATH) {
                     #pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        const float4 b = __ldg(b4 + i), s = __ldg(s4 + i);
-                        v[4 * i + 0] = belu(v[4 * i + 0] + b.x, s.x); v[4 * i + 1] = belu(v[4 * i + 1] + b.y, s.y);
-                        v[4 * i + 2] = belu(v[4 * i + 2] + b.z, s.z); v[4 * i + 3] = belu(v[4 * i + 3] + b.w, s.w);
-                    }
+                    for (int i = 0; i < 16; ++i) v[i] = belu(v[i] + bias[i], slope[i]);
                 }
                 // Padding::Same of conv8 / conv9: l2 is ZERO outside the image (not BeLU(bias)); lanes past the
                 // strip's 126 valid l2 pixels hold garbage accumulators and are zeroed too
                 const bool valid = y >= 0 && y < p.H && px >= 0 && px < p.W && m < C::L2W;
                 if (DBG && p.dbg_l2 && valid) {
-                    float4* dst = reinterpret_cast<float4*>(p.dbg_l2 + (((size_t)w.img * p.H + y) * p.W + px) * 32);
+                    float4* dst = reinterpret_cast<float4*>(p.dbg_l2 + (((size_t)w.img * p.H + y) * p.W + px) * 32 + 16 * half);
                     #pragma unroll
-                    for (int i = 0; i < 8; ++i) dst[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+                    for (int i = 0; i < 4; ++i) dst[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
                 }
-                uint32_t words[32];
-                pack_split_row<PREC>(v, words, !valid);
+                uint32_t words[16];
+                if (ABL_NO_E1_MATH) {
+                    #pragma unroll
+                    for (int i = 0; i < 16; ++i) words[i] = __float_as_uint(v[i]);
+                } else pack_split_half<PREC>(v, words, !valid);
                 // the MMAs that read the previous occupant of this ring slot must have completed
                 FWP(&l2_empty[ls], ((c / C::NR2) & 1) ^ 1, 32, FP_E1_L2_EMPTY);
-                store_row_swizzled(words, sL_u + ls * C::SLOT + m * 128, m & 7);
+                store_half_row_swizzled(words, sL_u + ls * C::SLOT + m * 128, m & 7, half);
                 fence_proxy_async_smem();   // generic-proxy writes -> visible to the tensor core's async-proxy reads
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) {
-                    // (pair: both arrive on the leader's barriers; release at cluster scope)
+                    // (pair: both CTAs' warps arrive on the leader's barriers)
                     if (PAIR) mbar_arrive_cluster(l2_full0 + ls * 8); else mbar_arrive(&l2_full[ls]);
                     // halo rows have no S2 / E2: their T slot is released here
                     if (q == 0 || q == w.n + 1) {
@@ -553,17 +562,40 @@ __global__ void __launch_bounds__(FusedCfg::NTHREADS, 1) conv_fused_mid_kernel(c
         }
         if (FPROF_ON) prof_acc[FP_E1_TOTAL] = clock64() - prof_t0;
         if (warp == 4) FPROF_FLUSH(FP_E1_T1_FULL, 4);
-    } else if (warp >= 8 && warp < 12) {
-        // ===== E2: T[32:64] (+ P3) -> l3;  T[64:96] -> E =====
-        // This warp's lanes are pixels xl .. xl+31 with xl = x0-1+32*ew; the strip's outputs are lanes 1..124, so
-        // warp 0 drops its lane 0 (staging row = lane-1, 31-pixel store at x0) and warp 3 its lanes 29..31.
-        const int ew = warp - 8;
-        const uint32_t stage = smem_u32(sO) + ew * 4096;
+    } else if (warp >= 12 && warp < 20) {
+        // ===== E2: T[32:64] (+ P3) -> l3;  T[64:96] -> E; this warp: lane quarter ew, channels 16*half .. +15 of both =====
+        // Lane m of the strip is pixel x0-1+m; the strip's outputs are lanes 1..124, so quarter 0 drops its lane 0 (staging
+        // row = lane-1, 31-pixel store at x0) and quarter 3 its lanes 29..31 (29-pixel store).
+        const int ew = warp & 3, half = (warp - 12) >> 2;
+        const int m = ew * 32 + lane;
+        const uint32_t stage_l3 = smem_u32(sO) + (warp - 12) * 4096, stage_e = stage_l3 + 2048;
         const uint32_t sP3_u = smem_u32(sP3);
         const int bx = ew == 0 ? 1 : ew == 3 ? 2 : 0;     // tensor maps with 32 / 31 / 29 pixel boxes
         const int srow = ew == 0 ? lane - 1 : lane;       // staging row of this lane (-1: not stored)
+        const float* bias = p.l3_bias + 16 * half;
+        const float* slope = p.l3_slope + 16 * half;
         uint32_t c1_item = 0, c2 = 0;
         const long long prof_t0 = FPROF_ON ? clock64() : 0;
+        // one TMA store of this warp's half tile; the previous store from the same tile must have finished READING it: at
+        // most the one newer store (of the other tile) may still be pending
+        auto store_tile = [&](const uint32_t (&words)[16], uint32_t stage, const CUtensorMap* tm, int c0, int xs, int y, int img) {
+            {
+                const long long t0s = FPROF_ON ? clock64() : 0;
+                if (elect_one()) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+                __syncwarp();
+                if (FPROF_ON) prof_acc[FP_E2_STORE_READ] += clock64() - t0s;
+            }
+            if (srow >= 0) store_row64_swizzled(words, stage, srow);
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (elect_one()) {
+                asm volatile(
+                    "cp.async.bulk.tensor.4d.global.shared::cta.tile.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+                    ::"l"(reinterpret_cast<uint64_t>(tm)), "r"(stage), "r"(c0), "r"(xs), "r"(y), "r"(img)
+                    : "memory");
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            }
+        };
         while (fitem_next<PAIR>(p, cur, end, rank, w)) {
             const int xl = w.x0 - 1 + ew * 32;
             const int xs = ew == 0 ? w.x0 : xl;            // first pixel this warp stores
@@ -574,66 +606,34 @@ __global__ void __launch_bounds__(FusedCfg::NTHREADS, 1) conv_fused_mid_kernel(c
                 const bool live = live_x && y < w.y_e;   // (pair: the peer's padding rows are computed, not stored)
                 FWP(&t2_full[c2 % C::NT], (c2 / C::NT) & 1, 33, FP_E2_T2_FULL);
                 tc_fence_after();
-                const uint32_t trow = tmem_base + ((uint32_t)(ew * 32) << 16) + ts * C::TCOLS;
-                uint32_t raw[32];
-                float v[32];
-                // --- l3 ---
-                tmem_ld_32x32(trow + 32, raw);
+                const uint32_t trow = tmem_base + ((uint32_t)(ew * 32) << 16) + ts * C::TCOLS + 16 * half;
+                uint32_t raw[16], raw_e[16];
+                tmem_ld_32x16(trow + 32, raw);
+                tmem_ld_32x16(trow + 64, raw_e);
                 tmem_ld_wait();
+                float v[16];
                 #pragma unroll
-                for (int k = 0; k < 32; ++k) v[k] = __uint_as_float(raw[k]);
-                if (DBG && p.dbg_t3 && live) {
-                    const int m = ew * 32 + lane, px = xl + lane;
-                    if (m >= 1 && m <= C::STRIP && px < p.W) {
-                        float4* dst = reinterpret_cast<float4*>(p.dbg_t3 + (((size_t)w.img * p.H + y) * p.W + px) * 32);
-                        #pragma unroll
-                        for (int i = 0; i < 8; ++i) dst[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
-                    }
+                for (int k = 0; k < 16; ++k) v[k] = __uint_as_float(raw[k]);
+                // --- E: raw fp32 partial of `expand` ---
+                if (!ABL_NO_EPI_OUT && !ABL_NO_E2_STORE && live) store_tile(raw_e, stage_e, &p.tmE[bx], 16 * half, xs, y, w.img);
+                if (DBG && p.dbg_t3 && live && m >= 1 && m <= C::STRIP && xl + lane < p.W) {
+                    float4* dst = reinterpret_cast<float4*>(p.dbg_t3 + (((size_t)w.img * p.H + y) * p.W + xl + lane) * 32 + 16 * half);
+                    #pragma unroll
+                    for (int i = 0; i < 4; ++i) dst[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
                 }
+                // --- l3 ---
                 FWP(p3_full, c2 & 1, 34, FP_E2_P3_FULL);
-                epi_add_partial_tile(v, sP3_u, ew * 32 + lane);
+                epi_add_partial_half(v, sP3_u, m, half);
                 __syncwarp();
                 if (lane == 0) mbar_arrive(p3_empty);
-                if (live) {
-                    {
-                        const long long t0s = FPROF_ON ? clock64() : 0;
-                        if (elect_one()) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-                        __syncwarp();
-                        if (FPROF_ON) prof_acc[FP_E2_STORE_READ] += clock64() - t0s;
-                    }
-                    if (srow >= 0) epi_split_to_stage<PREC>(p.g_l3, v, stage, srow);
-                    fence_proxy_async_smem();
-                    __syncwarp();
-                    if (elect_one()) {
-                        asm volatile(
-                            "cp.async.bulk.tensor.4d.global.shared::cta.tile.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
-                            ::"l"(reinterpret_cast<uint64_t>(&p.tmL3[bx])), "r"(stage), "r"(0), "r"(xs), "r"(y), "r"(w.img)
-                            : "memory");
-                        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-                    }
-                }
-                // --- E ---
-                tmem_ld_32x32(trow + 64, raw);
-                tmem_ld_wait();
-                #pragma unroll
-                for (int k = 0; k < 32; ++k) v[k] = __uint_as_float(raw[k]);
-                if (live) {
-                    {
-                        const long long t0s = FPROF_ON ? clock64() : 0;
-                        if (elect_one()) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-                        __syncwarp();
-                        if (FPROF_ON) prof_acc[FP_E2_STORE_READ] += clock64() - t0s;
-                    }
-                    if (srow >= 0) epi_raw_to_stage(v, stage, srow);
-                    fence_proxy_async_smem();
-                    __syncwarp();
-                    if (elect_one()) {
-                        asm volatile(
-                            "cp.async.bulk.tensor.4d.global.shared::cta.tile.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
-                            ::"l"(reinterpret_cast<uint64_t>(&p.tmE[bx])), "r"(stage), "r"(0), "r"(xs), "r"(y), "r"(w.img)
-                            : "memory");
-                        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-                    }
+                if (ABL_NO_EPI_OUT) { if (v[0] == 123.456f) p.dbg_l2[0] = v[1] + __uint_as_float(raw_e[0]); }
+                else if (live) {
+                    #pragma unroll
+                    for (int i = 0; i < 16; ++i) v[i] = belu(v[i] + bias[i], slope[i]);
+                    uint32_t words[16];
+                    pack_split_half<PREC>(v, words);
+                    if (ABL_NO_E2_STORE) { if (words[0] == 0x12345678u) p.dbg_l2[0] = __uint_as_float(words[1] ^ words[5] ^ words[9] ^ words[13]); }
+                    else store_tile(words, stage_l3, &p.tmL3[bx], 32 * half, xs, y, w.img);
                 }
                 tc_fence_before();
                 __syncwarp();
@@ -644,7 +644,7 @@ __global__ void __launch_bounds__(FusedCfg::NTHREADS, 1) conv_fused_mid_kernel(c
             c1_item += w.n + 2;
         }
         if (FPROF_ON) prof_acc[FP_E2_TOTAL] = clock64() - prof_t0;
-        if (warp == 8) FPROF_FLUSH(FP_E2_T2_FULL, 4);
+        if (warp == 12) FPROF_FLUSH(FP_E2_T2_FULL, 4);
         if (elect_one()) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     }
     tc_fence_before();

@@ -216,7 +216,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(C::NTHREADS, 1) conv
                                         const uint32_t a_e = arow[r + ta] + tb * (C::RB >> 4);
                                         const uint32_t d = d_pass + r * C::NCOL;
                                         #pragma unroll
-                                        for (int c = 0; c < C::KC; ++c) MM::chunk(d, a_e, b_e, c, 256, C::NCOL, sf, (t | c) != 0 ? 1u : 0u);
+                                        for (int c = 0; c < C::KC; ++c) {
+                                            if (ABL_NO_MMA) continue;
+                                            MM::chunk(d, a_e, b_e, c, 256, C::NCOL, sf, (t | c) != 0 ? 1u : 0u);
+                                        }
                                     }
                                     if (tb == C::KW - 1 && ta < NEARLY) {
                                         uint32_t sl = slot0 + ta;

@@ -16,10 +16,12 @@
 //               factor 2^-11 is applied by the tensor core, so everything lands in one fp32 accumulator.  Executed
 //               cost 2 MMAs per chunk; error <= 2.5e-4 linear light on uniform noise, <= 5e-5 on natural images
 //               (tools/precision_probe.py; tests/cuda/umma_mx_probe.cu pins the instruction semantics).
-//               Pixel row: [32 x fp16 a_h | 16 x e4m3 2^11 a_l, 16 x e4m3 a  (ch 0-15) | the same for ch 16-31];
-//               weight row: [32 x fp16 w_h | 16 x e4m3 w, 16 x e4m3 2^11 w_l | ...].
+//               Pixel row (128 B) = two 64-byte K chunks of 16 channels: [16 x fp16 a_h | 16 x e4m3 2^11 a_l | 16 x e4m3 a];
+//               weight row: per chunk [16 x fp16 w_h | 16 x e4m3 w | 16 x e4m3 2^11 w_l].
 //   PREC_BF16X3 (RSR_FLAG_BF16X3, conv0's x-im2col input, the generic conv) a_hi*w_hi + a_mid*w_hi + a_hi*w_mid, all
-//               bf16: three kind::f16 MMAs per chunk, error <= 8e-5.  Pixel row: [32 x bf16 hi | 32 x bf16 mid].
+//               bf16: three kind::f16 MMAs per chunk, error <= 8e-5.  Per 64-byte chunk: [16 x bf16 hi | 16 x bf16 mid].
+//   Either way a 16-channel chunk is 64 contiguous bytes (first plane 32 B, second plane 32 B), so an epilogue can split a
+//   pixel's channels over two warps that each own four consecutive 16-byte pieces of the row.
 //
 // Data movement: a CTA walks down a 128-pixel-wide column strip.  Input rows are TMA-loaded ONCE
 // each into a ring of row slots in shared memory (box = 128 + KW - 1 pixels, SWIZZLE_128B,
@@ -58,6 +60,8 @@
 #define ABL_NO_PIN (RSR_ABL & 4)        // partial-sum tiles: no TMA (MMAs still issued)
 #define ABL_NO_MMA (RSR_ABL & 8)        // no tcgen05.mma at all
 #define ABL_NO_EPI_OUT (RSR_ABL & 16)   // epilogue: TMEM load only, no math / staging / store
+#define ABL_NO_E2_STORE (RSR_ABL & 128)  // fused kernel, second-level epilogue: math kept, global stores dropped
+#define ABL_NO_E1_MATH (RSR_ABL & 64)   // fused kernel, first-level epilogue: no bias / BeLU / split (raw bits into the l2 ring)
 
 namespace rsr {
 
@@ -259,28 +263,67 @@ __device__ __forceinline__ void store_row_swizzled(const uint32_t (&w)[32], uint
     #pragma unroll
     for (int j = 0; j < 8; ++j) st_shared_v4(row + ((j ^ sw) << 4), w[4 * j], w[4 * j + 1], w[4 * j + 2], w[4 * j + 3]);
 }
-// One pixel's 32 activation values -> the 32 words of its row in storage format OFMT (zero: a padding pixel, all zeros).
+// 16 activation values (one K chunk) -> the 16 words of its 64 bytes in storage format OFMT:
+// F16MX [8 words fp16 a_h | 4 words e4m3(2^11 a_l) | 4 words e4m3(a)], BF16X3 [8 words bf16 hi | 8 words bf16 mid].
 template <int OFMT>
-__device__ __forceinline__ void pack_split_row(const float (&v)[32], uint32_t (&w)[32], bool zero = false) {
+__device__ __forceinline__ void pack_split_chunk(const float* v, uint32_t* w) {
     if (OFMT == PREC_F16MX) {
-        // chunks 0-3: fp16 a_h (8 channels each) | 4: e4m3 2^11 a_l ch 0-15 | 5: e4m3 a ch 0-15 | 6, 7: the same for ch 16-31
         #pragma unroll
-        for (int i = 0; i < 8; ++i) {
+        for (int i = 0; i < 4; ++i) {
             uint32_t la, lb, aa, ab;
             split_pair_f16mx(v[4 * i], v[4 * i + 1], w[2 * i], la, aa);
             split_pair_f16mx(v[4 * i + 2], v[4 * i + 3], w[2 * i + 1], lb, ab);
-            const int c = i >> 2, k = i & 3;   // 16-channel chunk, word within its 16 bytes
-            w[16 + 8 * c + k] = la | (lb << 16);
-            w[20 + 8 * c + k] = aa | (ab << 16);
+            w[8 + i] = la | (lb << 16);
+            w[12 + i] = aa | (ab << 16);
         }
     } else {
-        // chunks 0-3: bf16 hi | 4-7: bf16 mid
         #pragma unroll
-        for (int i = 0; i < 16; ++i) split_pair(v[2 * i], v[2 * i + 1], w[i], w[16 + i]);
+        for (int i = 0; i < 8; ++i) split_pair(v[2 * i], v[2 * i + 1], w[i], w[8 + i]);
     }
+}
+// One pixel's 32 activation values -> the 32 words of its row (zero: a padding pixel, all zeros).
+template <int OFMT>
+__device__ __forceinline__ void pack_split_row(const float (&v)[32], uint32_t (&w)[32], bool zero = false) {
+    pack_split_chunk<OFMT>(&v[0], &w[0]);
+    pack_split_chunk<OFMT>(&v[16], &w[16]);
     if (zero) {
         #pragma unroll
         for (int i = 0; i < 32; ++i) w[i] = 0u;
+    }
+}
+
+// Half rows (16 channels = one K chunk = the row's 16-byte pieces 4h .. 4h+3), for epilogues that split a pixel's 32
+// channels over two warps.
+template <int OFMT>
+__device__ __forceinline__ void pack_split_half(const float (&v)[16], uint32_t (&w)[16], bool zero = false) {
+    pack_split_chunk<OFMT>(&v[0], &w[0]);
+    if (zero) {
+        #pragma unroll
+        for (int i = 0; i < 16; ++i) w[i] = 0u;
+    }
+}
+// into a tile of 128-byte rows with the 128-byte swizzle (sw = row & 7)
+__device__ __forceinline__ void store_half_row_swizzled(const uint32_t (&w)[16], uint32_t row, uint32_t sw, int h) {
+    #pragma unroll
+    for (int k = 0; k < 4; ++k)
+        st_shared_v4(row + (((uint32_t)(4 * h + k) ^ sw) << 4), w[4 * k], w[4 * k + 1], w[4 * k + 2], w[4 * k + 3]);
+}
+// into a tile of 64-byte rows with the 64-byte TMA swizzle (16-byte piece j of row r sits at piece j ^ ((r >> 1) & 3))
+__device__ __forceinline__ void store_row64_swizzled(const uint32_t (&w)[16], uint32_t tile, int r) {
+    const uint32_t row = tile + r * 64, sw = (r >> 1) & 3;
+    #pragma unroll
+    for (int k = 0; k < 4; ++k) st_shared_v4(row + (((uint32_t)k ^ sw) << 4), w[4 * k], w[4 * k + 1], w[4 * k + 2], w[4 * k + 3]);
+}
+// v += channels 16h .. 16h+15 of the pixel's fp32 partial sums in a TMA-loaded (128 B swizzled) tile of 128 pixels
+__device__ __forceinline__ void epi_add_partial_half(float (&v)[16], uint32_t tile_addr, int row, int h) {
+    const uint32_t base = tile_addr + row * 128;
+    const uint32_t sw = row & 7;
+    #pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        float4 t;
+        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                     : "=f"(t.x), "=f"(t.y), "=f"(t.z), "=f"(t.w) : "r"(base + (((uint32_t)(4 * h + j) ^ sw) << 4)));
+        v[4 * j + 0] += t.x; v[4 * j + 1] += t.y; v[4 * j + 2] += t.z; v[4 * j + 3] += t.w;
     }
 }
 
@@ -461,26 +504,26 @@ __device__ __forceinline__ void epi_add_partial_tile(float* v, uint32_t tile_add
 
 // ---- MMA issue: the split products of one 16-channel K chunk ---------------------------------------------------
 // a_e / b_e: encoded (>> 4) shared-memory addresses of the pixel row / weight row starts (with the LBO bits);
-// chunk c lives at +32 B (encoded +2), the second plane (bf16 mid / fp8 section) at +RB/2 bytes.
+// chunk c lives at +64c bytes (encoded +4c), its second plane (bf16 mid / fp8 pair) 32 bytes further (encoded +2).
 template <int PREC, int CG, int RB>
 struct SplitMma {
     static constexpr uint32_t HI = (uint32_t)make_sdesc_hi(8 * RB, RB == 128 ? UMMA_SW_128B : UMMA_SW_64B);
-    static constexpr uint32_t PLANE2 = (RB / 2) >> 4;
+    static constexpr uint32_t PLANE2 = 2, CHUNK = 4;
     static __device__ __forceinline__ uint64_t desc(uint32_t lo) { return ((uint64_t)HI << 32) | lo; }
     static __host__ __device__ constexpr uint32_t idesc(int M, int N) {
         return PREC == PREC_F16MX ? make_idesc_f16(M, N) : make_idesc_bf16(M, N);
     }
     // the leading product (hi x hi): the only one that may overwrite the accumulator
     static __device__ __forceinline__ void head(uint32_t d, uint32_t a_e, uint32_t b_e, int c, int M, int N, uint32_t acc) {
-        umma_f16_cg<CG>(d, desc(a_e + 2 * c), desc(b_e + 2 * c), idesc(M, N), acc);
+        umma_f16_cg<CG>(d, desc(a_e + CHUNK * c), desc(b_e + CHUNK * c), idesc(M, N), acc);
     }
     // the correction products, always accumulated; sf = TMEM address of the scale-factor columns (F16MX)
     static __device__ __forceinline__ void tail(uint32_t d, uint32_t a_e, uint32_t b_e, int c, int M, int N, uint32_t sf) {
         if (PREC == PREC_F16MX) {
-            umma_mxf8<CG>(d, desc(a_e + PLANE2 + 2 * c), desc(b_e + PLANE2 + 2 * c), make_idesc_mxf8(M, N), sf, sf + 16, 1);
+            umma_mxf8<CG>(d, desc(a_e + CHUNK * c + PLANE2), desc(b_e + CHUNK * c + PLANE2), make_idesc_mxf8(M, N), sf, sf + 16, 1);
         } else {
-            umma_f16_cg<CG>(d, desc(a_e + PLANE2 + 2 * c), desc(b_e + 2 * c), idesc(M, N), 1);
-            umma_f16_cg<CG>(d, desc(a_e + 2 * c), desc(b_e + PLANE2 + 2 * c), idesc(M, N), 1);
+            umma_f16_cg<CG>(d, desc(a_e + CHUNK * c + PLANE2), desc(b_e + CHUNK * c), idesc(M, N), 1);
+            umma_f16_cg<CG>(d, desc(a_e + CHUNK * c), desc(b_e + CHUNK * c + PLANE2), idesc(M, N), 1);
         }
     }
     static __device__ __forceinline__ void chunk(uint32_t d, uint32_t a_e, uint32_t b_e, int c, int M, int N, uint32_t sf, uint32_t acc) {

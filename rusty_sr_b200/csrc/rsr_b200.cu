@@ -268,6 +268,7 @@ struct rsr_ctx {
     // packed weights (conv_strip.cuh storage formats), biases / slopes (32 floats each, zero padded; expand_bias: 64)
     uint8_t *w0 = nullptr, *w1 = nullptr, *w2 = nullptr, *w3 = nullptr, *w4 = nullptr;
     float* vecs = nullptr;  // 8 x 32 floats: f_bias f_activ l1_bias l1_activ l2_bias l2_activ l3_bias l3_activ, then 64: expand_bias
+    std::vector<float> vecs_host;   // the same on the host (the fused launch takes its bias / slope vectors as kernel parameters)
     // workspace
     DevBuf xcol, xf4, actA, actB, partA, partB, partC, out_f32, out_u8, in_stage;
     int plan = 0;               // middle levels: 0 = by width (fused unless the 124-pixel strips waste too much), 1 = fused, 2 = split
@@ -319,22 +320,22 @@ static inline void split_bf16(float w, __nv_bfloat16& hi, __nv_bfloat16& mid) {
     mid = __float2bfloat16_rn(w - __bfloat162float(hi));
 }
 
-// 32 input-channel weights of one (tap, output channel) -> the 128-byte weight row of operand format `prec`
-// (conv_strip.cuh): BF16X3 [32 x bf16 hi | 32 x bf16 mid]; F16MX [32 x fp16 w_h | per 16 channels: 16 x e4m3(w), 16 x e4m3(2^11 w_l)].
+// 32 input-channel weights of one (tap, output channel) -> the 128-byte weight row of operand format `prec` (conv_strip.cuh):
+// two 64-byte K chunks of 16 channels, BF16X3 [16 x bf16 hi | 16 x bf16 mid]; F16MX [16 x fp16 w_h | 16 x e4m3(w) | 16 x e4m3(2^11 w_l)].
 static void pack_weight_row(const float* w, uint8_t* row, int prec) {
-    if (prec == PREC_F16MX) {
-        __half* h = reinterpret_cast<__half*>(row);
-        for (int ci = 0; ci < 32; ++ci) {
+    for (int ci = 0; ci < 32; ++ci) {
+        uint8_t* chunk = row + (ci >> 4) * 64;
+        const int k = ci & 15;
+        if (prec == PREC_F16MX) {
             const __half wh = __float2half_rn(w[ci]);
-            h[ci] = wh;
+            reinterpret_cast<__half*>(chunk)[k] = wh;
             const float wl = w[ci] - __half2float(wh);
-            uint8_t* sec = row + 64 + (ci >> 4) * 32;
-            sec[ci & 15] = (uint8_t)__nv_cvt_float_to_fp8(w[ci], __NV_SATFINITE, __NV_E4M3);
-            sec[16 + (ci & 15)] = (uint8_t)__nv_cvt_float_to_fp8(wl * F16MX_SCALE, __NV_SATFINITE, __NV_E4M3);
+            chunk[32 + k] = (uint8_t)__nv_cvt_float_to_fp8(w[ci], __NV_SATFINITE, __NV_E4M3);
+            chunk[48 + k] = (uint8_t)__nv_cvt_float_to_fp8(wl * F16MX_SCALE, __NV_SATFINITE, __NV_E4M3);
+        } else {
+            __nv_bfloat16* q = reinterpret_cast<__nv_bfloat16*>(chunk);
+            split_bf16(w[ci], q[k], q[16 + k]);
         }
-    } else {
-        __nv_bfloat16* q = reinterpret_cast<__nv_bfloat16*>(row);
-        for (int ci = 0; ci < 32; ++ci) split_bf16(w[ci], q[ci], q[32 + ci]);
     }
 }
 
@@ -515,6 +516,7 @@ static int create_impl(rsr_ctx* c, const float* params) {
         for (int i = 0; i < 8; ++i) memcpy(&v[i * 32], params + src[i], sizeof(float) * 32);
         memcpy(&v[8 * 32], params + L.expand_bias, sizeof(float) * ce);
         if (int rc = upload(&c->vecs, v.data(), v.size() * 4)) return rc;
+        c->vecs_host = v;
     }
     return dispatch(c->prec, c->factor, SetAttrs{});
 }
@@ -602,27 +604,29 @@ extern "C" int rsr_synchronize(rsr_ctx* c) {
 
 // ------------------------------------------------------------------------------ tensor maps
 // activation / xcol tensor: rows of `row_bytes` (128: swizzle 128B; 64: swizzle 64B) per pixel, described as 2-byte elements
-static int make_map_act(rsr_ctx* c, CUtensorMap* m, const void* base, int row_bytes, int W, int H, int N, int boxw) {
+// box_bytes: bytes of a pixel row one box covers (default: the whole row); 64-byte boxes use the 64-byte swizzle
+static int make_map_act(rsr_ctx* c, CUtensorMap* m, const void* base, int row_bytes, int W, int H, int N, int boxw, int box_bytes = 0) {
     const cuuint64_t rb = (cuuint64_t)row_bytes;
     const int elems = row_bytes / 2;
+    if (!box_bytes) box_bytes = row_bytes;
     cuuint64_t dims[4] = {(cuuint64_t)elems, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
     cuuint64_t strides[3] = {rb, rb * W, rb * W * H};
-    cuuint32_t box[4] = {(cuuint32_t)elems, (cuuint32_t)boxw, 1, 1};
+    cuuint32_t box[4] = {(cuuint32_t)(box_bytes / 2), (cuuint32_t)boxw, 1, 1};
     cuuint32_t es[4] = {1, 1, 1, 1};
     CUresult r = c->encode(m, CU_TENSOR_MAP_DATA_TYPE_UINT16, 4, const_cast<void*>(base), dims, strides, box, es,
                            CU_TENSOR_MAP_INTERLEAVE_NONE,
-                           row_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                           box_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
                            RSR_L2PROMO, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail(RSR_E_CUDA, "cuTensorMapEncodeTiled(activation %dx%dx%d) failed: %d", W, H, N, (int)r);
     return 0;
 }
-static int make_map_part(rsr_ctx* c, CUtensorMap* m, const void* base, int W, int H, int N, int boxw) {
+static int make_map_part(rsr_ctx* c, CUtensorMap* m, const void* base, int W, int H, int N, int boxw, int box_ch = 32) {
     cuuint64_t dims[4] = {32, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
     cuuint64_t strides[3] = {128, (cuuint64_t)128 * W, (cuuint64_t)128 * W * H};
-    cuuint32_t box[4] = {32, (cuuint32_t)boxw, 1, 1};
+    cuuint32_t box[4] = {(cuuint32_t)box_ch, (cuuint32_t)boxw, 1, 1};
     cuuint32_t es[4] = {1, 1, 1, 1};
     CUresult r = c->encode(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<void*>(base), dims, strides, box, es,
-                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, box_ch == 32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail(RSR_E_CUDA, "cuTensorMapEncodeTiled(partial %dx%dx%d) failed: %d", W, H, N, (int)r);
     return 0;
@@ -785,14 +789,17 @@ static int forward_impl(rsr_ctx* c, const void* d_in, bool u8, int in_ch, int n,
         if (int rc = make_map_w(c, &q.tmB2, c->w3, 128, 9 * 64, fpair ? 32 : 64)) return rc;
         if (int rc = part_map(&q.tmP2, P2, 128)) return rc;
         if (int rc = part_map(&q.tmP3, P3, 128)) return rc;
-        if (int rc = in_map(&q.tmL3[0], l3_act, 32)) return rc;
-        if (int rc = in_map(&q.tmL3[1], l3_act, 31)) return rc;
-        if (int rc = in_map(&q.tmL3[2], l3_act, 29)) return rc;
-        if (int rc = part_map(&q.tmE[0], E[0], 32)) return rc;
-        if (int rc = part_map(&q.tmE[1], E[0], 31)) return rc;
-        if (int rc = part_map(&q.tmE[2], E[0], 29)) return rc;
-        q.g_l2 = EpiGroup{EPI_ACT, 1, l2_bias, l2_slope, 0, 0};
-        q.g_l3 = EpiGroup{EPI_ACT, 1, l3_bias, l3_slope, 0, 0};
+        {   // half-row (one K chunk = 64 B) boxes of 32 / 31 / 29 pixels for the E2 warps' stores
+            const int bw[3] = {32, 31, 29};
+            for (int k = 0; k < 3; ++k) {
+                if (int rc = make_map_act(c, &q.tmL3[k], l3_act, 128, w, h, n, bw[k], 64)) return rc;
+                if (int rc = make_map_part(c, &q.tmE[k], E[0], w, h, n, bw[k], 16)) return rc;
+            }
+        }
+        memcpy(q.l2_bias, &c->vecs_host[4 * 32], sizeof q.l2_bias);
+        memcpy(q.l2_slope, &c->vecs_host[5 * 32], sizeof q.l2_slope);
+        memcpy(q.l3_bias, &c->vecs_host[6 * 32], sizeof q.l3_bias);
+        memcpy(q.l3_slope, &c->vecs_host[7 * 32], sizeof q.l3_slope);
         q.dbg_flags = c->fused_dbg & 1;
         if (c->fused_dbg & 2) {
             if (int rc = ensure(c->dbg_l2, npx * 128)) return rc;
@@ -1081,15 +1088,16 @@ extern "C" int rsr_debug_stop_after(rsr_ctx* c, int k) {
 }
 // one stored activation row (128 B, conv_strip.cuh storage formats) -> 32 floats
 static void unpack_act_row(const uint8_t* row, int prec, float* out) {
-    if (prec == PREC_F16MX) {
-        const __half* h = reinterpret_cast<const __half*>(row);
-        for (int ch = 0; ch < 32; ++ch) {
-            const __nv_fp8_storage_t lo = row[64 + (ch >> 4) * 32 + (ch & 15)];
-            out[ch] = __half2float(h[ch]) + __half2float(__half(__nv_cvt_fp8_to_halfraw(lo, __NV_E4M3))) / F16MX_SCALE;
+    for (int ch = 0; ch < 32; ++ch) {
+        const uint8_t* chunk = row + (ch >> 4) * 64;
+        const int k = ch & 15;
+        if (prec == PREC_F16MX) {
+            const __nv_fp8_storage_t lo = chunk[32 + k];
+            out[ch] = __half2float(reinterpret_cast<const __half*>(chunk)[k]) + __half2float(__half(__nv_cvt_fp8_to_halfraw(lo, __NV_E4M3))) / F16MX_SCALE;
+        } else {
+            const __nv_bfloat16* q = reinterpret_cast<const __nv_bfloat16*>(chunk);
+            out[ch] = __bfloat162float(q[k]) + __bfloat162float(q[16 + k]);
         }
-    } else {
-        const __nv_bfloat16* q = reinterpret_cast<const __nv_bfloat16*>(row);
-        for (int ch = 0; ch < 32; ++ch) out[ch] = __bfloat162float(q[ch]) + __bfloat162float(q[32 + ch]);
     }
 }
 extern "C" int rsr_debug_read_node(rsr_ctx* c, int which, float* out, size_t npx) {
@@ -1319,11 +1327,15 @@ __global__ void __launch_bounds__(256) pack_planes_kernel(const float* __restric
         uint32_t hi[16], mid[16];
         #pragma unroll
         for (int k = 0; k < 16; ++k) split_pair(src[2 * k], src[2 * k + 1], hi[k], mid[k]);
+        // two 64-byte K chunks of 16 channels: [16 hi | 16 mid] each (conv_strip.cuh BF16X3 row)
         uint4* dst = reinterpret_cast<uint4*>(planes + ((size_t)cb * npx + px) * 64);
         #pragma unroll
-        for (int k = 0; k < 4; ++k) dst[k] = make_uint4(hi[4 * k], hi[4 * k + 1], hi[4 * k + 2], hi[4 * k + 3]);
-        #pragma unroll
-        for (int k = 0; k < 4; ++k) dst[4 + k] = make_uint4(mid[4 * k], mid[4 * k + 1], mid[4 * k + 2], mid[4 * k + 3]);
+        for (int c = 0; c < 2; ++c) {
+            dst[4 * c + 0] = make_uint4(hi[8 * c], hi[8 * c + 1], hi[8 * c + 2], hi[8 * c + 3]);
+            dst[4 * c + 1] = make_uint4(hi[8 * c + 4], hi[8 * c + 5], hi[8 * c + 6], hi[8 * c + 7]);
+            dst[4 * c + 2] = make_uint4(mid[8 * c], mid[8 * c + 1], mid[8 * c + 2], mid[8 * c + 3]);
+            dst[4 * c + 3] = make_uint4(mid[8 * c + 4], mid[8 * c + 5], mid[8 * c + 6], mid[8 * c + 7]);
+        }
     }
 }
 
@@ -1417,9 +1429,9 @@ extern "C" int rsr_conv2d_3x3_f32(int device, const float* x, const float* weigh
                 for (int ci = 0; ci < cin; ++ci) {
                     __nv_bfloat16 hh, mm;
                     split_bf16(weights[(((size_t)(co0 + o)) * 9 + t) * cin + ci], hh, mm);
-                    const size_t row = (((size_t)(ci / 32) * 9 + t) * n + o) * 64;
-                    pk[row + ci % 32] = hh;
-                    pk[row + 32 + ci % 32] = mm;
+                    const size_t row = (((size_t)(ci / 32) * 9 + t) * n + o) * 64 + ((ci % 32) >> 4) * 32;   // 64-byte chunk of 16 channels
+                    pk[row + (ci & 15)] = hh;
+                    pk[row + 16 + (ci & 15)] = mm;
                 }
     }
     float* d_x = nullptr; float* d_out = nullptr; __nv_bfloat16* d_planes = nullptr; int* d_fault = nullptr;

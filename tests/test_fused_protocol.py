@@ -49,7 +49,7 @@ def test_pair_protocol_random():
         F.PairSim(items, seed=2000 + k, queue_depth=rng.choice([1, 2, 3, 8])).run()
 
 
-@pytest.mark.parametrize("tps,nb,nr1", [(1, 9, 4), (1, 6, 5), (3, 2, 4), (9, 2, 4)])
+@pytest.mark.parametrize("tps,nb,nr1", [(1, 9, 4), (1, 6, 5), (3, 2, 4), (9, 2, 4), (3, 3, 4), (3, 4, 3)])
 def test_pair_protocol_other_ring_geometries(tps, nb, nr1):
     """The build-time variants of the pair kernel (RSR_FUSED_PAIR_TPS / _NB / _NR1) run the same protocol."""
     old = (F.PAIR_TPS, F.PAIR_NB, F.PAIR_NR1)

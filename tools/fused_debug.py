@@ -73,7 +73,7 @@ FP_NAMES = ["a_empty(l1 producer)", "b_empty(weight producer)", "p2_empty(P2 pro
 def profile(mode=4):
     """mode 4: the single-CTA debug kernel (any build).  mode 8: the plan's own kernel, single CTA or CTA pair
     (RSR_B200_PAIR bit 3), in a library built with -DRSR_FUSED_PROF=1 (tools/ablate.sh; RSR_B200_LIB selects it)."""
-    up = R.Upscaler(parameters="imagenet", flags=R.RSR_FLAG_FUSED_MID)
+    up = R.Upscaler(parameters="imagenet", flags=R.RSR_FLAG_FUSED_MID | int(os.environ.get("AB_FLAGS", "0")))
     x = noise_image(1080, 1920, 1234)
     up.forward(x)
     up.debug_fused(mode)

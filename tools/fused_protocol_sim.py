@@ -13,7 +13,7 @@ from __future__ import annotations
 import random
 from collections import deque
 
-NR1, NR2, NB, NT, LOOKAHEAD = 4, 3, 5, 5, 4
+NR1, NR2, NB, NT, LOOKAHEAD = 3, 3, 4, 5, 4   # single-CTA kernel: FusedCfgT<false>
 
 
 class Bar:
@@ -301,7 +301,7 @@ class Sim:
 #     land independently, in either order, some time after the commit retires);
 #   * the epilogue warps of both CTAs arrive on the leader's l2_full / t_empty (count 8).
 # Weight stages hold TPS taps (PAIR_TPS) in a ring of PAIR_NB stages; the l1 ring has PAIR_NR1 slots.
-PAIR_TPS, PAIR_NB, PAIR_NR1 = 3, 3, 4
+PAIR_TPS, PAIR_NB, PAIR_NR1 = 3, 3, 3
 
 
 class PairSim:
