@@ -436,7 +436,7 @@ def bench_config5(R, peaks):
         roof = max(fl / (peaks["bf16_tflops"] * 1e12), by / (peaks["hbm_gbs"] * 1e9)) * 1e3
         rows.append({"C": C, "HW": S, "ms": ms, "tflops_useful": fl / (ms * 1e-3) / 1e12, "gbs_fp32_algorithmic": by / (ms * 1e-3) / 1e9,
                      "roofline_ms": roof, "frac": roof / ms})
-    return {"workload": "3x3 conv, stride 1, zero pad, Cin = Cout = C, fp32 in/out, bf16x3 operands (rsr_conv2d_3x3_f32)", "rows": rows}
+    return {"workload": "3x3 conv, stride 1, zero pad, Cin = Cout = C, fp32 in/out (rsr_conv2d_3x3_f32: C <= 64 fp16 + mxfp8 operands with row-folded MMAs, C >= 128 bf16x3 operands)", "rows": rows}
 
 
 def run_ours(args):
@@ -641,6 +641,7 @@ def run_ours(args):
                     "h2d_bytes_per_step": int(H_LR * W_LR * 3), "d2h_bytes_per_step": int(H_LR * W_LR * 9 * 3),
                     "call": "rsr_submit_u8_rgb / rsr_wait (host u8 RGB -> host u8 RGB = data_to_img, pinned, 3 frames in flight)",
                     "frac_of_value": ms_step / e2e_rgb_ms,
+                    "frac_of_sustained_value": None if ms_sus is None else ms_sus / e2e_rgb_ms,
                     "rgba": {"value": world * OUT_MPIX / (e2e_rgba_ms * 1e-3), "ms_per_step": e2e_rgba_ms, "d2h_bytes_per_step": int(H_LR * W_LR * 9 * 4),
                              "call": "rsr_submit_u8 / rsr_wait (RGBA out: data_to_img(..).to_rgba())"},
                     "unpipelined_ms_per_step": sync_ms_step,

@@ -264,6 +264,7 @@ __global__ void __launch_bounds__(FusedCfg::NTHREADS, 1) conv_fused_mid_kernel(c
     }
     tc_fence_before();
     __syncthreads();
+    if (PAIR) cluster_sync_all();   // both CTAs' cta_group::2 allocations (each may write both tmem_slots) have completed
     tc_fence_after();
     const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
     init_scale_factors<C>(tmem_base, warp);

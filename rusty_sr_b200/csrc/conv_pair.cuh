@@ -95,9 +95,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(C::NTHREADS, 1) conv
     }
     tc_fence_before();
     __syncthreads();
+    // a cta_group::2 allocation is performed for the pair: either CTA's tcgen05.alloc may write the (common) address into
+    // both CTAs' tmem_slot, so read it only after both allocations have completed (compute-sanitizer racecheck, r02)
+    cluster_sync_all();
     tc_fence_after();
     const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
-    init_scale_factors<C>(tmem_base, warp);   // (each CTA its own tensor memory; before the cluster barrier)
+    init_scale_factors<C>(tmem_base, warp);   // (each CTA its own tensor memory; before the second cluster barrier)
     tc_fence_before();
     cluster_sync_all();     // both CTAs' barriers are initialised (and scale factors written) before any cross-CTA signal
     tc_fence_after();

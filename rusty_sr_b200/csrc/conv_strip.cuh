@@ -878,9 +878,10 @@ __global__ void __launch_bounds__(C::NTHREADS, 1) conv_strip_kernel(const __grid
                                 #pragma unroll
                                 for (int c = 0; c < C::KC; ++c) {
                                     if (ABL_NO_MMA) continue;
-                                    if (sp == 0 && c == 0 && i < C::R) {
+                                    if (sp == 0 && c == 0 && i < C::R && cb == 0) {
                                         // the first product that reaches output row i (= r_hi) overwrites its accumulator; the
                                         // rows above it in the same block already hold sums: two MMAs instead of one
+                                        // (further channel blocks of the generic conv accumulate onto the first one's sums)
                                         if (n > 1) MM::head(d, a_e, b_e, c, 128, (n - 1) * C::NCOL, 1);
                                         MM::head(d + (n - 1) * C::NCOL, a_e, b_e + (n - 1) * (C::TAP_BYTES >> 4), c, 128, C::NCOL, 0);
                                     } else {

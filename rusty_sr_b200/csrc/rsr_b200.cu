@@ -1306,36 +1306,38 @@ extern "C" int rsr_downsample_u8(int device, const uint8_t* in, int w, int h, in
 }
 
 // --------------------------------------------------------------- generic 3x3 convolution (config 5 sweep)
-// Same kernel template; the input's Cin/32 channel blocks are stored as planes in the activation format
-// ([cb][H][W][32 hi | 32 mid]) and accumulated in TMEM (ConvParams::n_cb), the output is fp32 [H][W][Cout]
+// Same kernel template; the input's Cin/32 channel blocks are stored as planes in the activation storage format
+// ([cb][H][W][128 B], conv_strip.cuh) and accumulated in TMEM (ConvParams::n_cb), the output is fp32 [H][W][Cout]
 // written 32 channels at a time by the RAW epilogue through a tensor map with a channel coordinate.
-//                        KH KW  RB NG R NR TPS NBS NPIN NOUT SHUF
-using CvN32  = ConvCfg<3, 3, 128, 1, 2, 6, 3, 3, 0, 2, 0>;
-using CvN64  = ConvCfg<3, 3, 128, 2, 2, 6, 2, 3, 0, 2, 0>;
+// Cout <= 64 per call: fp16 + mxfp8 operands and row-folded MMAs (an N <= 64 MMA is bound by its A-tile read, so folding the
+// three vertical taps into one MMA and issuing 2 instead of 3 products per chunk takes these shapes from 41-46 % to the HBM
+// side); wider outputs: bf16x3 operands, N = 128 / 256 MMAs are tensor-bound and the accumulators fill tensor memory.
+//                        KH KW  RB NG R NR TPS NBS NPIN NOUT SHUF NEPI PAIR FOLD PREC
+using CvN32  = ConvCfg<3, 3, 128, 1, 2, 6, 3, 3, 0, 2, 0, 4, false, true, PREC_F16MX>;
+using CvN64  = ConvCfg<3, 3, 128, 2, 2, 6, 3, 3, 0, 2, 0, 4, false, true, PREC_F16MX>;
+using CvB32  = ConvCfg<3, 3, 128, 1, 2, 6, 3, 3, 0, 2, 0>;
+using CvB64  = ConvCfg<3, 3, 128, 2, 2, 6, 2, 3, 0, 2, 0>;
 using CvN128 = ConvCfg<3, 3, 128, 4, 2, 6, 1, 4, 0, 2, 0>;
 using CvN256 = ConvCfg<3, 3, 128, 8, 1, 5, 1, 3, 0, 2, 0>;
 
+template <int PREC>
 __global__ void __launch_bounds__(256) pack_planes_kernel(const float* __restrict__ x, int W, int H, int Ci,
-                                                           __nv_bfloat16* __restrict__ planes) {
-    // one thread = one pixel x one channel block of 32
+                                                           uint8_t* __restrict__ planes) {
+    // one thread = one pixel x one channel block of 32 -> its 128-byte row in storage format PREC
     const size_t npx = (size_t)W * H;
     const int ncb = Ci / 32;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < npx * ncb; i += (size_t)gridDim.x * blockDim.x) {
         const size_t px = i % npx;
         const int cb = (int)(i / npx);
         const float* src = x + px * Ci + cb * 32;
-        uint32_t hi[16], mid[16];
+        float v[32];
         #pragma unroll
-        for (int k = 0; k < 16; ++k) split_pair(src[2 * k], src[2 * k + 1], hi[k], mid[k]);
-        // two 64-byte K chunks of 16 channels: [16 hi | 16 mid] each (conv_strip.cuh BF16X3 row)
-        uint4* dst = reinterpret_cast<uint4*>(planes + ((size_t)cb * npx + px) * 64);
+        for (int k = 0; k < 32; ++k) v[k] = src[k];
+        uint32_t w[32];
+        pack_split_row<PREC>(v, w);
+        uint4* dst = reinterpret_cast<uint4*>(planes + ((size_t)cb * npx + px) * 128);
         #pragma unroll
-        for (int c = 0; c < 2; ++c) {
-            dst[4 * c + 0] = make_uint4(hi[8 * c], hi[8 * c + 1], hi[8 * c + 2], hi[8 * c + 3]);
-            dst[4 * c + 1] = make_uint4(hi[8 * c + 4], hi[8 * c + 5], hi[8 * c + 6], hi[8 * c + 7]);
-            dst[4 * c + 2] = make_uint4(mid[8 * c], mid[8 * c + 1], mid[8 * c + 2], mid[8 * c + 3]);
-            dst[4 * c + 3] = make_uint4(mid[8 * c + 4], mid[8 * c + 5], mid[8 * c + 6], mid[8 * c + 7]);
-        }
+        for (int k = 0; k < 8; ++k) dst[k] = make_uint4(w[4 * k], w[4 * k + 1], w[4 * k + 2], w[4 * k + 3]);
     }
 }
 
@@ -1352,8 +1354,8 @@ static int encode_map(PFN_cuTensorMapEncodeTiled_v12000 enc, CUtensorMap* m, CUt
 }
 
 template <class C>
-static int conv2d_block(PFN_cuTensorMapEncodeTiled_v12000 enc, int num_sms, cudaStream_t st, const __nv_bfloat16* planes,
-                        const __nv_bfloat16* wpack, float* d_out, int W, int H, int Ci, int Co, int co0, int* fault) {
+static int conv2d_block(PFN_cuTensorMapEncodeTiled_v12000 enc, int num_sms, cudaStream_t st, const uint8_t* planes,
+                        const uint8_t* wpack, float* d_out, int W, int H, int Ci, int Co, int co0, int* fault) {
     ConvParams p{};
     p.W = W; p.H = H; p.NIMG = 1; p.row_begin = 0; p.row_end = H; p.fault = fault;
     p.n_cb = Ci / 32;
@@ -1361,13 +1363,13 @@ static int conv2d_block(PFN_cuTensorMapEncodeTiled_v12000 enc, int num_sms, cuda
         cuuint64_t dims[4] = {64, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)p.n_cb};
         cuuint64_t strides[3] = {128, (cuuint64_t)128 * W, (cuuint64_t)128 * W * H};
         cuuint32_t box[4] = {64, (cuuint32_t)C::BOXW, 1, 1};
-        if (int rc = encode_map(enc, &p.tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, planes, dims, strides, box)) return rc;
+        if (int rc = encode_map(enc, &p.tmA, CU_TENSOR_MAP_DATA_TYPE_UINT16, 4, planes, dims, strides, box)) return rc;
     }
     {
         cuuint64_t dims[2] = {64, (cuuint64_t)p.n_cb * 9 * C::NCOL};
         cuuint64_t strides[1] = {128};
         cuuint32_t box[2] = {64, (cuuint32_t)(C::TPS * C::NCOL)};
-        if (int rc = encode_map(enc, &p.tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, wpack, dims, strides, box)) return rc;
+        if (int rc = encode_map(enc, &p.tmB, CU_TENSOR_MAP_DATA_TYPE_UINT16, 2, wpack, dims, strides, box)) return rc;
     }
     for (int g = 0; g < C::NG; ++g) {
         cuuint64_t dims[4] = {(cuuint64_t)Co, (cuuint64_t)W, (cuuint64_t)H, 1};
@@ -1418,24 +1420,24 @@ extern "C" int rsr_conv2d_3x3_f32(int device, const float* x, const float* weigh
         blocks.push_back({co0, n});
         co0 += n;
     }
-    // weights [cout][3][3][cin] -> per block [cb][tap][n][32 hi | 32 mid]
-    std::vector<std::vector<__nv_bfloat16>> packs(blocks.size());
+    // narrow outputs: fp16 + mxfp8 operands, row-folded MMAs (tap blocks stored bottom tap first: tb * 3 + (2 - ta))
+    const bool narrow = cout <= 64;
+    const int prec = narrow ? PREC_F16MX : PREC_BF16X3;
+    // weights [cout][3][3][cin] -> per block [cb][tap block][n][128 B weight row]
+    std::vector<std::vector<uint8_t>> packs(blocks.size());
     for (size_t b = 0; b < blocks.size(); ++b) {
         const int n = blocks[b].n, co0 = blocks[b].co0;
         auto& pk = packs[b];
-        pk.assign((size_t)ncb * 9 * n * 64 + (size_t)n * 64 * 4, __float2bfloat16_rn(0.f));  // tail pad: last stage may over-read
+        pk.assign(((size_t)ncb * 9 * n + (size_t)n * 4) * 128, 0);  // tail pad: last stage may over-read
         for (int o = 0; o < n; ++o)
             for (int t = 0; t < 9; ++t)
-                for (int ci = 0; ci < cin; ++ci) {
-                    __nv_bfloat16 hh, mm;
-                    split_bf16(weights[(((size_t)(co0 + o)) * 9 + t) * cin + ci], hh, mm);
-                    const size_t row = (((size_t)(ci / 32) * 9 + t) * n + o) * 64 + ((ci % 32) >> 4) * 32;   // 64-byte chunk of 16 channels
-                    pk[row + (ci & 15)] = hh;
-                    pk[row + 16 + (ci & 15)] = mm;
+                for (int cb = 0; cb < ncb; ++cb) {
+                    const int blk = narrow ? (t % 3) * 3 + (2 - t / 3) : t;
+                    pack_weight_row(&weights[(((size_t)(co0 + o)) * 9 + t) * cin + cb * 32], &pk[(((size_t)cb * 9 + blk) * n + o) * 128], prec);
                 }
     }
-    float* d_x = nullptr; float* d_out = nullptr; __nv_bfloat16* d_planes = nullptr; int* d_fault = nullptr;
-    std::vector<__nv_bfloat16*> d_w(blocks.size(), nullptr);
+    float* d_x = nullptr; float* d_out = nullptr; uint8_t* d_planes = nullptr; int* d_fault = nullptr;
+    std::vector<uint8_t*> d_w(blocks.size(), nullptr);
     cudaStream_t st = nullptr;
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     int rc = 0;
@@ -1456,13 +1458,14 @@ extern "C" int rsr_conv2d_3x3_f32(int device, const float* x, const float* weigh
     CV_TRY(cudaMalloc((void**)&d_fault, 64 * sizeof(int)));   // fault code + per-warp records (ptx.cuh mbar_wait)
     CV_TRY(cudaMemsetAsync(d_fault, 0, 64 * sizeof(int), st));
     for (size_t b = 0; b < blocks.size(); ++b) {
-        CV_TRY(cudaMalloc((void**)&d_w[b], packs[b].size() * 2));
-        CV_TRY(cudaMemcpyAsync(d_w[b], packs[b].data(), packs[b].size() * 2, cudaMemcpyHostToDevice, st));
+        CV_TRY(cudaMalloc((void**)&d_w[b], packs[b].size()));
+        CV_TRY(cudaMemcpyAsync(d_w[b], packs[b].data(), packs[b].size(), cudaMemcpyHostToDevice, st));
     }
     CV_TRY(cudaMemcpyAsync(d_x, x, npx * cin * sizeof(float), cudaMemcpyHostToDevice, st));
     {
         const int nblk = (int)std::min<size_t>((npx * ncb + 255) / 256, (size_t)prop.multiProcessorCount * 16);
-        pack_planes_kernel<<<nblk, 256, 0, st>>>(d_x, w, h, cin, d_planes);
+        if (narrow) pack_planes_kernel<PREC_F16MX><<<nblk, 256, 0, st>>>(d_x, w, h, cin, d_planes);
+        else        pack_planes_kernel<PREC_BF16X3><<<nblk, 256, 0, st>>>(d_x, w, h, cin, d_planes);
         CV_TRY(cudaGetLastError());
     }
     for (int it = 0; it < iters + 1; ++it) {   // first round is a warm-up
@@ -1471,8 +1474,10 @@ extern "C" int rsr_conv2d_3x3_f32(int device, const float* x, const float* weigh
             const int n = blocks[b].n, co0 = blocks[b].co0;
             if (n == 256)      rc = conv2d_block<CvN256>(enc, prop.multiProcessorCount, st, d_planes, d_w[b], d_out, w, h, cin, cout, co0, d_fault);
             else if (n == 128) rc = conv2d_block<CvN128>(enc, prop.multiProcessorCount, st, d_planes, d_w[b], d_out, w, h, cin, cout, co0, d_fault);
-            else if (n == 64)  rc = conv2d_block<CvN64>(enc, prop.multiProcessorCount, st, d_planes, d_w[b], d_out, w, h, cin, cout, co0, d_fault);
-            else               rc = conv2d_block<CvN32>(enc, prop.multiProcessorCount, st, d_planes, d_w[b], d_out, w, h, cin, cout, co0, d_fault);
+            else if (n == 64)  rc = narrow ? conv2d_block<CvN64>(enc, prop.multiProcessorCount, st, d_planes, d_w[b], d_out, w, h, cin, cout, co0, d_fault)
+                                           : conv2d_block<CvB64>(enc, prop.multiProcessorCount, st, d_planes, d_w[b], d_out, w, h, cin, cout, co0, d_fault);
+            else               rc = narrow ? conv2d_block<CvN32>(enc, prop.multiProcessorCount, st, d_planes, d_w[b], d_out, w, h, cin, cout, co0, d_fault)
+                                           : conv2d_block<CvB32>(enc, prop.multiProcessorCount, st, d_planes, d_w[b], d_out, w, h, cin, cout, co0, d_fault);
             if (rc) { cleanup(); return rc; }
         }
     }

@@ -84,3 +84,20 @@ def noise_image(H, W, seed):
     """Uniform-random u8 RGB as f32 /255."""
     rng = np.random.default_rng(seed)
     return (rng.integers(0, 256, size=(H, W, 3), dtype=np.uint8).astype(np.float32) / 255.0)
+
+
+def synthetic_params(base: np.ndarray, factor: int, seed: int = 1234) -> np.ndarray:
+    """Parameters of sr_net(factor, None) for a factor the reference ships no weights for: every layer that does not depend
+    on the factor is taken from `base` (a factor-3 vector); conv7 / conv9 / conv10 and expand_bias (3 * factor^2 output
+    channels, network.rs:37-38,67,70,72) are drawn from N(0, sigma) with the sigma of the corresponding bundled tensor."""
+    import rusty_sr_b200 as R
+    src = {s.name: s for s in R.param_layout(3)}
+    rng = np.random.default_rng(seed)
+    out = np.empty(R.num_params(factor), np.float32)
+    for s in R.param_layout(factor):
+        b = base[src[s.name].offset:src[s.name].offset + src[s.name].count]
+        if s.count == src[s.name].count:
+            out[s.offset:s.offset + s.count] = b
+        else:
+            out[s.offset:s.offset + s.count] = rng.normal(0.0, float(b.std()), s.count).astype(np.float32)
+    return out

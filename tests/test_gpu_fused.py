@@ -40,6 +40,17 @@ def test_launch_plans(pair):
     assert f["anime"].last_launch_count() == 5 and s["anime"].last_launch_count() == 6
 
 
+@pytest.mark.parametrize("width,launches", [(100, 5), (124, 5), (125, 6), (128, 6), (248, 5), (256, 6), (260, 5), (372, 5), (384, 5), (1000, 5)])
+def test_default_plan_is_chosen_by_width(R, weights, width, launches):
+    """Without a plan flag the middle levels run fused unless the 124-pixel strips of the fused launch waste too much against
+    the 128-pixel strips of the split launches (e.g. BASELINE config 3's 256-wide patches: 3 strips vs 2)."""
+    x = noise_image(6, width, width)
+    with R.Upscaler(weights["anime"]) as u, R.Upscaler(weights["anime"], flags=R.RSR_FLAG_SPLIT_MID) as s:
+        out = u.forward(x)
+        assert u.last_launch_count() == launches, u.plan()
+        assert np.abs(out - s.forward(x)).max() < 1e-4
+
+
 @pytest.mark.parametrize("wname", ["imagenet", "imagenetlinear", "anime"])
 @pytest.mark.parametrize("case", ["cartoon", "butterfly", "kat", "noise256"])
 def test_fused_parity(pair, weights, wname, case):
