@@ -491,22 +491,29 @@ def run_ours(args):
         mark("timed_region")
         ms_step = timed(torch, stream, D, counted_step, args.steps)
         mark("timed_region")
+        # per-kernel durations (CUDA events the library records on the same stream around every launch), first in the same
+        # (burst) regime as `value`, then again right after the sustained loop (power-capped clocks)
+        def kernel_breakdown():
+            runs = []
+            up.set_kernel_timing(True)      # events between the launches: serialises them, so only for this breakdown
+            for i in range(min(args.steps, 10)):
+                step(i)
+                runs.append(up.last_kernel_times_ms())
+            up.set_kernel_timing(False)
+            kt = {k: statistics.mean(r[k] for r in runs) for k in runs[0]}
+            if up.last_launch_count() == 5:      # conv5|6|7 and conv8|9 run as one launch (conv_fused.cuh)
+                kt["conv5|6|7+conv8|9 (fused)"] = kt.pop("conv5|6|7") + kt.pop("conv8|9")
+            return kt
+
+        ktimes = kernel_breakdown()
+        plan = up.plan()
         n_sus = max(args.steps, int(args.sustain_s * 1e3 / ms_step)) if args.sustain_s > 0 else 0
-        ms_sus = None
+        ms_sus, ktimes_sus = None, None
         if n_sus:
             mark("sustained")
             ms_sus = timed(torch, stream, D, step, n_sus)
             mark("sustained")
-        # per-kernel durations (CUDA events the library records on the same stream around every launch)
-        kt_runs = []
-        for i in range(min(args.steps, 10)):
-            step(i)
-            kt_runs.append(up.last_kernel_times_ms())
-        ktimes = {k: statistics.mean(r[k] for r in kt_runs) for k in kt_runs[0]}
-        fused = up.last_launch_count() == 5      # conv5|6|7 and conv8|9 run as one launch (conv_fused.cuh)
-        plan = up.plan()
-        if fused:
-            ktimes["conv5|6|7+conv8|9 (fused)"] = ktimes.pop("conv5|6|7") + ktimes.pop("conv8|9")
+            ktimes_sus = kernel_breakdown()
     value = world * OUT_MPIX / (ms_step * 1e-3)
 
     # ---- end to end through the host calls, pinned buffers ---------------------------------------
@@ -630,6 +637,7 @@ def run_ours(args):
                                  f"{mma_per_chunk}x that (operand split), so the ceiling of this formulation is 1/{mma_per_chunk}",
                          "executed_frac": mma_per_chunk * achieved_tf / peaks["bf16_tflops_burst"]},
             "kernel_ms": ktimes,
+            "kernel_ms_after_sustained_loop": ktimes_sus,
             "per_launch_roofline": per_launch,
             "reference_layer_roofline": {"ms": ref_roof, "frac": ref_roof / ms_step,
                                          "frac_sustained": None if ms_sus is None else ref_roof / ms_sus,

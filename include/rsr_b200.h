@@ -180,7 +180,10 @@ int rsr_set_stream(rsr_ctx* ctx, void* cuda_stream);
 
 /* Per-kernel device times (ms, CUDA events on the launching stream) of the most recent call,
  * in launch order: pack, conv0, conv1|2|3, conv5|6|7, conv8|9, conv10+expand.  Synchronises.
- * Returns the number of entries written (<= cap) or a negative error. */
+ * Returns the number of entries written (<= cap) or a negative error; 0 unless rsr_set_kernel_timing(ctx, 1)
+ * was called before the forward pass.  Timing is off by default: the events between the launches would serialise them,
+ * and the conv launches are chained with programmatic dependent launch (each sets itself up under its predecessor's tail). */
+int rsr_set_kernel_timing(rsr_ctx* ctx, int enable);
 int rsr_last_kernel_times(rsr_ctx* ctx, float* ms, int cap);
 /* Names matching rsr_last_kernel_times entries. */
 const char* rsr_kernel_name(int index);

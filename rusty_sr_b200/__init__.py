@@ -210,6 +210,11 @@ class Upscaler:
     def synchronize(self) -> None:
         _lib.check(self._L.rsr_synchronize(self._h))
 
+    def set_kernel_timing(self, enable: bool = True) -> None:
+        """Record CUDA events around every launch so that last_kernel_times_ms() has data (off by default: the events
+        serialise the launches, which otherwise overlap through programmatic dependent launch)."""
+        _lib.check(self._L.rsr_set_kernel_timing(self._h, int(enable)))
+
     def last_kernel_times_ms(self) -> dict:
         buf = (ctypes.c_float * 16)()
         n = self._L.rsr_last_kernel_times(self._h, buf, 16)

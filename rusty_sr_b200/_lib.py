@@ -31,7 +31,7 @@ EXPORTS = (
     "rsr_debug_profile", "rsr_debug_read_profile", "rsr_debug_fused", "rsr_debug_read_fused_profile",
     "rsr_bilinear_f32", "rsr_bilinear_u8", "rsr_downsample_f32", "rsr_downsample_u8", "rsr_conv2d_3x3_f32",
     "rsr_upscale_u8_rgb", "rsr_upscale_device_u8_rgb", "rsr_upscale_band_device_f32", "rsr_upscale_band_device_u8",
-    "rsr_submit_u8_rgb", "rsr_rsr_encoded_size", "rsr_rsr_encode", "rsr_rsr_decode", "rsr_debug_create",
+    "rsr_submit_u8_rgb", "rsr_rsr_encoded_size", "rsr_rsr_encode", "rsr_rsr_decode", "rsr_debug_create", "rsr_set_kernel_timing",
 )
 
 _lib = None
@@ -98,6 +98,8 @@ def load() -> ctypes.CDLL:
     L.rsr_multi_upscale_frame_u8.argtypes = [vp, vp, ci, ci, ci, vp]
     L.rsr_set_stream.argtypes = [vp, vp]
     L.rsr_last_kernel_times.argtypes = [vp, fp, ci]
+    L.rsr_set_kernel_timing.argtypes = [vp, ci]
+    L.rsr_set_kernel_timing.restype = ci
     L.rsr_kernel_name.restype = ctypes.c_char_p
     L.rsr_kernel_name.argtypes = [ci]
     L.rsr_last_launch_count.argtypes = [vp]

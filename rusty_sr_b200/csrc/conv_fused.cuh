@@ -273,6 +273,8 @@ __global__ void __launch_bounds__(FusedCfg::NTHREADS, 1) conv_fused_mid_kernel(c
         cluster_sync_all();
         tc_fence_after();
     }
+    griddep_launch_dependents();   // programmatic dependent launch (see conv_strip.cuh)
+    griddep_wait();
 
     // work ranges are per cluster (pair) or per CTA
     const long long nrange = PAIR ? gridDim.x >> 1 : gridDim.x, irange = PAIR ? blockIdx.x >> 1 : blockIdx.x;

@@ -104,6 +104,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(C::NTHREADS, 1) conv
     tc_fence_before();
     cluster_sync_all();     // both CTAs' barriers are initialised (and scale factors written) before any cross-CTA signal
     tc_fence_after();
+    griddep_launch_dependents();   // programmatic dependent launch (see conv_strip.cuh)
+    griddep_wait();
 
     PairIter it;
     {

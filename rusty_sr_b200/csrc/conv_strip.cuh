@@ -735,6 +735,10 @@ __global__ void __launch_bounds__(C::NTHREADS, 1) conv_strip_kernel(const __grid
     tc_fence_after();
     const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);  // warp-uniform for the compiler
     init_scale_factors<C>(tmem_base, warp);
+    // programmatic dependent launch: everything above (barriers, tensor memory, scale factors, descriptor prefetch) may run
+    // under the previous launch's tail; its results are needed from here on.  The next launch may be set up at once.
+    griddep_launch_dependents();
+    griddep_wait();
 
     // All role loops below are executed by the whole warp with warp-uniform control flow; only the
     // TMA / MMA / commit instructions themselves are issued by one lane, chosen with elect.sync —

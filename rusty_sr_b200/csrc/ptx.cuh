@@ -83,6 +83,13 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int* g
     }
 }
 
+// ------------------------------------------------------------------ programmatic dependent launch
+// A kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization may start while its predecessor in the stream is
+// still running (as soon as every CTA of the predecessor has executed griddep_launch_dependents or exited); it must call
+// griddep_wait before touching memory the predecessor reads or writes.  Both are no-ops in an ordinary launch.
+__device__ __forceinline__ void griddep_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 // ------------------------------------------------------------------ TMA
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* m) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");

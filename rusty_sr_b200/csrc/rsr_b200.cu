@@ -213,6 +213,7 @@ template <bool U8>
 __global__ void __launch_bounds__(256) pack_input_kernel(const void* __restrict__ in, int in_ch, int W, int H,
                                                           int NIMG, __nv_bfloat16* __restrict__ xcol,
                                                           float4* __restrict__ xf4) {
+    griddep_launch_dependents();                          // conv0 may be set up while this kernel runs (it waits before reading xcol)
     const int lane = threadIdx.x & 31;
     const int segs = (W + 27) / 28;                       // warp segments per row
     const long long nseg = (long long)NIMG * H * segs;
@@ -280,6 +281,7 @@ struct rsr_ctx {
     int* fault = nullptr;       // device alias of fault_host (mapped pinned memory: readable after a kernel trap)
     int* fault_host = nullptr;  // [0] = code, [4 + 4*warp ..] = which barrier each warp role was stuck on
     cudaEvent_t ev[K_COUNT + 1] = {};
+    bool kernel_timing = false; // record CUDA events around every launch (rsr_set_kernel_timing): costs the launch overlap
     bool timed = false;
     int last_launches = 0;
     int stop_after = -1;  // test hook
@@ -645,6 +647,36 @@ static int make_map_w(rsr_ctx* c, CUtensorMap* m, const void* base, int row_byte
     return 0;
 }
 
+// One kernel launch: optional cluster of 2 CTAs, optional programmatic dependent launch (the kernel calls griddep_wait before it
+// touches the previous launch's data, so its prologue overlaps that launch's tail).
+template <class P>
+static int launch_kernel(void (*kernel)(P), int grid, int block, int smem, cudaStream_t stream, bool pair, bool pdl, const P& params) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(block);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute at[2];
+    int na = 0;
+    if (pair) {
+        at[na].id = cudaLaunchAttributeClusterDimension;
+        at[na].val.clusterDim.x = 2; at[na].val.clusterDim.y = 1; at[na].val.clusterDim.z = 1;
+        ++na;
+    }
+#ifdef RSR_NO_PDL   // lab builds: A/B of the launch overlap
+    pdl = false;
+#endif
+    if (pdl) {
+        at[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        at[na].val.programmaticStreamSerializationAllowed = 1;
+        ++na;
+    }
+    cfg.attrs = at;
+    cfg.numAttrs = na;
+    CUDA_TRY(cudaLaunchKernelEx(&cfg, kernel, params));
+    return 0;
+}
+
 // CTA-pair launch (conv_pair.cuh): p.tmB must have been built with a box of NCOL / 2 rows (one CTA's half tap).
 template <class C>
 static int launch_conv_pair(rsr_ctx* c, ConvParams& p, int kindex) {
@@ -653,8 +685,7 @@ static int launch_conv_pair(rsr_ctx* c, ConvParams& p, int kindex) {
     const int ncl = (int)std::min<long long>(p.total_rowtiles, c->num_sms / 2);
     p.prof = nullptr;
     c->prof_grid[kindex] = 0;
-    conv_pair_kernel<C><<<2 * ncl, C::NTHREADS, C::SMEM_BYTES, c->stream>>>(p);
-    CUDA_TRY(cudaGetLastError());
+    if (int rc = launch_kernel(conv_pair_kernel<C>, 2 * ncl, C::NTHREADS, C::SMEM_BYTES, c->stream, true, !c->kernel_timing, p)) return rc;
     c->last_launches++;
     return 0;
 }
@@ -665,8 +696,7 @@ static int launch_conv(rsr_ctx* c, ConvParams& p, int kindex) {
     const int grid = (int)std::min<long long>(p.total_rowtiles, c->num_sms);
     p.prof = (c->prof && grid <= 256) ? c->prof + (size_t)kindex * 256 * 16 : nullptr;
     c->prof_grid[kindex] = grid;
-    conv_strip_kernel<C><<<grid, C::NTHREADS, C::SMEM_BYTES, c->stream>>>(p);
-    CUDA_TRY(cudaGetLastError());
+    if (int rc = launch_kernel(conv_strip_kernel<C>, grid, C::NTHREADS, C::SMEM_BYTES, c->stream, false, !c->kernel_timing, p)) return rc;
     c->last_launches++;
     return 0;
 }
@@ -722,7 +752,7 @@ static int forward_impl(rsr_ctx* c, const void* d_in, bool u8, int in_ch, int n,
                 *l2_slope = V + 160, *l3_bias = V + 192, *l3_slope = V + 224, *e_bias = V + 256;
 
     c->last_launches = 0;
-    CUDA_TRY(cudaEventRecord(c->ev[0], c->stream));
+    if (c->kernel_timing) CUDA_TRY(cudaEventRecord(c->ev[0], c->stream));
     {
         const long long nseg = (long long)n * h * ((w + 27) / 28);
         const int blocks = (int)std::min<long long>((nseg + 7) / 8, (long long)c->num_sms * 16);
@@ -731,7 +761,7 @@ static int forward_impl(rsr_ctx* c, const void* d_in, bool u8, int in_ch, int n,
         CUDA_TRY(cudaGetLastError());
         c->last_launches++;
     }
-    CUDA_TRY(cudaEventRecord(c->ev[1], c->stream));
+    if (c->kernel_timing) CUDA_TRY(cudaEventRecord(c->ev[1], c->stream));
     if (c->stop_after == 0) return 0;
 
     ConvParams p{};
@@ -754,7 +784,7 @@ static int forward_impl(rsr_ctx* c, const void* d_in, bool u8, int in_ch, int n,
     if (int rc = in_map(&p.tmOut[0], f_act, 32)) return rc;
     set_groups({EpiGroup{EPI_ACT, 0, f_bias, f_slope, 0, 0}});
     if (int rc = launch_conv<typename N::C0>(c, p, 1)) return rc;
-    CUDA_TRY(cudaEventRecord(c->ev[2], c->stream));
+    if (c->kernel_timing) CUDA_TRY(cudaEventRecord(c->ev[2], c->stream));
     if (c->stop_after == 1) return 0;
 
     // f -> l1 = BeLU(conv1(f) + l1_bias); P2 = conv2(f); P3 = conv3(f)  network.rs:60-62,50,54
@@ -767,7 +797,7 @@ static int forward_impl(rsr_ctx* c, const void* d_in, bool u8, int in_ch, int n,
                 EpiGroup{EPI_RAW, 0, nullptr, nullptr, 0, 0}});
     if (pair(2)) { if (int rc = launch_conv_pair<typename N::P1>(c, p, 2)) return rc; }
     else         { if (int rc = launch_conv<typename N::C1>(c, p, 2)) return rc; }
-    CUDA_TRY(cudaEventRecord(c->ev[3], c->stream));
+    if (c->kernel_timing) CUDA_TRY(cudaEventRecord(c->ev[3], c->stream));
     if (c->stop_after == 2) return 0;
 
     if constexpr (NGE == 1) {
@@ -814,29 +844,20 @@ static int forward_impl(rsr_ctx* c, const void* d_in, bool u8, int in_ch, int n,
             CUDA_TRY(cudaMemsetAsync(c->dbg_prof.p, 0, 256 * FPROF_N * sizeof(long long), c->stream));
             q.prof = (long long*)c->dbg_prof.p;
         }
+        const bool pdl = !c->kernel_timing;
         if (fpair) {
             const int ncl = (int)std::min<long long>(q.total_rowtiles, c->num_sms / 2);
-            cudaLaunchConfig_t cfg{};
-            cfg.gridDim = dim3(2 * ncl);
-            cfg.blockDim = dim3(FusedCfg::NTHREADS);
-            cfg.dynamicSmemBytes = FusedCfgT<true, PREC>::SMEM_BYTES;
-            cfg.stream = c->stream;
-            cudaLaunchAttribute at[1];
-            at[0].id = cudaLaunchAttributeClusterDimension;
-            at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-            cfg.attrs = at;
-            cfg.numAttrs = 1;
-            CUDA_TRY(cudaLaunchKernelEx(&cfg, conv_fused_mid_kernel<false, true, PREC>, q));
+            if (int rc = launch_kernel(conv_fused_mid_kernel<false, true, PREC>, 2 * ncl, FusedCfg::NTHREADS, FusedCfgT<true, PREC>::SMEM_BYTES, c->stream, true, pdl, q)) return rc;
         } else {
             const int grid = (int)std::min<long long>(q.total_rowtiles, c->num_sms);
-            if (c->fused_dbg & 7) conv_fused_mid_kernel<true, false, PREC><<<grid, FusedCfg::NTHREADS, FusedCfgT<false, PREC>::SMEM_BYTES, c->stream>>>(q);
-            else conv_fused_mid_kernel<false, false, PREC><<<grid, FusedCfg::NTHREADS, FusedCfgT<false, PREC>::SMEM_BYTES, c->stream>>>(q);
+            if (c->fused_dbg & 7) { if (int rc = launch_kernel(conv_fused_mid_kernel<true, false, PREC>, grid, FusedCfg::NTHREADS, FusedCfgT<false, PREC>::SMEM_BYTES, c->stream, false, pdl, q)) return rc; }
+            else { if (int rc = launch_kernel(conv_fused_mid_kernel<false, false, PREC>, grid, FusedCfg::NTHREADS, FusedCfgT<false, PREC>::SMEM_BYTES, c->stream, false, pdl, q)) return rc; }
         }
         CUDA_TRY(cudaGetLastError());
         c->last_launches++;
         // reported in the conv5|6|7 slot of rsr_last_kernel_times; the conv8|9 slot then reads ~0
-        CUDA_TRY(cudaEventRecord(c->ev[4], c->stream));
-        CUDA_TRY(cudaEventRecord(c->ev[5], c->stream));
+        if (c->kernel_timing) CUDA_TRY(cudaEventRecord(c->ev[4], c->stream));
+        if (c->kernel_timing) CUDA_TRY(cudaEventRecord(c->ev[5], c->stream));
         if (c->stop_after == 3 || c->stop_after == 4) return 0;
     }
     }
@@ -855,7 +876,7 @@ static int forward_impl(rsr_ctx* c, const void* d_in, bool u8, int in_ch, int n,
         set_groups({EpiGroup{EPI_ACT, 1, l2_bias, l2_slope, 0, 0}, EpiGroup{EPI_RAW, 1, nullptr, nullptr, 0, 0},
                     EpiGroup{EPI_RAW, 0, nullptr, nullptr, 0, 0}, NGE == 2 ? EpiGroup{EPI_RAW, 0, nullptr, nullptr, 0, 0} : none});
         if (int rc = launch_conv<typename N::C2>(c, p, 3)) return rc;
-        CUDA_TRY(cudaEventRecord(c->ev[4], c->stream));
+        if (c->kernel_timing) CUDA_TRY(cudaEventRecord(c->ev[4], c->stream));
         if (c->stop_after == 3) return 0;
 
         // l2 -> l3 = BeLU(P3 + conv8(l2) + l3_bias); E += conv9(l2)                  :69-70,52,56
@@ -870,7 +891,7 @@ static int forward_impl(rsr_ctx* c, const void* d_in, bool u8, int in_ch, int n,
         set_groups({EpiGroup{EPI_ACT, 1, l3_bias, l3_slope, 0, 0}, EpiGroup{EPI_RAW, 1, nullptr, nullptr, 0, 0},
                     NGE == 2 ? EpiGroup{EPI_RAW, 1, nullptr, nullptr, 0, 0} : none});
         if (int rc = launch_conv<typename N::C3>(c, p, 4)) return rc;
-        CUDA_TRY(cudaEventRecord(c->ev[5], c->stream));
+        if (c->kernel_timing) CUDA_TRY(cudaEventRecord(c->ev[5], c->stream));
         if (c->stop_after == 4) return 0;
     }
 
@@ -887,8 +908,8 @@ static int forward_impl(rsr_ctx* c, const void* d_in, bool u8, int in_ch, int n,
     p.out_u8_ch = o.u8_ch;
     p.out_vec_ok = ((w * F) % 4 == 0) && ((reinterpret_cast<uintptr_t>(o.f32 ? (void*)o.f32 : (void*)o.u8) & 15) == 0);
     if (int rc = launch_conv<typename N::C4>(c, p, 5)) return rc;
-    CUDA_TRY(cudaEventRecord(c->ev[6], c->stream));
-    c->timed = true;
+    if (c->kernel_timing) CUDA_TRY(cudaEventRecord(c->ev[6], c->stream));
+    c->timed = c->kernel_timing;
     return 0;
 }
 
@@ -1055,6 +1076,12 @@ extern "C" int rsr_upscale_band_u8(rsr_ctx* c, const uint8_t* in_rows, int w, in
     return upscale_host(c, in_rows, true, in_channels, 1, w, rows_in, out_rows_rgba, 4, top_halo, bottom_halo);
 }
 
+extern "C" int rsr_set_kernel_timing(rsr_ctx* c, int enable) {
+    if (!c) return fail(RSR_E_BAD_ARG, "ctx is null");
+    c->kernel_timing = enable != 0;
+    if (!enable) c->timed = false;
+    return 0;
+}
 extern "C" int rsr_last_kernel_times(rsr_ctx* c, float* ms, int cap) {
     if (!c || !ms) return fail(RSR_E_BAD_ARG, "null argument");
     if (!c->timed) return 0;

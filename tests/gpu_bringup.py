@@ -53,6 +53,7 @@ def stage_check(params, x, label):
             print(f"    bad pixels: {bad.sum()} of {bad.size}; y range {ys.min()}..{ys.max()} x range {xs.min()}..{xs.max()}")
             break
     up.debug_stop_after(-1)
+    up.set_kernel_timing(True)
     t = time.time()
     out = up.forward(x)
     dt = time.time() - t
@@ -82,6 +83,7 @@ def fused_check(params, x, label):
             print(f"    bad pixels: {bad.sum()} of {bad.size}; y {ys.min()}..{ys.max()} x {xs.min()}..{xs.max()};"
                   f" bad columns mod 124: {sorted(set((xs % 124).tolist()))[:20]}")
         up.debug_stop_after(-1)
+        up.set_kernel_timing(True)
         out = up.forward(x)
         launches = up.last_launch_count()
         times = up.last_kernel_times_ms()

@@ -17,6 +17,7 @@ W, H = int(os.environ.get("AB_W", 1920)), int(os.environ.get("AB_H", 1080))
 rng = np.random.default_rng(1234)
 x = (rng.integers(0, 256, size=(H, W, 3), dtype=np.uint8).astype(np.float32) / 255.0)
 up = R.Upscaler(parameters="imagenet", flags=int(os.environ.get("AB_FLAGS", "0")))
+up.set_kernel_timing(True)
 acc = {}
 for i in range(steps + 1):
     up.forward(x)

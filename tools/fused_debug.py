@@ -75,6 +75,7 @@ def profile(mode=4):
     (RSR_B200_PAIR bit 3), in a library built with -DRSR_FUSED_PROF=1 (tools/ablate.sh; RSR_B200_LIB selects it)."""
     up = R.Upscaler(parameters="imagenet", flags=R.RSR_FLAG_FUSED_MID | int(os.environ.get("AB_FLAGS", "0")))
     x = noise_image(1080, 1920, 1234)
+    up.set_kernel_timing(True)
     up.forward(x)
     up.debug_fused(mode)
     up.forward(x)

@@ -17,6 +17,7 @@ rng = np.random.default_rng(1234)
 x = torch.from_numpy(rng.integers(0, 256, size=(H, W, 3), dtype=np.uint8).astype(np.float32) / 255.0).cuda()
 out = torch.empty((3 * H, 3 * W, 3), dtype=torch.float32, device="cuda")
 up = R.Upscaler(parameters="imagenet")
+up.set_kernel_timing(os.environ.get("PROFILE_TIMING", "1") == "1")   # PROFILE_TIMING=0: launches overlap as in production
 for _ in range(steps):
     up.forward_device(x.data_ptr(), 1, W, H, d_out_f32=out.data_ptr())
 up.synchronize()

@@ -13,6 +13,7 @@ W, H = (int(sys.argv[1]), int(sys.argv[2])) if len(sys.argv) > 2 else (1920, 108
 rng = np.random.default_rng(1234)
 x = rng.integers(0, 256, size=(H, W, 3), dtype=np.uint8).astype(np.float32) / 255.0
 up = R.Upscaler(parameters="imagenet")
+up.set_kernel_timing(True)
 up.forward(x)
 up.debug_profile(True)
 up.forward(x)
