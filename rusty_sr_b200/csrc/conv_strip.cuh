@@ -256,6 +256,20 @@ __device__ __forceinline__ void split_pair_f16mx(float v0, float v1, uint32_t& h
 __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
     asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
+// explicit shared-space accesses for the staging tiles (pointers derived from the aligned dynamic-smem base are generic to the compiler)
+__device__ __forceinline__ void st_shared_b32(uint32_t addr, uint32_t v) {
+    asm volatile("st.shared.b32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_shared_b32(uint32_t addr) {
+    uint32_t v;
+    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+    return v;
+}
+__device__ __forceinline__ uint4 ld_shared_v4(uint32_t addr) {
+    uint4 v;
+    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
+    return v;
+}
 
 // A pixel's 128-byte row as 8 chunks of 16 bytes, written at `row` (shared-memory address of the row inside a tile laid out
 // with the 128-byte TMA swizzle: chunk j of row r sits at chunk j ^ (r & 7)); sw = r & 7.
@@ -357,17 +371,42 @@ __device__ __forceinline__ void epi_split_to_stage(const EpiGroup& g, float (&v)
 struct SkipNb {
     float v[3][3][3];
 };
-__device__ __forceinline__ void load_skip_nb(const ConvParams& p, int img, int y, int x, SkipNb& nb) {
+// What one lane fetches of it: its own pixel column (rows y-1, y, y+1) — the left / right columns come from the neighbouring
+// lanes by shuffle — plus, in lanes 0 and 31 only, the column just outside the warp's 32 pixels.  6 load instructions per
+// tile instead of 9, few enough registers (18) to prefetch a whole pass ahead.
+struct SkipCol {
+    float v[3][3], e[3][3];
+};
+__device__ __forceinline__ void load_skip_col(const ConvParams& p, int img, int y, int x, int lane, SkipCol& c) {
     const int W = p.W, H = p.H;
     const int ys[3] = {max(y - 1, 0), y, min(y + 1, H - 1)};
-    const int xs[3] = {max(x - 1, 0), x, min(x + 1, W - 1)};
+    const int xo = min(x, W - 1);                                        // lanes past the image edge clamp (they serve as
+    const int xe = lane == 0 ? max(x - 1, 0) : min(x + 1, W - 1);        // right neighbour of the last pixel)
     const float4* xi = p.xf4 + (size_t)img * H * W;
+    #pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        const float4 t = __ldg(xi + (size_t)ys[a] * W + xo);
+        c.v[a][0] = t.x; c.v[a][1] = t.y; c.v[a][2] = t.z;
+    }
+    if (lane == 0 || lane == 31) {
+        #pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            const float4 t = __ldg(xi + (size_t)ys[a] * W + xe);
+            c.e[a][0] = t.x; c.e[a][1] = t.y; c.e[a][2] = t.z;
+        }
+    }
+}
+// whole warp
+__device__ __forceinline__ void expand_skip(const SkipCol& c, int lane, SkipNb& nb) {
     #pragma unroll
     for (int a = 0; a < 3; ++a)
         #pragma unroll
-        for (int b = 0; b < 3; ++b) {
-            const float4 t = __ldg(xi + (size_t)ys[a] * W + xs[b]);
-            nb.v[a][b][0] = t.x; nb.v[a][b][1] = t.y; nb.v[a][b][2] = t.z;
+        for (int ch = 0; ch < 3; ++ch) {
+            const float m = c.v[a][ch];
+            float l = __shfl_up_sync(0xffffffffu, m, 1), r = __shfl_down_sync(0xffffffffu, m, 1);
+            if (lane == 0) l = c.e[a][ch];
+            if (lane == 31) r = c.e[a][ch];
+            nb.v[a][0][ch] = l; nb.v[a][1][ch] = m; nb.v[a][2][ch] = r;
         }
 }
 
@@ -409,14 +448,13 @@ __device__ __forceinline__ uint32_t quant_u8(float v) {   // data_to_img (main.r
 // The image store of the last launch for one warp = 32 LR pixels of LR row y: F output rows of 32 * F pixels each, staged
 // in the warp's 4 KB tile `stg` and written with coalesced (vector where aligned) stores as f32 RGB, u8 RGBA or u8 RGB.
 template <int F, int NV>
-__device__ __forceinline__ void epi_shuffle_store(const ConvParams& p, const float (&v)[NV], const SkipNb& nb, uint8_t* stg, int img,
+__device__ __forceinline__ void epi_shuffle_store(const ConvParams& p, const float (&v)[NV], const SkipNb& nb, uint32_t stg, int img,
                                                   int y, int xw, int lane) {
     const int npx_valid = min(32, p.W - xw);
     const size_t OW = (size_t)p.W * F;                                              // output pixels per row
     const size_t opx0 = ((size_t)img * p.out_rows * F + (size_t)(y - p.out_row0) * F) * OW + (size_t)xw * F;
     if (p.out_f32) {
         constexpr int DYC = F * F * 384 <= 4096 ? F : 4096 / (F * 384);              // output rows staged at once
-        float* sf = reinterpret_cast<float*>(stg);
         #pragma unroll
         for (int dy0 = 0; dy0 < F; dy0 += DYC) {
             #pragma unroll
@@ -425,7 +463,7 @@ __device__ __forceinline__ void epi_shuffle_store(const ConvParams& p, const flo
                 float o[3 * F];
                 shuffle_row<F, NV>(v, nb, dy0 + dd, o);
                 #pragma unroll
-                for (int k = 0; k < 3 * F; ++k) sf[dd * (96 * F) + lane * (3 * F) + k] = o[k];
+                for (int k = 0; k < 3 * F; ++k) st_shared_b32(stg + 4 * (dd * (96 * F) + lane * (3 * F) + k), __float_as_uint(o[k]));
             }
             __syncwarp();
             #pragma unroll
@@ -433,24 +471,23 @@ __device__ __forceinline__ void epi_shuffle_store(const ConvParams& p, const flo
                 if (dy0 + dd >= F) continue;
                 float* dst = p.out_f32 + (opx0 + (size_t)(dy0 + dd) * OW) * 3;
                 if (npx_valid == 32 && p.out_vec_ok) {
-                    for (int i = lane; i < 24 * F; i += 32)
-                        reinterpret_cast<float4*>(dst)[i] = reinterpret_cast<const float4*>(sf + dd * (96 * F))[i];
+                    for (int i = lane; i < 24 * F; i += 32) reinterpret_cast<uint4*>(dst)[i] = ld_shared_v4(stg + 4 * (dd * (96 * F)) + 16 * i);
                 } else {
-                    for (int i = lane; i < npx_valid * 3 * F; i += 32) dst[i] = sf[dd * (96 * F) + i];
+                    for (int i = lane; i < npx_valid * 3 * F; i += 32) dst[i] = __uint_as_float(ld_shared_b32(stg + 4 * (dd * (96 * F) + i)));
                 }
             }
             __syncwarp();
         }
     } else {
         // u8: stage RGBA words (alpha 255: data_to_img(..).to_rgba(), main.rs:175), [dy][32 * F pixels]
-        uint32_t* sq = reinterpret_cast<uint32_t*>(stg);
         #pragma unroll
         for (int dy = 0; dy < F; ++dy) {
             float o[3 * F];
             shuffle_row<F, NV>(v, nb, dy, o);
             #pragma unroll
             for (int dx = 0; dx < F; ++dx)
-                sq[dy * (32 * F) + lane * F + dx] = quant_u8(o[dx * 3]) | (quant_u8(o[dx * 3 + 1]) << 8) | (quant_u8(o[dx * 3 + 2]) << 16) | 0xFF000000u;
+                st_shared_b32(stg + 4 * (dy * (32 * F) + lane * F + dx),
+                              quant_u8(o[dx * 3]) | (quant_u8(o[dx * 3 + 1]) << 8) | (quant_u8(o[dx * 3 + 2]) << 16) | 0xFF000000u);
         }
         __syncwarp();
         const int nop = npx_valid * F;   // valid output pixels per row
@@ -458,22 +495,22 @@ __device__ __forceinline__ void epi_shuffle_store(const ConvParams& p, const flo
             #pragma unroll
             for (int dy = 0; dy < F; ++dy) {
                 uint32_t* dst = reinterpret_cast<uint32_t*>(p.out_u8) + opx0 + (size_t)dy * OW;
-                for (int i = lane; i < nop; i += 32) dst[i] = sq[dy * (32 * F) + i];
+                for (int i = lane; i < nop; i += 32) dst[i] = ld_shared_b32(stg + 4 * (dy * (32 * F) + i));
             }
         } else {
             // packed RGB: 4 pixels = 3 words; word j takes its bytes from staged pixels 4(j/3) + j%3 and the next one
             #pragma unroll
             for (int dy = 0; dy < F; ++dy) {
                 uint8_t* dst = p.out_u8 + (opx0 + (size_t)dy * OW) * 3;
-                const uint32_t* src = sq + dy * (32 * F);
+                const uint32_t src = stg + 4 * (dy * (32 * F));
                 if (npx_valid == 32 && p.out_vec_ok) {
                     for (int j = lane; j < 24 * F; j += 32) {
                         const int q = j / 3, m = j - 3 * q;
-                        const uint32_t w0 = src[4 * q + m], w1 = src[4 * q + m + 1];
+                        const uint32_t w0 = ld_shared_b32(src + 4 * (4 * q + m)), w1 = ld_shared_b32(src + 4 * (4 * q + m + 1));
                         reinterpret_cast<uint32_t*>(dst)[j] = __byte_perm(w0, w1, m == 0 ? 0x4210 : m == 1 ? 0x5421 : 0x6542);
                     }
                 } else {
-                    for (int i = lane; i < nop * 3; i += 32) dst[i] = (uint8_t)(src[i / 3] >> (8 * (i % 3)));
+                    for (int i = lane; i < nop * 3; i += 32) dst[i] = (uint8_t)(ld_shared_b32(src + 4 * (i / 3)) >> (8 * (i % 3)));
                 }
             }
         }
@@ -579,16 +616,23 @@ __device__ __forceinline__ void conv_epilogue_role(const ConvParams& p, uint8_t*
         if (RSR_PROF_ON) prof_acc[1] += clock64() - t0s;
     };
     WorkItem w;
+    SkipCol next_col;
+    bool have_next = false;
     while (next_item(w)) {
         const int xw = w.x0 + ew * 32;  // first pixel of this warp's 32-pixel slice
         const int x = xw + lane;
+        have_next = false;
         for (int j = 0; j < w.npass; ++j, buf ^= 1, tpar ^= (buf == 0)) {
-            SkipNb nb;
+            SkipCol col;
             if (C::SHUF) {
-                // the skip input does not depend on the MMAs: fetch this warp's first row before waiting
+                // the skip input does not depend on the MMAs: this warp's first row of the pass was fetched a pass ago (or is
+                // fetched now, at the start of an item), and the next pass's row is requested before this pass's work
                 // (SHUF launches: one tile per row; with 8 warps this warp owns rows r % 2 == eh)
                 const int y = w.y_b + j * C::R + eh;
-                if (y < w.y_e && x < p.W) load_skip_nb(p, w.img, y, x, nb);
+                if (have_next) col = next_col;
+                else if (y < w.y_e) load_skip_col(p, w.img, y, x, lane, col);
+                have_next = j + 1 < w.npass && y + C::R < w.y_e;
+                if (have_next) load_skip_col(p, w.img, y + C::R, x, lane, next_col);
             }
             RSR_WAIT(&t_full[buf], tpar, 6, 0);
             tc_fence_after();
@@ -626,14 +670,10 @@ __device__ __forceinline__ void conv_epilogue_role(const ConvParams& p, uint8_t*
                     }
                     if (ABL_NO_EPI_OUT) { if (v[0] == 123.456f && p.out_f32) p.out_f32[0] = v[1]; ++oc; continue; }
                     const long long to0 = RSR_PROF_ON ? clock64() : 0;
-                    if (r > eh && x < p.W) load_skip_nb(p, w.img, y, x, nb);
-                    if (x >= p.W) {
-                        #pragma unroll
-                        for (int a = 0; a < 3; ++a)
-                            #pragma unroll
-                            for (int b = 0; b < 3; ++b) { nb.v[a][b][0] = 0.f; nb.v[a][b][1] = 0.f; nb.v[a][b][2] = 0.f; }
-                    }
-                    epi_shuffle_store<C::FACTOR, NV>(p, v, nb, smem + C::OFF_O + (e * C::NOUT + (oc % C::NOUT)) * 4096, w.img, y, xw, lane);
+                    if (r > eh) load_skip_col(p, w.img, y, x, lane, col);   // (4 epilogue warps only: further rows of the pass)
+                    SkipNb nb;
+                    expand_skip(col, lane, nb);
+                    epi_shuffle_store<C::FACTOR, NV>(p, v, nb, stage0 + (oc % C::NOUT) * 4096, w.img, y, xw, lane);
                     if (RSR_PROF_ON) prof_acc[6] += clock64() - to0;
                     ++oc;
                 } else {
