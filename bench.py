@@ -50,8 +50,7 @@ FLOPS_CONV123_PER_LR_PX = 3 * 51200                     # conv1 + conv2 + conv3 
 # once in its stored layout, padding lanes not counted as useful FLOPs.  The fused middle launch moves 640 B/px (l1, P2, P3 in;
 # l3, E out) where conv5|6|7 + conv8|9 move 768 + 640.
 LAUNCH_WORK = {
-    "pack_input": (0, 12 + 80),
-    "conv0": (4800, 64 + 128),
+    "conv0": (4800, 12 + 128 + 16),      # image in; f and the float4 copy of x (bilinear skip) out
     "conv1|2|3": (153600, 128 + 384),
     "conv5|6|7": (18432 * 2 + 15552, 384 + 384),
     "conv8|9": (18432 + 15552, 384 + 256),
@@ -501,7 +500,7 @@ def run_ours(args):
                 runs.append(up.last_kernel_times_ms())
             up.set_kernel_timing(False)
             kt = {k: statistics.mean(r[k] for r in runs) for k in runs[0]}
-            if up.last_launch_count() == 5:      # conv5|6|7 and conv8|9 run as one launch (conv_fused.cuh)
+            if up.last_launch_count() == 4:      # conv5|6|7 and conv8|9 run as one launch (conv_fused.cuh)
                 kt["conv5|6|7+conv8|9 (fused)"] = kt.pop("conv5|6|7") + kt.pop("conv8|9")
             return kt
 

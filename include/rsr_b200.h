@@ -179,7 +179,8 @@ long long rsr_rsr_decode(const uint8_t* data, size_t len, float* params, size_t 
 int rsr_set_stream(rsr_ctx* ctx, void* cuda_stream);
 
 /* Per-kernel device times (ms, CUDA events on the launching stream) of the most recent call,
- * in launch order: pack, conv0, conv1|2|3, conv5|6|7, conv8|9, conv10+expand.  Synchronises.
+ * in launch order: conv0 (reads the image itself: img_to_data and the x-im2col happen on the way into shared memory),
+ * conv1|2|3, conv5|6|7, conv8|9, conv10+expand.  Synchronises.
  * Returns the number of entries written (<= cap) or a negative error; 0 unless rsr_set_kernel_timing(ctx, 1)
  * was called before the forward pass.  Timing is off by default: the events between the launches would serialise them,
  * and the conv launches are chained with programmatic dependent launch (each sets itself up under its predecessor's tail). */
@@ -194,8 +195,8 @@ const char* rsr_plan(rsr_ctx* ctx);
 
 /* Test hooks (used by tests/ to localise a parity failure to one launch; not needed by a host
  * integration).  rsr_debug_create = rsr_create with an explicit CTA-pair launch mask (bit 2: conv1|2|3, bit 3: the fused
- * middle launch; negative = library default).  rsr_debug_stop_after(k): subsequent calls stop after launch index k (see
- * rsr_kernel_name; negative = run everything; outputs are then not written).  rsr_debug_read_node
+ * middle launch; negative = library default).  rsr_debug_stop_after(k): subsequent calls stop after launch index k
+ * (k = 1 + the index of rsr_kernel_name: 1 = conv0 .. 5 = conv10; negative = run everything; outputs are then not written).  rsr_debug_read_node
  * copies one workspace buffer of the most recent call to the host as f32 [n*h*w][32]:
  * which = 0: activation buffer A (f, later l2), 1: activation buffer B (l1, later l3),
  *         2: partial buffer A (conv2(f), later expand), 3: partial buffer B (l3_conv partial),

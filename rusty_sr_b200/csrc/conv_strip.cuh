@@ -42,6 +42,10 @@
 // column stored bottom tap first, those contributions are ONE MMA with N = (rows hit) x NCOL: same tensor work, KH times
 // fewer A reads (measured, profiles/r02a_fold_session.log: conv10 207 -> 172 us, conv0 83 -> 79 us).
 //
+// conv0 (ConvCfg::RAWIN) has no TMA input at all: four extra warps read the image (f32 or u8) and write the x-im2col'd,
+// split rows straight into the row ring (raw_row_producer_role) — the 80 B/px tensor a separate packing launch used to
+// write and conv0 to read back is gone (same-box A/B: pack 50-54 + conv0 79-84 us -> 96 us).
+//
 // Warp roles: warp 0 = input-row producer, warp 3 = weight producer, warp 2 = TMEM allocator +
 // partial-sum producer, warp 1 = MMA issuer (one lane), warps 4.. = epilogue (4 or 8 warps per config;
 // with 8, two warps per TMEM lane quarter take alternate (row, group) tiles of a pass, which hides the
@@ -100,6 +104,11 @@ struct ConvParams {
     int n_cb;           // input channel blocks of 32 accumulated per output (1 for the sr_net launches; the
                         // generic conv uses Cin / 32, planes stored as images img * n_cb + cb)
     const float4* xf4;  // EPI_SHUFFLE: input image as float4 [N][H][W] (bilinear skip)
+    // ConvCfg::RAWIN (conv0): the image itself, f32 [N][H][W][3] or u8 [N][H][W][raw_ch]; the producer warps also leave
+    // every pixel as a float4 in xf4_out for the last launch's bilinear skip
+    const void* raw_in;
+    int raw_u8, raw_ch;
+    float4* xf4_out;
     float* out_f32;     // EPI_SHUFFLE: [N][fH][fW][3] (or null)
     uint8_t* out_u8;    // EPI_SHUFFLE: [N][fH][fW][out_u8_ch] (or null)
     int out_u8_ch;      // 4 = RGBA (alpha 255, data_to_img(..).to_rgba()), 3 = RGB (data_to_img alone)
@@ -128,9 +137,13 @@ struct ConvParams {
 
 // SHUF_: 0 = ordinary launch, f > 0 = last launch of the net with upscaling factor f (Expand + LinearInterp epilogue).
 // PREC_: operand format of the INPUT node and the weights; OFMT_: storage format of the activations this launch writes.
+// RAWIN_: the input node is the IMAGE (conv0): four extra warps read the raw pixels and build the x-im2col'd, split rows
+// straight into the shared-memory row ring (no TMA, no intermediate tensor in HBM).
 template <int KH_, int KW_, int RB_, int NG_, int R_, int NR_, int TPS_, int NBS_, int NPIN_, int NOUT_, int SHUF_, int NEPI_ = 4,
-          bool PAIR_ = false, bool FOLD_ = false, int PREC_ = PREC_BF16X3, int OFMT_ = PREC_>
+          bool PAIR_ = false, bool FOLD_ = false, int PREC_ = PREC_BF16X3, int OFMT_ = PREC_, bool RAWIN_ = false>
 struct ConvCfg {
+    static constexpr bool RAWIN = RAWIN_;
+    static constexpr int NPROD = RAWIN ? 4 : 0;                        // raw-image producer warps (each builds every 4th row of the ring)
     static constexpr bool PAIR = PAIR_;                                // CTA-pair kernel (conv_pair.cuh): half a weight tap per CTA
     // Row-folded MMAs (see the MMA role): the KH vertical taps of one tap column become ONE MMA per input row whose N spans
     // the up to KH output rows that row contributes to.
@@ -139,7 +152,7 @@ struct ConvCfg {
     static constexpr int KH = KH_, KW = KW_, RB = RB_, NG = NG_, R = R_;
     static constexpr int NEPI = NEPI_;                                 // epilogue warps (4 or 8)
     static_assert(NEPI == 4 || NEPI == 8, "4 or 8 epilogue warps");
-    static constexpr int NTHREADS = 128 + 32 * NEPI;
+    static constexpr int NTHREADS = 128 + 32 * NEPI + 32 * NPROD;
     static constexpr int NBS = NBS_, NPIN = NPIN_, NOUT = NEPI == 8 ? 1 : NOUT_;   // staging tiles per epilogue warp
     static constexpr bool SHUF = SHUF_ > 0;
     static constexpr int FACTOR = SHUF_;
@@ -165,7 +178,9 @@ struct ConvCfg {
     static constexpr int OFF_B = NR * SLOT;
     static constexpr int OFF_P = OFF_B + NBS * BST;
     static constexpr int OFF_O = OFF_P + NPIN * PIN_BYTES;
-    static constexpr int OFF_BAR = OFF_O + NEPI * NOUT * 4096;
+    static constexpr int RAW_SCRATCH = 2048;                           // RAWIN: scratch per producer warp (132 x 3 floats)
+    static constexpr int OFF_RAW = OFF_O + NEPI * NOUT * 4096;
+    static constexpr int OFF_BAR = OFF_RAW + NPROD * RAW_SCRATCH;
     static constexpr int NBAR = 2 * NR + 2 * NBS + 2 * (NPIN > 0 ? NPIN : 1) + 4;
     static constexpr int SMEM_BYTES = 1024 + OFF_BAR + NBAR * 8 + 16;
     static constexpr uint32_t SWZ = RB == 128 ? UMMA_SW_128B : UMMA_SW_64B;
@@ -179,6 +194,8 @@ struct ConvCfg {
     static_assert(SMEM_BYTES <= 232448, "shared memory budget");
     static_assert(!FOLD || (!PAIR && TPS == KH && KH * NCOL <= 256), "row folding: one weight stage = the KH taps of one tap column");
     static_assert(!SHUF || 3 * FACTOR * FACTOR <= NCOL, "expand channels must fit the accumulator groups");
+    static_assert(!RAWIN || NR % 4 == 0, "a producer warp keeps to its own ring slots");
+    static_assert(!RAWIN || (KW == 1 && KH == 5 && RB == 64 && PREC == PREC_BF16X3 && !PAIR), "raw input: the 5x5x3 conv0 on 64-byte x-im2col rows");
 };
 
 struct WorkItem {
@@ -729,6 +746,124 @@ __device__ __forceinline__ void conv_epilogue_role(const ConvParams& p, uint8_t*
     if (elect_one()) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 }
 
+// ---- raw-image row producer (ConvCfg::RAWIN: conv0 straight from the image) ------------------------------------------
+// img_to_data (main.rs:170) and the layout change conv0 needs, done on the way into shared memory: for every pixel the 5
+// horizontal neighbours x-2..x+2 (zero outside the image = Padding::Same) x 3 channels become one 16-element K chunk
+// (k = dx*3 + c, k = 15 zero), split bf16 hi | mid = 64 B per pixel, written with the 64-byte swizzle exactly where a TMA
+// load of an x-im2col tensor would have put it.  Producer warp pw of NPROD builds every NPROD-th row of the ring, all 128
+// pixels of it (four per lane: the role is a chain of dependent latencies — global load, scratch round trip, split, proxy
+// fence, barrier — so rows are spread over warps and every step of the chain carries four pixels): its lanes fetch the
+// 132 x 3 values of the row segment with coalesced loads, issued two of its rows (= 2 NPROD ring rows) ahead, pass them
+// through 1.6 KB of scratch so that a lane can pick up the 15 consecutive values of a pixel (stride 3 words: conflict-free),
+// and arrive on the row's full barrier after a proxy fence.  Rows the CTA owns also leave each pixel as a float4 in xf4_out
+// for the bilinear skip of the last launch.
+template <class C>
+__device__ __forceinline__ void raw_row_producer_role(const ConvParams& p, uint8_t* smem, uint64_t* a_full, uint64_t* a_empty,
+                                                      int pw, int lane, long long* prof_acc) {
+    constexpr int NE = 13;                       // 32-lane load rounds covering the 396 values of a row segment
+    constexpr int PF = 2;                        // rows of this warp in flight
+    const uint32_t scr = smem_u32(smem + C::OFF_RAW) + pw * C::RAW_SCRATCH;
+    const uint32_t sA_u = smem_u32(smem);
+    const int W = p.W, H = p.H;
+    const float* in_f = reinterpret_cast<const float*>(p.raw_in);
+    const uint8_t* in_b = reinterpret_cast<const uint8_t*>(p.raw_in);
+    const bool u8 = p.raw_u8 != 0;
+    const int rch = p.raw_ch;
+    // values lane + 32 k (k < NE) of the segment that starts at pixel xs (may be negative) of row y; value e sits at position
+    // 3 xs + e of the row's packed RGB values.  u8 / 255 is the IEEE quotient (as img_to_data's division) without the
+    // division's slow path: one Newton step on x * (1/255) is exact for all 256 inputs (checked exhaustively).
+    auto load_row = [&](int img, int y, int xs, float (&v)[NE]) {
+        const bool rowok = y >= 0 && y < H;
+        const size_t rowbase = ((size_t)img * H + (rowok ? y : 0)) * W;
+        const int idx0 = xs * 3 + lane;
+        const unsigned lim = rowok ? 3u * (unsigned)W : 0u;
+        if (!u8) {
+            const float* q = in_f + rowbase * 3;
+            #pragma unroll
+            for (int k = 0; k < NE; ++k) {
+                const int idx = idx0 + 32 * k;
+                const bool ok = (unsigned)idx < lim && (k < NE - 1 || lane < 12);
+                v[k] = ok ? __ldg(q + idx) : 0.f;
+            }
+        } else {
+            uint32_t b[NE];
+            if (rch == 3) {
+                const uint8_t* q = in_b + rowbase * 3;
+                #pragma unroll
+                for (int k = 0; k < NE; ++k) {
+                    const int idx = idx0 + 32 * k;
+                    const bool ok = (unsigned)idx < lim && (k < NE - 1 || lane < 12);
+                    b[k] = ok ? (uint32_t)__ldg(q + idx) : 0u;
+                }
+            } else {
+                const uint8_t* q = in_b + rowbase * 4;
+                #pragma unroll
+                for (int k = 0; k < NE; ++k) {
+                    const int idx = idx0 + 32 * k;
+                    const bool ok = (unsigned)idx < lim && (k < NE - 1 || lane < 12);
+                    b[k] = ok ? (uint32_t)__ldg(q + idx + (unsigned)idx / 3u) : 0u;   // 4 px + c = (3 px + c) + px
+                }
+            }
+            const float rcp = 1.0f / 255.0f;
+            #pragma unroll
+            for (int k = 0; k < NE; ++k) {
+                const float x = (float)b[k], q0 = x * rcp;
+                v[k] = fmaf(fmaf(-q0, 255.0f, x), rcp, q0);
+            }
+        }
+    };
+    uint32_t g_item = 0;                         // ring rows produced (by all producer warps) before the current item
+    ItemIter it = item_begin(p);
+    WorkItem w;
+    while (item_next<C>(p, it, w)) {
+        const int nrows = w.npass * C::R + 2 * C::PH;
+        const int y0 = w.y_b - C::PH;
+        const int xs = w.x0 - 2;
+        const int i_first = (int)((pw - g_item) & (C::NPROD - 1));   // this warp's first row of the item
+        float buf[PF][NE];
+        #pragma unroll
+        for (int j = 0; j < PF; ++j)
+            if (i_first + j * C::NPROD < nrows) load_row(w.img, y0 + i_first + j * C::NPROD, xs, buf[j]);
+        for (int i0 = i_first; i0 < nrows; i0 += PF * C::NPROD) {
+            #pragma unroll
+            for (int j = 0; j < PF; ++j) {
+                const int i = i0 + j * C::NPROD, y = y0 + i;
+                if (i >= nrows) break;           // (warp-uniform)
+                #pragma unroll
+                for (int k = 0; k < NE; ++k)
+                    if (k < NE - 1 || lane < 12) st_shared_b32(scr + 4 * (lane + 32 * k), __float_as_uint(buf[j][k]));
+                if (i + PF * C::NPROD < nrows) load_row(w.img, y + PF * C::NPROD, xs, buf[j]);
+                __syncwarp();
+                const uint32_t g = g_item + i, slot = g % C::NR, par = ((g / C::NR) & 1) ^ 1;
+                RSR_WAIT(&a_empty[slot], par, 1, 0);
+                const bool own = y >= w.y_b && y < w.y_e;        // rows of this item (not its halo): keep x for the skip
+                float4* xrow = p.xf4_out + ((size_t)w.img * H + (own ? y : 0)) * W + w.x0;
+                #pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const int r = 32 * q + lane;                 // pixel of the strip = row of the slot
+                    float v[16];
+                    #pragma unroll
+                    for (int k = 0; k < 15; ++k) v[k] = __uint_as_float(ld_shared_b32(scr + 4 * (3 * r + k)));
+                    v[15] = 0.f;
+                    uint32_t hi[8], mid[8];
+                    #pragma unroll
+                    for (int k = 0; k < 8; ++k) split_pair(v[2 * k], v[2 * k + 1], hi[k], mid[k]);
+                    const uint32_t row = sA_u + slot * C::SLOT + r * 64, sw = (r >> 1) & 3;
+                    st_shared_v4(row + ((0u ^ sw) << 4), hi[0], hi[1], hi[2], hi[3]);
+                    st_shared_v4(row + ((1u ^ sw) << 4), hi[4], hi[5], hi[6], hi[7]);
+                    st_shared_v4(row + ((2u ^ sw) << 4), mid[0], mid[1], mid[2], mid[3]);
+                    st_shared_v4(row + ((3u ^ sw) << 4), mid[4], mid[5], mid[6], mid[7]);
+                    if (own && w.x0 + r < W) xrow[r] = make_float4(v[6], v[7], v[8], 0.f);
+                }
+                fence_proxy_async_smem();        // generic-proxy writes -> visible to the tensor core's async-proxy reads
+                __syncwarp();                    // (also: the scratch is rewritten by this warp's next row)
+                if (lane == 0) mbar_arrive(&a_full[slot]);
+            }
+        }
+        g_item += nrows;
+    }
+}
+
 // ---- the kernel ------------------------------------------------------------------------------
 template <class C>
 __global__ void __launch_bounds__(C::NTHREADS, 1) conv_strip_kernel(const __grid_constant__ ConvParams p) {
@@ -766,7 +901,7 @@ __global__ void __launch_bounds__(C::NTHREADS, 1) conv_strip_kernel(const __grid
         for (int i = 0; i < NPB; ++i) { mbar_init(&p_full[i], 1); mbar_init(&p_empty[i], C::NEPI); }
         for (int i = 0; i < 2; ++i) { mbar_init(&t_full[i], 1); mbar_init(&t_empty[i], C::NEPI); }
         fence_mbar_init();
-        tma_prefetch_desc(&p.tmA);
+        if (!C::RAWIN) tma_prefetch_desc(&p.tmA);
         tma_prefetch_desc(&p.tmB);
     }
     if (warp == 2) { tmem_alloc(tmem_slot, C::TMEM_COLS); tmem_relinquish(); }
@@ -784,12 +919,14 @@ __global__ void __launch_bounds__(C::NTHREADS, 1) conv_strip_kernel(const __grid
     // TMA / MMA / commit instructions themselves are issued by one lane, chosen with elect.sync —
     // the pattern ptxas recognises.  (Issuing from inside a divergent `if (lane == 0)` region makes
     // it wrap every tcgen05.mma in an ELECT / R2UR "waterfall" loop: ~100 issue cycles per MMA.)
-    if (warp == 0) {
-        // ===== input-row producer =====
+    if (C::RAWIN && warp >= 4 + C::NEPI) {
+        raw_row_producer_role<C>(p, smem, a_full, a_empty, warp - 4 - C::NEPI, lane, prof_acc);
+    } else if (warp == 0) {
+        // ===== input-row producer (TMA; idle when the raw-image producer warps fill the ring) =====
         uint32_t slot = 0, par = 1;   // waiting on parity 1 of a fresh barrier returns immediately
         ItemIter it = item_begin(p);
         WorkItem w;
-        while (item_next<C>(p, it, w)) {
+        while (!C::RAWIN && item_next<C>(p, it, w)) {
             // n_cb == 1: one sliding window over the item's rows.  n_cb > 1: every (pass, channel block)
             // loads its own window of R + 2*PH rows from plane img * n_cb + cb.
             const int nseg = p.n_cb == 1 ? 1 : w.npass * p.n_cb;
@@ -999,7 +1136,7 @@ __global__ void __launch_bounds__(C::NTHREADS, 1) conv_strip_kernel(const __grid
                 if (buf == 0) tpar ^= 1;
             }
         }
-    } else if (warp >= 4) {
+    } else if (warp >= 4 && warp < 4 + C::NEPI) {
         // ===== epilogue =====
         ItemIter it = item_begin(p);
         conv_epilogue_role<C>(p, smem, p_full, p_empty, t_full, tmem_base, warp, lane, prof_acc,

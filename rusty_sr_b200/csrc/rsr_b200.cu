@@ -93,7 +93,7 @@ static Layout make_layout(int factor) {
 #define RSR_CFG0_R 8   // 8 rows per pass: conv0's MMAs are tiny, so the per-pass hand-offs dominate; 4 -> 8: -20 % (same-box A/B, r01j)
 #endif
 #ifndef RSR_CFG0_NR
-#define RSR_CFG0_NR 16
+#define RSR_CFG0_NR 20   // window of 12 rows + the 8 new rows of the next pass (the raw-image producers work a pass ahead)
 #endif
 #ifndef RSR_CFG1_NR
 #define RSR_CFG1_NR 7
@@ -182,8 +182,9 @@ template <int PREC, int F>
 struct Net {
     static constexpr int NGE = (3 * F * F + 31) / 32;
     //                      KH KW  RB NG  R NR TPS NBS NPIN NOUT SHUF NEPI PAIR  FOLD  PREC OFMT
-    // conv0 on the x-im2col'd input (K = 5 taps x 16, always BF16x3 operands), row-folded; writes f in format PREC
-    using C0 = ConvCfg<5, 1,  64, 1, RSR_CFG0_R, RSR_CFG0_NR, 5, 2, 0, 2, 0, 8, false, true, PREC_BF16X3, PREC>;
+    // conv0 straight from the image: four producer warps build the x-im2col rows in shared memory (K = 5 taps x 16, always
+    // BF16x3 operands), row-folded; writes f in format PREC
+    using C0 = ConvCfg<5, 1,  64, 1, RSR_CFG0_R, RSR_CFG0_NR, 5, 2, 0, 2, 0, 8, false, true, PREC_BF16X3, PREC, true>;
     // f -> conv1 | conv2 | conv3
     using C1 = ConvCfg<5, 5, 128, 3, 2, RSR_CFG1_NR, RSR_CFG1_TPS, RSR_CFG1_NBS, 0, 2, 0, 4, false, false, PREC>;
     using P1 = ConvCfg<5, 5, 128, 3, 2, RSR_PCFG1_NR, RSR_PCFG1_TPS, RSR_PCFG1_NBS, 0, 2, 0, RSR_PCFG1_NEPI, true, false, PREC>;
@@ -198,62 +199,10 @@ struct Net {
                                             ConvCfg<3, 3, 128, 2, 2, 6, 3, 2, 2, 2, F, 8, false, true, PREC>>;
 };
 
+// Launch indices (pair masks, rsr_debug_stop_after, profile rows).  Index 0 was the separate input-packing launch of earlier
+// versions; conv0 now reads the image itself, so the public per-launch times / names start at index 1.
 enum { K_PACK = 0, K_CONV0, K_F, K_L1, K_L2, K_L3, K_COUNT };
-static const char* kKernelNames[K_COUNT] = {"pack_input", "conv0", "conv1|2|3", "conv5|6|7", "conv8|9",
-                                            "conv10+expand+skip"};
-
-// ------------------------------------------------------------------------------ pack kernel
-// img_to_data (main.rs:170) fused with the layout change conv0 needs: for every pixel the 5
-// horizontal neighbours x-2..x+2 (zero outside the image = Padding::Same) x 3 channels become
-// one 16-element K chunk (15 used), stored split as bf16 hi | mid = 64 B per pixel.  Also keeps
-// the pixel as a float4 for the bilinear skip of the last kernel.
-// A warp covers 28 consecutive pixels of one row: lane l loads pixel x0 - 2 + l once (coalesced), the neighbours come from
-// warp shuffles, lanes 2..29 produce the outputs.
-template <bool U8>
-__global__ void __launch_bounds__(256) pack_input_kernel(const void* __restrict__ in, int in_ch, int W, int H,
-                                                          int NIMG, __nv_bfloat16* __restrict__ xcol,
-                                                          float4* __restrict__ xf4) {
-    griddep_launch_dependents();                          // conv0 may be set up while this kernel runs (it waits before reading xcol)
-    const int lane = threadIdx.x & 31;
-    const int segs = (W + 27) / 28;                       // warp segments per row
-    const long long nseg = (long long)NIMG * H * segs;
-    const long long wstride = (long long)gridDim.x * (blockDim.x >> 5);
-    for (long long sgi = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); sgi < nseg; sgi += wstride) {
-        const long long row = sgi / segs;                 // img * H + y
-        const int x = (int)(sgi - row * segs) * 28 - 2 + lane;
-        float r = 0.f, g = 0.f, b = 0.f;
-        if (x >= 0 && x < W) {
-            const size_t i = (size_t)row * W + x;
-            if (U8) {
-                const uint8_t* q = reinterpret_cast<const uint8_t*>(in) + i * in_ch;
-                r = (float)q[0] / 255.0f; g = (float)q[1] / 255.0f; b = (float)q[2] / 255.0f;
-            } else {
-                const float* q = reinterpret_cast<const float*>(in) + i * 3;
-                r = q[0]; g = q[1]; b = q[2];
-            }
-        }
-        float v[16];
-        #pragma unroll
-        for (int d = 0; d < 5; ++d) {                     // neighbour x + d - 2 lives in lane + d - 2
-            v[d * 3 + 0] = __shfl_sync(0xffffffffu, r, (lane + d - 2) & 31);
-            v[d * 3 + 1] = __shfl_sync(0xffffffffu, g, (lane + d - 2) & 31);
-            v[d * 3 + 2] = __shfl_sync(0xffffffffu, b, (lane + d - 2) & 31);
-        }
-        v[15] = 0.f;
-        if (lane >= 2 && lane < 30 && x < W) {
-            uint32_t hi[8], mid[8];
-            #pragma unroll
-            for (int k = 0; k < 8; ++k) split_pair(v[2 * k], v[2 * k + 1], hi[k], mid[k]);
-            const size_t i = (size_t)row * W + x;
-            uint4* dst = reinterpret_cast<uint4*>(xcol + i * 32);
-            dst[0] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-            dst[1] = make_uint4(hi[4], hi[5], hi[6], hi[7]);
-            dst[2] = make_uint4(mid[0], mid[1], mid[2], mid[3]);
-            dst[3] = make_uint4(mid[4], mid[5], mid[6], mid[7]);
-            xf4[i] = make_float4(r, g, b, 0.f);
-        }
-    }
-}
+static const char* kKernelNames[K_COUNT] = {"", "conv0", "conv1|2|3", "conv5|6|7", "conv8|9", "conv10+expand+skip"};
 
 // ---------------------------------------------------------------------------------- context
 struct DevBuf {
@@ -271,7 +220,7 @@ struct rsr_ctx {
     float* vecs = nullptr;  // 8 x 32 floats: f_bias f_activ l1_bias l1_activ l2_bias l2_activ l3_bias l3_activ, then 64: expand_bias
     std::vector<float> vecs_host;   // the same on the host (the fused launch takes its bias / slope vectors as kernel parameters)
     // workspace
-    DevBuf xcol, xf4, actA, actB, partA, partB, partC, out_f32, out_u8, in_stage;
+    DevBuf xf4, actA, actB, partA, partB, partC, out_f32, out_u8, in_stage;
     int plan = 0;               // middle levels: 0 = by width (fused unless the 124-pixel strips waste too much), 1 = fused, 2 = split
     bool fused_last = false;    // plan the most recent call ran
     int pair_mask = 0;          // bit 2: conv1|2|3 on CTA pairs, bit 3: fused middle launch on CTA pairs (conv_pair.cuh)
@@ -366,7 +315,7 @@ extern "C" size_t rsr_num_params(int factor) {
 extern "C" const char* rsr_last_error(void) { return g_err.c_str(); }
 extern "C" int rsr_last_error_code(void) { return g_err_code; }
 extern "C" const char* rsr_version(void) { return "rsr_b200 0.2 sm_100a (tcgen05 implicit-GEMM, fp16 + mxfp8 split operands)"; }
-extern "C" const char* rsr_kernel_name(int i) { return (i >= 0 && i < K_COUNT) ? kKernelNames[i] : ""; }
+extern "C" const char* rsr_kernel_name(int i) { return (i >= 0 && i + 1 < K_COUNT) ? kKernelNames[i + 1] : ""; }
 
 extern "C" void rsr_destroy(rsr_ctx* c) {
     if (!c) return;
@@ -375,7 +324,7 @@ extern "C" void rsr_destroy(rsr_ctx* c) {
     cudaFree(c->w0); cudaFree(c->w1); cudaFree(c->w2); cudaFree(c->w3); cudaFree(c->w4);
     cudaFree(c->vecs); cudaFree(c->prof);
     if (c->fault_host) cudaFreeHost(c->fault_host);
-    release(c->xcol); release(c->xf4); release(c->actA); release(c->actB); release(c->partA);
+    release(c->xf4); release(c->actA); release(c->actB); release(c->partA);
     release(c->partB); release(c->partC); release(c->dbg_l2); release(c->dbg_t3); release(c->dbg_prof); release(c->out_f32); release(c->out_u8); release(c->in_stage);
     for (auto& e : c->ev) if (e) cudaEventDestroy(e);
     for (auto& sl : c->slot) {
@@ -729,7 +678,6 @@ static int forward_impl(rsr_ctx* c, const void* d_in, bool u8, int in_ch, int n,
     using N = Net<PREC, F>;
     constexpr int NGE = N::NGE;
     const size_t npx = (size_t)n * w * h;
-    if (int rc = ensure(c->xcol, npx * 64)) return rc;
     if (int rc = ensure(c->xf4, npx * 16)) return rc;
     if (int rc = ensure(c->actA, npx * 128)) return rc;
     if (int rc = ensure(c->actB, npx * 128)) return rc;
@@ -739,7 +687,6 @@ static int forward_impl(rsr_ctx* c, const void* d_in, bool u8, int in_ch, int n,
     if (fused || NGE == 2) { if (int rc = ensure(c->partC, npx * 128)) return rc; }
     c->fused_last = fused;
 
-    uint8_t* xcol = (uint8_t*)c->xcol.p;
     uint8_t* f_act = (uint8_t*)c->actA.p;   // f, later l2
     uint8_t* l1_act = (uint8_t*)c->actB.p;  // l1, later l3
     uint8_t* l2_act = f_act;
@@ -752,15 +699,6 @@ static int forward_impl(rsr_ctx* c, const void* d_in, bool u8, int in_ch, int n,
                 *l2_slope = V + 160, *l3_bias = V + 192, *l3_slope = V + 224, *e_bias = V + 256;
 
     c->last_launches = 0;
-    if (c->kernel_timing) CUDA_TRY(cudaEventRecord(c->ev[0], c->stream));
-    {
-        const long long nseg = (long long)n * h * ((w + 27) / 28);
-        const int blocks = (int)std::min<long long>((nseg + 7) / 8, (long long)c->num_sms * 16);
-        if (u8) pack_input_kernel<true><<<blocks, 256, 0, c->stream>>>(d_in, in_ch, w, h, n, (__nv_bfloat16*)xcol, (float4*)c->xf4.p);
-        else    pack_input_kernel<false><<<blocks, 256, 0, c->stream>>>(d_in, 3, w, h, n, (__nv_bfloat16*)xcol, (float4*)c->xf4.p);
-        CUDA_TRY(cudaGetLastError());
-        c->last_launches++;
-    }
     if (c->kernel_timing) CUDA_TRY(cudaEventRecord(c->ev[1], c->stream));
     if (c->stop_after == 0) return 0;
 
@@ -778,8 +716,9 @@ static int forward_impl(rsr_ctx* c, const void* d_in, bool u8, int in_ch, int n,
     auto pair = [&](int kindex) { return (c->pair_mask >> kindex & 1) != 0; };
     auto part_map = [&](CUtensorMap* m, const void* base, int boxw) { return make_map_part(c, m, base, w, h, n, boxw); };
 
-    // conv0: xcol -> f = BeLU(conv0(x) + f_bias)                       network.rs:33-35
-    if (int rc = make_map_act(c, &p.tmA, xcol, 64, w, h, n, N::C0::BOXW)) return rc;
+    // conv0: image -> f = BeLU(conv0(x) + f_bias), x as float4 for the skip    main.rs:170, network.rs:33-35
+    p.raw_in = d_in; p.raw_u8 = u8 ? 1 : 0; p.raw_ch = u8 ? in_ch : 3;
+    p.xf4_out = (float4*)c->xf4.p;
     if (int rc = make_map_w(c, &p.tmB, c->w0, 64, 5 * 32, N::C0::TPS * 32)) return rc;
     if (int rc = in_map(&p.tmOut[0], f_act, 32)) return rc;
     set_groups({EpiGroup{EPI_ACT, 0, f_bias, f_slope, 0, 0}});
@@ -1087,7 +1026,7 @@ extern "C" int rsr_last_kernel_times(rsr_ctx* c, float* ms, int cap) {
     if (!c->timed) return 0;
     if (int rc = rsr_synchronize(c)) return rc;
     int nout = 0;
-    for (int i = 0; i < K_COUNT && i < cap; ++i, ++nout) CUDA_TRY(cudaEventElapsedTime(&ms[i], c->ev[i], c->ev[i + 1]));
+    for (int i = 1; i < K_COUNT && nout < cap; ++i, ++nout) CUDA_TRY(cudaEventElapsedTime(&ms[nout], c->ev[i], c->ev[i + 1]));
     return nout;
 }
 extern "C" int rsr_last_launch_count(rsr_ctx* c) { return c ? c->last_launches : 0; }
@@ -1095,8 +1034,8 @@ extern "C" const char* rsr_plan(rsr_ctx* c) {
     static thread_local std::string s;
     if (!c) return "";
     const bool fused = c->plan == 1 || (c->plan == 0 && (c->last_launches == 0 || c->fused_last));
-    s = fused ? "5 launches: pack, conv0, conv1|2|3, conv5|6|7+conv8|9 fused, conv10+expand"
-              : "6 launches: pack, conv0, conv1|2|3, conv5|6|7, conv8|9, conv10+expand";
+    s = fused ? "4 launches: conv0 (from the image), conv1|2|3, conv5|6|7+conv8|9 fused, conv10+expand"
+              : "5 launches: conv0 (from the image), conv1|2|3, conv5|6|7, conv8|9, conv10+expand";
     if (c->plan == 0) s += " (middle levels by image width)";
     s += c->prec == PREC_F16MX ? "; operands fp16 + mxfp8 (2 MMAs per K chunk)" : "; operands bf16x3 (3 MMAs per K chunk)";
     s += "; CTA pairs (cta_group::2):";

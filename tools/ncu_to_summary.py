@@ -19,7 +19,7 @@ for r in rows[2:]:
     if len(r) != len(hdr):
         continue
     name = r[hdr.index("Kernel Name")]
-    if "pack_input" in name:
+    if "pack_input" in name:   # (reports made before conv0 read the image itself)
         key = "pack_input"
     elif "conv_fused" in name:
         key = "conv5|6|7+conv8|9 (fused)"
