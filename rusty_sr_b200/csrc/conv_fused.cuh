@@ -532,7 +532,7 @@ __global__ void __launch_bounds__(FusedCfg::NTHREADS, 1) conv_fused_mid_kernel(c
                 if (lane == 0) mbar_arrive(p2_empty);
                 if (!ABL_NO_E1_MATH) {
                     #pragma unroll
-                    for (int i = 0; i < 16; ++i) v[i] = belu(v[i] + bias[i], slope[i]);
+                    for (int i = 0; i < 16; i += 2) bias_belu2(v[i], v[i + 1], bias[i], bias[i + 1], slope[i], slope[i + 1]);
                 }
                 // Padding::Same of conv8 / conv9: l2 is ZERO outside the image (not BeLU(bias)); lanes past the
                 // strip's 126 valid l2 pixels hold garbage accumulators and are zeroed too
@@ -632,7 +632,7 @@ __global__ void __launch_bounds__(FusedCfg::NTHREADS, 1) conv_fused_mid_kernel(c
                 if (ABL_NO_EPI_OUT) { if (v[0] == 123.456f) p.dbg_l2[0] = v[1] + __uint_as_float(raw_e[0]); }
                 else if (live) {
                     #pragma unroll
-                    for (int i = 0; i < 16; ++i) v[i] = belu(v[i] + bias[i], slope[i]);
+                    for (int i = 0; i < 16; i += 2) bias_belu2(v[i], v[i + 1], bias[i], bias[i + 1], slope[i], slope[i + 1]);
                     uint32_t words[16];
                     pack_split_half<PREC>(v, words);
                     if (ABL_NO_E2_STORE) { if (words[0] == 0x12345678u) p.dbg_l2[0] = __uint_as_float(words[1] ^ words[5] ^ words[9] ^ words[13]); }

@@ -247,6 +247,8 @@ struct rsr_ctx {
     PFN_cuTensorMapEncodeTiled_v12000 encode = nullptr;
 };
 
+constexpr int kFaultInts = 4 + 4 * 32;   // fault word + one record per warp of a CTA (mbar_timeout, ptx.cuh)
+
 static int ensure(DevBuf& b, size_t bytes) {
     if (bytes <= b.cap) return 0;
     if (b.p) cudaFree(b.p);
@@ -413,8 +415,8 @@ static int create_impl(rsr_ctx* c, const float* params) {
         CUDA_TRY(cudaEventCreateWithFlags(&sl.ev_done, cudaEventDisableTiming));
         CUDA_TRY(cudaEventCreateWithFlags(&sl.ev_out, cudaEventDisableTiming));
     }
-    CUDA_TRY(cudaHostAlloc((void**)&c->fault_host, 64 * sizeof(int), cudaHostAllocMapped));
-    memset(c->fault_host, 0, 64 * sizeof(int));
+    CUDA_TRY(cudaHostAlloc((void**)&c->fault_host, kFaultInts * sizeof(int), cudaHostAllocMapped));
+    memset(c->fault_host, 0, kFaultInts * sizeof(int));
     CUDA_TRY(cudaHostGetDevicePointer((void**)&c->fault, c->fault_host, 0));
 
     // conv0: [32][5][5][3] -> w0[4 - a][n][k = b*3 + c | 16 + k]  (x-im2col form, 64 B rows of bf16 hi | mid; tap rows stored
@@ -544,7 +546,7 @@ extern "C" int rsr_synchronize(rsr_ctx* c) {
     if (e != cudaSuccess) {
         std::string log;
         if (c->fault_host)
-            for (int wq = 0; wq < 12; ++wq) {
+            for (int wq = 0; wq < 32; ++wq) {
                 const int* r = c->fault_host + 4 + wq * 4;
                 if (r[0]) { char b[96]; snprintf(b, sizeof b, " [warp %d: tag %d cta %d parity %d bar@0x%x]", wq, r[0], r[1], r[2], r[3]); log += b; }
             }

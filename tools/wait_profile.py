@@ -20,8 +20,10 @@ up.forward(x)
 names = ["a_empty(rowprod)", "t_empty(mma)", "a_full(mma)", "b_full(mma)", "p_full(mma)", "p_empty(pinprod)",
          "b_empty(wprod)", "t_full(epi)", "store_read(epi)", "MMA_ISSUE_BLOCK(mma)", "EPI_BUSY(epi)", "p_full(epi, inside EPI_BUSY)", "tmem_ld(epi)", "out_path(epi: math+stage+store issue)"]
 kt = up.last_kernel_times_ms()
-for k, kname in enumerate(list(kt)[1:], start=1):
+for k, kname in enumerate(list(kt), start=1):   # launch index = 1 + position in the kernel-time list
     prof = up.debug_read_profile(k).astype(np.float64)
+    if len(prof) == 0:          # CTA-pair launches / the fused launch carry no strip-kernel profile
+        continue
     tot = prof[:, 15]
     line = f"{kname:20s} {kt[kname]*1e3:7.1f} us  grid {len(prof):3d}  cycles/CTA mean {tot.mean():9.0f} max {tot.max():9.0f} | "
     line += "  ".join(f"{n} {100*prof[:, i].mean()/tot.mean():4.1f}%" for i, n in enumerate(names))
