@@ -434,7 +434,8 @@ __device__ __forceinline__ void load_skip_col(const ConvParams& p, int img, int 
     const int W = p.W, H = p.H;
     const int ys[3] = {max(y - 1, 0), y, min(y + 1, H - 1)};
     const int xo = min(x, W - 1);                                        // lanes past the image edge clamp (they serve as
-    const int xe = lane == 0 ? max(x - 1, 0) : min(x + 1, W - 1);        // right neighbour of the last pixel)
+    const int xe = lane == 0 ? min(max(x - 1, 0), W - 1) : min(x + 1, W - 1);   // right neighbour of the last pixel; a warp whose
+                                                                          // whole slice lies past the edge still loads, in bounds)
     const float4* xi = p.xf4 + (size_t)img * H * W;
     #pragma unroll
     for (int a = 0; a < 3; ++a) {
