@@ -1277,16 +1277,15 @@ extern "C" int rsr_downsample_u8(int device, const uint8_t* in, int w, int h, in
 // Same kernel template; the input's Cin/32 channel blocks are stored as planes in the activation storage format
 // ([cb][H][W][128 B], conv_strip.cuh) and accumulated in TMEM (ConvParams::n_cb), the output is fp32 [H][W][Cout]
 // written 32 channels at a time by the RAW epilogue through a tensor map with a channel coordinate.
-// Cout <= 64 per call: fp16 + mxfp8 operands and row-folded MMAs (an N <= 64 MMA is bound by its A-tile read, so folding the
-// three vertical taps into one MMA and issuing 2 instead of 3 products per chunk takes these shapes from 41-46 % to the HBM
-// side); wider outputs: bf16x3 operands, N = 128 / 256 MMAs are tensor-bound and the accumulators fill tensor memory.
+// Operands are fp16 + mxfp8 (2 MMAs per 16-channel chunk) for every width.  Output blocks of <= 64 channels use row-folded
+// MMAs (an N <= 64 MMA is bound by its A-tile read, so the three vertical taps become one MMA); wider outputs run as blocks of
+// 128 channels, one row per pass (N = 128 MMAs are tensor-bound; 2 x 128 accumulator columns + the scale-factor columns fit
+// tensor memory, two rows would not).  With several input-channel blocks every (pass, block) segment loads its own window of
+// rows, so the row ring holds two windows: the next segment's rows land while the current one's MMAs run.
 //                        KH KW  RB NG R NR TPS NBS NPIN NOUT SHUF NEPI PAIR FOLD PREC
 using CvN32  = ConvCfg<3, 3, 128, 1, 2, 6, 3, 3, 0, 2, 0, 4, false, true, PREC_F16MX>;
-using CvN64  = ConvCfg<3, 3, 128, 2, 2, 6, 3, 3, 0, 2, 0, 4, false, true, PREC_F16MX>;
-using CvB32  = ConvCfg<3, 3, 128, 1, 2, 6, 3, 3, 0, 2, 0>;
-using CvB64  = ConvCfg<3, 3, 128, 2, 2, 6, 2, 3, 0, 2, 0>;
-using CvN128 = ConvCfg<3, 3, 128, 4, 2, 6, 1, 4, 0, 2, 0>;
-using CvN256 = ConvCfg<3, 3, 128, 8, 1, 5, 1, 3, 0, 2, 0>;
+using CvN64  = ConvCfg<3, 3, 128, 2, 2, 8, 3, 2, 0, 2, 0, 4, false, true, PREC_F16MX>;
+using CvN128 = ConvCfg<3, 3, 128, 4, 1, 6, 1, 4, 0, 2, 0, 4, false, false, PREC_F16MX>;
 
 template <int PREC>
 __global__ void __launch_bounds__(256) pack_planes_kernel(const float* __restrict__ x, int W, int H, int Ci,
@@ -1379,18 +1378,16 @@ extern "C" int rsr_conv2d_3x3_f32(int device, const float* x, const float* weigh
 
     const size_t npx = (size_t)w * h;
     const int ncb = cin / 32;
-    // output-channel blocks: the widest kernel (N = 256, 128, 64, 32) that fits what is left
+    // output-channel blocks: the widest kernel (N = 128, 64, 32) that fits what is left
     struct Blk { int co0, n; };
     std::vector<Blk> blocks;
     for (int co0 = 0; co0 < cout;) {
         const int left = cout - co0;
-        const int n = left >= 256 ? 256 : left >= 128 ? 128 : left >= 64 ? 64 : 32;
+        const int n = left >= 128 ? 128 : left >= 64 ? 64 : 32;
         blocks.push_back({co0, n});
         co0 += n;
     }
-    // narrow outputs: fp16 + mxfp8 operands, row-folded MMAs (tap blocks stored bottom tap first: tb * 3 + (2 - ta))
-    const bool narrow = cout <= 64;
-    const int prec = narrow ? PREC_F16MX : PREC_BF16X3;
+    const int prec = PREC_F16MX;
     // weights [cout][3][3][cin] -> per block [cb][tap block][n][128 B weight row]
     std::vector<std::vector<uint8_t>> packs(blocks.size());
     for (size_t b = 0; b < blocks.size(); ++b) {
@@ -1400,7 +1397,8 @@ extern "C" int rsr_conv2d_3x3_f32(int device, const float* x, const float* weigh
         for (int o = 0; o < n; ++o)
             for (int t = 0; t < 9; ++t)
                 for (int cb = 0; cb < ncb; ++cb) {
-                    const int blk = narrow ? (t % 3) * 3 + (2 - t / 3) : t;
+                    // blocks of <= 64 channels run row-folded MMAs: tap blocks stored bottom tap first, tb * 3 + (2 - ta)
+                    const int blk = n <= 64 ? (t % 3) * 3 + (2 - t / 3) : t;
                     pack_weight_row(&weights[(((size_t)(co0 + o)) * 9 + t) * cin + cb * 32], &pk[(((size_t)cb * 9 + blk) * n + o) * 128], prec);
                 }
     }
@@ -1432,20 +1430,16 @@ extern "C" int rsr_conv2d_3x3_f32(int device, const float* x, const float* weigh
     CV_TRY(cudaMemcpyAsync(d_x, x, npx * cin * sizeof(float), cudaMemcpyHostToDevice, st));
     {
         const int nblk = (int)std::min<size_t>((npx * ncb + 255) / 256, (size_t)prop.multiProcessorCount * 16);
-        if (narrow) pack_planes_kernel<PREC_F16MX><<<nblk, 256, 0, st>>>(d_x, w, h, cin, d_planes);
-        else        pack_planes_kernel<PREC_BF16X3><<<nblk, 256, 0, st>>>(d_x, w, h, cin, d_planes);
+        pack_planes_kernel<PREC_F16MX><<<nblk, 256, 0, st>>>(d_x, w, h, cin, d_planes);
         CV_TRY(cudaGetLastError());
     }
     for (int it = 0; it < iters + 1; ++it) {   // first round is a warm-up
         if (it == 1) CV_TRY(cudaEventRecord(e0, st));
         for (size_t b = 0; b < blocks.size(); ++b) {
             const int n = blocks[b].n, co0 = blocks[b].co0;
-            if (n == 256)      rc = conv2d_block<CvN256>(enc, prop.multiProcessorCount, st, d_planes, d_w[b], d_out, w, h, cin, cout, co0, d_fault);
-            else if (n == 128) rc = conv2d_block<CvN128>(enc, prop.multiProcessorCount, st, d_planes, d_w[b], d_out, w, h, cin, cout, co0, d_fault);
-            else if (n == 64)  rc = narrow ? conv2d_block<CvN64>(enc, prop.multiProcessorCount, st, d_planes, d_w[b], d_out, w, h, cin, cout, co0, d_fault)
-                                           : conv2d_block<CvB64>(enc, prop.multiProcessorCount, st, d_planes, d_w[b], d_out, w, h, cin, cout, co0, d_fault);
-            else               rc = narrow ? conv2d_block<CvN32>(enc, prop.multiProcessorCount, st, d_planes, d_w[b], d_out, w, h, cin, cout, co0, d_fault)
-                                           : conv2d_block<CvB32>(enc, prop.multiProcessorCount, st, d_planes, d_w[b], d_out, w, h, cin, cout, co0, d_fault);
+            if (n == 128)     rc = conv2d_block<CvN128>(enc, prop.multiProcessorCount, st, d_planes, d_w[b], d_out, w, h, cin, cout, co0, d_fault);
+            else if (n == 64) rc = conv2d_block<CvN64>(enc, prop.multiProcessorCount, st, d_planes, d_w[b], d_out, w, h, cin, cout, co0, d_fault);
+            else              rc = conv2d_block<CvN32>(enc, prop.multiProcessorCount, st, d_planes, d_w[b], d_out, w, h, cin, cout, co0, d_fault);
             if (rc) { cleanup(); return rc; }
         }
     }

@@ -18,7 +18,7 @@ if os.path.exists(pk):
     peaks = {"bf16_tflops": d.get("bf16_tflops_sustained", 1455.1), "hbm_gbs": d.get("hbm_gbs", 6573.5)}
 sizes = [int(a) for a in sys.argv[1:]] or [256, 512, 1024, 2048]
 rows = []
-print("| C | H=W | ms | useful TFLOP/s | executed TFLOP/s (x3) | alg. GB/s | bound | % of roofline (useful) |")
+print("| C | H=W | ms | useful TFLOP/s | executed TFLOP/s (x2) | alg. GB/s | bound | % of roofline (useful) |")
 print("|---|---|---|---|---|---|---|---|")
 for C in (32, 64, 128, 256):
     for S in sizes:
@@ -35,8 +35,8 @@ for C in (32, 64, 128, 256):
         r = {"C": C, "HW": S, "ms": ms, "useful_tflops": flops / ms / 1e9, "alg_gbs": byts / ms / 1e6, "bound": bound,
              "roofline_frac": frac}
         rows.append(r)
-        print(f"| {C} | {S} | {ms:.4f} | {r['useful_tflops']:.1f} | {3*r['useful_tflops']:.1f} | {r['alg_gbs']:.0f} | {bound} | {100*frac:.1f} % |",
+        print(f"| {C} | {S} | {ms:.4f} | {r['useful_tflops']:.1f} | {2*r['useful_tflops']:.1f} | {r['alg_gbs']:.0f} | {bound} | {100*frac:.1f} % |",
               flush=True)
 print(json.dumps({"peaks": peaks, "note": "roofline = max(useful FLOPs / measured sustained bf16 peak, fp32 algorithmic bytes / measured HBM); "
-                  "BF16x3 executes 3x the useful FLOPs; the stored activation format is split-bf16 (same 4 B per element)",
+                  "the fp16 + mxfp8 operand split executes 2x the useful FLOPs; the stored activation format is 4 B per element like fp32",
                   "rows": rows}))
