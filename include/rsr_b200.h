@@ -59,7 +59,7 @@ enum {
 size_t rsr_num_params(int factor);
 
 /* Builds the device-side network from the flat parameter vector the reference passes as
- * `&params` (decoded .rsr, main.rs:138-152): copies, splits to bf16 hi/mid and repacks the
+ * `&params` (decoded .rsr, main.rs:138-152): copies, splits them into the kernels' operand format and repacks the
  * weights once.  The caller keeps ownership of `params`.  `device` is a CUDA ordinal.
  * Returns NULL on failure (see rsr_last_error / rsr_last_error_code). */
 rsr_ctx* rsr_create(const float* params, size_t n_params, int factor, int device, int flags);
@@ -67,7 +67,10 @@ void rsr_destroy(rsr_ctx* ctx);
 
 /* upscale, f32 in / f32 out — the exact tensor contract of graph.forward (main.rs:168-171):
  * in  : host [h][w][3] f32, sRGB-encoded 0..1 (what img_to_data produces, main.rs:170)
- * out : host [factor*h][factor*w][3] f32, NOT clamped (clamping is data_to_img's job). */
+ * out : host [factor*h][factor*w][3] f32, NOT clamped (clamping is data_to_img's job).
+ * The host calls are synchronous.  On one large frame the result's way back over PCIe takes as long as the forward pass or
+ * longer, so the library runs such a frame as up to four horizontal bands (7 halo rows recomputed, results identical bit for
+ * bit) and sends each band's rows to the host while the next band computes; pinned `out` memory makes that overlap real. */
 int rsr_upscale_f32(rsr_ctx* ctx, const float* in_hwc3, int w, int h, float* out_hwc3);
 
 /* upscale with the reference's image<->tensor mapping fused on the device

@@ -241,6 +241,7 @@ struct rsr_ctx {
         bool used = false;
     } slot[3];
     cudaStream_t s_h2d = nullptr, s_d2h = nullptr;
+    cudaEvent_t ev_band[4] = {};   // synchronous host calls on large frames: one event per band (upscale_host)
     long long next_ticket = 0;
     long long* prof = nullptr;  // test hook: [K_COUNT][256][16] wait-cycle counters
     int prof_grid[K_COUNT] = {};
@@ -337,6 +338,7 @@ extern "C" void rsr_destroy(rsr_ctx* c) {
     }
     if (c->s_h2d) cudaStreamDestroy(c->s_h2d);
     if (c->s_d2h) cudaStreamDestroy(c->s_d2h);
+    for (auto& e : c->ev_band) if (e) cudaEventDestroy(e);
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
     delete c;
 }
@@ -410,6 +412,7 @@ static int create_impl(rsr_ctx* c, const float* params) {
     for (auto& e : c->ev) CUDA_TRY(cudaEventCreate(&e));
     CUDA_TRY(cudaStreamCreateWithFlags(&c->s_h2d, cudaStreamNonBlocking));
     CUDA_TRY(cudaStreamCreateWithFlags(&c->s_d2h, cudaStreamNonBlocking));
+    for (auto& e : c->ev_band) CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     for (auto& sl : c->slot) {
         CUDA_TRY(cudaEventCreateWithFlags(&sl.ev_in, cudaEventDisableTiming));
         CUDA_TRY(cudaEventCreateWithFlags(&sl.ev_done, cudaEventDisableTiming));
@@ -897,6 +900,16 @@ extern "C" int rsr_upscale_band_device_u8(rsr_ctx* c, const uint8_t* d_in_rows, 
 }
 
 // Host-buffer entry points: H2D, forward, D2H on the context's stream, then synchronise.  out_ch: 0 = f32 RGB, 3 / 4 = u8.
+// Receptive field of sr_net in rows: 2 + 2 + 1 + 1 + 1 (network.rs:33,60-72) — the halo a band needs on each side.
+constexpr int kHaloRows = 7;
+// The synchronous host calls on one large frame: the device->host copy of the result takes as long as the forward pass
+// (u8) or several times longer (f32), so the frame runs as up to kSyncBands horizontal bands (halo rows recomputed; the
+// results are bit-identical to the whole frame, like rsr_upscale_band_*) and each band's rows travel to the host while the
+// next band computes.
+constexpr int kSyncBands = 4;
+constexpr int kSyncBandMinRows = 128;           // LR rows per band below which the halo recompute (14 rows) is not worth it
+constexpr size_t kSyncBandMinBytes = 8u << 20;  // result size below which the copy is too short to matter
+
 static int upscale_host(rsr_ctx* c, const void* in, bool u8, int in_ch, int n, int w, int h, void* out, int out_ch,
                         int top = 0, int bottom = 0) {
     if (!c) return fail(RSR_E_BAD_ARG, "ctx is null");
@@ -908,19 +921,43 @@ static int upscale_host(rsr_ctx* c, const void* in, bool u8, int in_ch, int n, i
     CUDA_TRY(cudaSetDevice(c->device));
     const int F = c->factor;
     const size_t npx = (size_t)n * w * h;
-    const size_t in_bytes = u8 ? npx * in_ch : npx * 3 * sizeof(float);
+    const size_t in_px = u8 ? (size_t)in_ch : 3 * sizeof(float), out_px = out_ch ? (size_t)out_ch : 3 * sizeof(float);
+    const size_t in_bytes = npx * in_px;
     if (int rc = ensure(c->in_stage, in_bytes)) return rc;
     CUDA_TRY(cudaMemcpyAsync(c->in_stage.p, in, in_bytes, cudaMemcpyHostToDevice, c->stream));
     const size_t opx = (size_t)n * w * (h - top - bottom) * F * F;
-    const size_t out_bytes = opx * (out_ch ? (size_t)out_ch : 3 * sizeof(float));
+    const size_t out_bytes = opx * out_px;
     DevBuf& ob = out_ch ? c->out_u8 : c->out_f32;
     if (int rc = ensure(ob, out_bytes)) return rc;
-    if (int rc = forward_device(c, c->in_stage.p, u8, in_ch, n, w, h,
-                                out_spec(out_ch ? nullptr : (float*)ob.p, out_ch ? (uint8_t*)ob.p : nullptr, out_ch ? out_ch : 4, top, bottom)))
-        return rc;
-    if (int rc = rsr_synchronize(c)) return rc;   // surfaces a kernel fault (with its fault word) before the copy
-    CUDA_TRY(cudaMemcpyAsync(out, ob.p, out_bytes, cudaMemcpyDeviceToHost, c->stream));
-    return rsr_synchronize(c);
+    auto spec = [&](uint8_t* d_out, int t, int b) {
+        return out_spec(out_ch ? nullptr : (float*)d_out, out_ch ? d_out : nullptr, out_ch ? out_ch : 4, t, b);
+    };
+    // (not under the test hooks / per-launch timing, which look at the buffers and events of ONE whole-frame pass)
+    const bool whole = c->kernel_timing || c->stop_after >= 0 || c->fused_dbg || c->prof;
+    const int nb = (n == 1 && top == 0 && bottom == 0 && !whole && out_bytes >= kSyncBandMinBytes) ? std::min(kSyncBands, h / kSyncBandMinRows) : 1;
+    if (nb < 2) {
+        if (int rc = forward_device(c, c->in_stage.p, u8, in_ch, n, w, h, spec((uint8_t*)ob.p, top, bottom))) return rc;
+        if (int rc = rsr_synchronize(c)) return rc;   // surfaces a kernel fault (with its fault word) before the copy
+        CUDA_TRY(cudaMemcpyAsync(out, ob.p, out_bytes, cudaMemcpyDeviceToHost, c->stream));
+        return rsr_synchronize(c);
+    }
+    const size_t in_row = (size_t)w * in_px, out_row = (size_t)w * F * out_px;
+    for (int b = 0; b < nb; ++b) {
+        // band b owns LR rows [y0, y1); its halo rows are rows of the same frame (none at the frame's own edges)
+        const int y0 = (int)((long long)b * h / nb), y1 = (int)((long long)(b + 1) * h / nb);
+        const int t = std::min(y0, kHaloRows), bt = std::min(h - y1, kHaloRows);
+        uint8_t* d_band = (uint8_t*)ob.p + (size_t)y0 * F * out_row;
+        if (int rc = forward_device(c, (const uint8_t*)c->in_stage.p + (size_t)(y0 - t) * in_row, u8, in_ch, 1, w, y1 - y0 + t + bt,
+                                    spec(d_band, t, bt)))
+            return rc;
+        CUDA_TRY(cudaEventRecord(c->ev_band[b], c->stream));
+        CUDA_TRY(cudaStreamWaitEvent(c->s_d2h, c->ev_band[b], 0));
+        CUDA_TRY(cudaMemcpyAsync((uint8_t*)out + (size_t)y0 * F * out_row, d_band, (size_t)(y1 - y0) * F * out_row, cudaMemcpyDeviceToHost, c->s_d2h));
+    }
+    if (int rc = rsr_synchronize(c)) return rc;       // kernel faults surface here, with the fault word
+    cudaError_t e = cudaStreamSynchronize(c->s_d2h);
+    if (e != cudaSuccess) return fail(RSR_E_CUDA, "device->host copy failed: %s", cudaGetErrorString(e));
+    return 0;
 }
 
 // ---- pipelined host API ---------------------------------------------------------------------

@@ -190,6 +190,23 @@ def test_band_mode_equals_full_frame(ups, weights):
     assert np.array_equal(tiled, full)
 
 
+def test_synchronous_call_on_a_large_frame_overlaps_its_copy_and_is_identical(ups):
+    """rsr_upscale_* on one large frame runs as up to four bands whose rows travel to the host while the next band computes
+    (rsr_b200.cu upscale_host); with per-launch timing on, the same call runs the frame in one pass.  Same bytes either way."""
+    u = ups["imagenet"]
+    rng = np.random.default_rng(77)
+    img = rng.integers(0, 256, size=(601, 397, 3), dtype=np.uint8)      # 4 bands of 150 / 151 rows, odd width
+    x = img.astype(np.float32) / 255.0
+    banded_u8, banded_rgb, banded_f32 = u.forward_u8(img), u.forward_u8(img, rgb=True), u.forward(x)
+    u.set_kernel_timing(True)
+    try:
+        whole_u8, whole_rgb, whole_f32 = u.forward_u8(img), u.forward_u8(img, rgb=True), u.forward(x)
+        assert len(u.last_kernel_times_ms()) == 5
+    finally:
+        u.set_kernel_timing(False)
+    assert np.array_equal(banded_u8, whole_u8) and np.array_equal(banded_rgb, whole_rgb) and np.array_equal(banded_f32, whole_f32)
+
+
 def test_1080p_properties(ups, weights):
     """BASELINE config 2 at full size: too big to oracle in a unit test in full, so check
     (a) a 64-row horizontal slab against the oracle (the slab + 7-row halo is self-contained),
