@@ -934,7 +934,8 @@ static int upscale_host(rsr_ctx* c, const void* in, bool u8, int in_ch, int n, i
     };
     // (not under the test hooks / per-launch timing, which look at the buffers and events of ONE whole-frame pass)
     const bool whole = c->kernel_timing || c->stop_after >= 0 || c->fused_dbg || c->prof;
-    const int nb = (n == 1 && top == 0 && bottom == 0 && !whole && out_bytes >= kSyncBandMinBytes) ? std::min(kSyncBands, h / kSyncBandMinRows) : 1;
+    const int r0 = top, r1 = h - bottom;             // LR rows whose outputs are produced (a band call's own halo rows are not)
+    const int nb = (n == 1 && !whole && out_bytes >= kSyncBandMinBytes) ? std::min(kSyncBands, (r1 - r0) / kSyncBandMinRows) : 1;
     if (nb < 2) {
         if (int rc = forward_device(c, c->in_stage.p, u8, in_ch, n, w, h, spec((uint8_t*)ob.p, top, bottom))) return rc;
         if (int rc = rsr_synchronize(c)) return rc;   // surfaces a kernel fault (with its fault word) before the copy
@@ -943,16 +944,16 @@ static int upscale_host(rsr_ctx* c, const void* in, bool u8, int in_ch, int n, i
     }
     const size_t in_row = (size_t)w * in_px, out_row = (size_t)w * F * out_px;
     for (int b = 0; b < nb; ++b) {
-        // band b owns LR rows [y0, y1); its halo rows are rows of the same frame (none at the frame's own edges)
-        const int y0 = (int)((long long)b * h / nb), y1 = (int)((long long)(b + 1) * h / nb);
+        // band b owns LR rows [y0, y1); its halo rows are rows of the same input (none at the frame's own edges)
+        const int y0 = r0 + (int)((long long)b * (r1 - r0) / nb), y1 = r0 + (int)((long long)(b + 1) * (r1 - r0) / nb);
         const int t = std::min(y0, kHaloRows), bt = std::min(h - y1, kHaloRows);
-        uint8_t* d_band = (uint8_t*)ob.p + (size_t)y0 * F * out_row;
+        uint8_t* d_band = (uint8_t*)ob.p + (size_t)(y0 - r0) * F * out_row;
         if (int rc = forward_device(c, (const uint8_t*)c->in_stage.p + (size_t)(y0 - t) * in_row, u8, in_ch, 1, w, y1 - y0 + t + bt,
                                     spec(d_band, t, bt)))
             return rc;
         CUDA_TRY(cudaEventRecord(c->ev_band[b], c->stream));
         CUDA_TRY(cudaStreamWaitEvent(c->s_d2h, c->ev_band[b], 0));
-        CUDA_TRY(cudaMemcpyAsync((uint8_t*)out + (size_t)y0 * F * out_row, d_band, (size_t)(y1 - y0) * F * out_row, cudaMemcpyDeviceToHost, c->s_d2h));
+        CUDA_TRY(cudaMemcpyAsync((uint8_t*)out + (size_t)(y0 - r0) * F * out_row, d_band, (size_t)(y1 - y0) * F * out_row, cudaMemcpyDeviceToHost, c->s_d2h));
     }
     if (int rc = rsr_synchronize(c)) return rc;       // kernel faults surface here, with the fault word
     cudaError_t e = cudaStreamSynchronize(c->s_d2h);

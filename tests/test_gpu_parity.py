@@ -205,6 +205,9 @@ def test_synchronous_call_on_a_large_frame_overlaps_its_copy_and_is_identical(up
     finally:
         u.set_kernel_timing(False)
     assert np.array_equal(banded_u8, whole_u8) and np.array_equal(banded_rgb, whole_rgb) and np.array_equal(banded_f32, whole_f32)
+    # a band call (rsr_upscale_band_*: rows with 7-row halos) large enough to be split further gives the frame's rows
+    lower = u.forward_band(x[300 - 7:], 7, 0)
+    assert np.array_equal(lower, whole_f32[900:])
 
 
 def test_1080p_properties(ups, weights):
