@@ -93,6 +93,9 @@ enum : int {
     FP_E2_STORE_READ,  //         staging tile still being read by the previous TMA store
     FP_E2_TOTAL,
     FP_ROWS,           // warp 1  S1 rows issued by this CTA
+    FP_SMID,           //         SM the CTA ran on; FP_T_START / FP_T_END: %globaltimer (ns) at the start / end of the MMA role
+    FP_T_START,        //         (tools/cta_spread.py: how long every cluster takes and where it sat)
+    FP_T_END,
     FPROF_N = 32
 };
 
@@ -390,6 +393,8 @@ __global__ void __launch_bounds__(FusedCfg::NTHREADS, 1) conv_fused_mid_kernel(c
         uint32_t bst = 0, bpar = 0;
         int n_item = 0;
         const long long prof_t0 = FPROF_ON ? clock64() : 0;
+        long long prof_g0 = 0;
+        if (FPROF_ON) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(prof_g0));
 
         // S1(q): l1 rows q..q+2 of the item -> T slot of row q
         auto s1 = [&](int q) {
@@ -503,7 +508,14 @@ __global__ void __launch_bounds__(FusedCfg::NTHREADS, 1) conv_fused_mid_kernel(c
         }
         if (FPROF_ON) prof_acc[FP_MMA_TOTAL] = clock64() - prof_t0;
         FPROF_FLUSH(FP_T_EMPTY, FP_MMA_TOTAL - FP_T_EMPTY + 1);
-        FPROF_FLUSH(FP_ROWS, 1);
+        if (FPROF_ON) {
+            uint32_t smid;
+            long long t1;
+            asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+            prof_acc[FP_SMID] = smid; prof_acc[FP_T_START] = prof_g0; prof_acc[FP_T_END] = t1;
+        }
+        FPROF_FLUSH(FP_ROWS, 4);
         }  // leader
     } else if (warp >= 4 && warp < 12) {
         // ===== E1: l2pre (+ P2) -> l2 row in the shared-memory ring; this warp: lane quarter ew, channels 16*half .. +15 =====
