@@ -943,17 +943,29 @@ static int upscale_host(rsr_ctx* c, const void* in, bool u8, int in_ch, int n, i
         return rsr_synchronize(c);
     }
     const size_t in_row = (size_t)w * in_px, out_row = (size_t)w * F * out_px;
+    // band b owns LR rows [y0, y1); its halo rows are rows of the same input (none at the frame's own edges)
+    auto band_rows = [&](int b, int& y0, int& y1) {
+        y0 = r0 + (int)((long long)b * (r1 - r0) / nb);
+        y1 = r0 + (int)((long long)(b + 1) * (r1 - r0) / nb);
+    };
+    // every band's forward pass is queued first and the copies after them: a copy into PAGEABLE host memory blocks the calling
+    // thread until it is done, and the bands behind it should be computing meanwhile
     for (int b = 0; b < nb; ++b) {
-        // band b owns LR rows [y0, y1); its halo rows are rows of the same input (none at the frame's own edges)
-        const int y0 = r0 + (int)((long long)b * (r1 - r0) / nb), y1 = r0 + (int)((long long)(b + 1) * (r1 - r0) / nb);
+        int y0, y1;
+        band_rows(b, y0, y1);
         const int t = std::min(y0, kHaloRows), bt = std::min(h - y1, kHaloRows);
         uint8_t* d_band = (uint8_t*)ob.p + (size_t)(y0 - r0) * F * out_row;
         if (int rc = forward_device(c, (const uint8_t*)c->in_stage.p + (size_t)(y0 - t) * in_row, u8, in_ch, 1, w, y1 - y0 + t + bt,
                                     spec(d_band, t, bt)))
             return rc;
         CUDA_TRY(cudaEventRecord(c->ev_band[b], c->stream));
+    }
+    for (int b = 0; b < nb; ++b) {
+        int y0, y1;
+        band_rows(b, y0, y1);
+        const size_t off = (size_t)(y0 - r0) * F * out_row;
         CUDA_TRY(cudaStreamWaitEvent(c->s_d2h, c->ev_band[b], 0));
-        CUDA_TRY(cudaMemcpyAsync((uint8_t*)out + (size_t)(y0 - r0) * F * out_row, d_band, (size_t)(y1 - y0) * F * out_row, cudaMemcpyDeviceToHost, c->s_d2h));
+        CUDA_TRY(cudaMemcpyAsync((uint8_t*)out + off, (const uint8_t*)ob.p + off, (size_t)(y1 - y0) * F * out_row, cudaMemcpyDeviceToHost, c->s_d2h));
     }
     if (int rc = rsr_synchronize(c)) return rc;       // kernel faults surface here, with the fault word
     cudaError_t e = cudaStreamSynchronize(c->s_d2h);

@@ -26,3 +26,11 @@ for timing in (False, True):
       "rgba %.3f" % run(L.rsr_upscale_u8, up._h, vp(pin_in.ctypes.data), 1920, 1080, 3, vp(o4.ctypes.data)),
       "rgb %.3f" % run(L.rsr_upscale_u8_rgb, up._h, vp(pin_in.ctypes.data), 1920, 1080, 3, vp(o3.ctypes.data)),
       "f32 %.3f ms" % run(L.rsr_upscale_f32, up._h, xf.ctypes.data_as(ctypes.POINTER(ctypes.c_float)), 1920, 1080, of.ctypes.data_as(ctypes.POINTER(ctypes.c_float))))
+# pageable host buffers (a plain Vec<u8> / numpy array): the copies block the calling thread, the bands behind them still compute
+up.set_kernel_timing(False)
+pg_in, pg4 = np.array(img), np.empty((3240, 5760, 4), np.uint8)
+banded = run(L.rsr_upscale_u8, up._h, vp(pg_in.ctypes.data), 1920, 1080, 3, vp(pg4.ctypes.data))
+up.set_kernel_timing(True)
+whole = run(L.rsr_upscale_u8, up._h, vp(pg_in.ctypes.data), 1920, 1080, 3, vp(pg4.ctypes.data))
+print("pageable buffers: rgba banded %.3f  whole frame %.3f ms" % (banded, whole))
+
