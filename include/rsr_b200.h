@@ -224,6 +224,13 @@ int rsr_debug_read_profile(rsr_ctx* ctx, int launch_index, long long* out, int c
 const char* rsr_last_error(void);
 int rsr_last_error_code(void);
 
+/* Page-locked host memory for image buffers (cudaHostAlloc / cudaFreeHost, so that a host program does not have to link the
+ * CUDA runtime itself).  Copies from / into such buffers run at PCIe speed and overlap the computation (rsr_upscale_* on a large
+ * frame, rsr_submit_*): 1080p u8 -> RGBA takes 1.8 ms per synchronous call with pinned buffers, 4.5 ms with pageable ones.
+ * rsr_host_alloc returns NULL on failure (see rsr_last_error). */
+void* rsr_host_alloc(size_t bytes);
+void rsr_host_free(void* p);
+
 /* Build identification, e.g. "rsr_b200 0.2 sm_100a ...". */
 const char* rsr_version(void);
 

@@ -31,7 +31,7 @@ EXPORTS = (
     "rsr_debug_profile", "rsr_debug_read_profile", "rsr_debug_fused", "rsr_debug_read_fused_profile",
     "rsr_bilinear_f32", "rsr_bilinear_u8", "rsr_downsample_f32", "rsr_downsample_u8", "rsr_conv2d_3x3_f32",
     "rsr_upscale_u8_rgb", "rsr_upscale_device_u8_rgb", "rsr_upscale_band_device_f32", "rsr_upscale_band_device_u8",
-    "rsr_submit_u8_rgb", "rsr_rsr_encoded_size", "rsr_rsr_encode", "rsr_rsr_decode", "rsr_debug_create", "rsr_set_kernel_timing",
+    "rsr_submit_u8_rgb", "rsr_host_alloc", "rsr_host_free", "rsr_rsr_encoded_size", "rsr_rsr_encode", "rsr_rsr_decode", "rsr_debug_create", "rsr_set_kernel_timing",
 )
 
 _lib = None
@@ -106,6 +106,10 @@ def load() -> ctypes.CDLL:
     L.rsr_plan.argtypes = [vp]
     L.rsr_plan.restype = ctypes.c_char_p
     L.rsr_last_error.restype = ctypes.c_char_p
+    L.rsr_host_alloc.restype = ctypes.c_void_p
+    L.rsr_host_alloc.argtypes = [ctypes.c_size_t]
+    L.rsr_host_free.restype = None
+    L.rsr_host_free.argtypes = [ctypes.c_void_p]
     L.rsr_last_error_code.restype = ci
     L.rsr_version.restype = ctypes.c_char_p
     L.rsr_bilinear_f32.argtypes = [ci, vp, ci, ci, ci, vp]

@@ -316,6 +316,19 @@ extern "C" size_t rsr_num_params(int factor) {
 }
 
 extern "C" const char* rsr_last_error(void) { return g_err.c_str(); }
+extern "C" void* rsr_host_alloc(size_t bytes) {
+    void* p = nullptr;
+    cudaError_t e = cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        fail(e == cudaErrorMemoryAllocation ? RSR_E_OOM : RSR_E_CUDA, "cudaHostAlloc(%zu bytes) failed: %s", bytes, cudaGetErrorString(e));
+        return nullptr;
+    }
+    return p;
+}
+extern "C" void rsr_host_free(void* p) {
+    if (p) cudaFreeHost(p);
+}
 extern "C" int rsr_last_error_code(void) { return g_err_code; }
 extern "C" const char* rsr_version(void) { return "rsr_b200 0.2 sm_100a (tcgen05 implicit-GEMM, fp16 + mxfp8 split operands)"; }
 extern "C" const char* rsr_kernel_name(int i) { return (i >= 0 && i + 1 < K_COUNT) ? kKernelNames[i + 1] : ""; }

@@ -135,15 +135,24 @@ int main(int argc, char** argv) {
         const rsr_host::Image in = rsr_host::read_png(pos[0]);
         rsr_ctx* ctx = rsr_create(params.data(), params.size(), FACTOR, device, 0);
         if (!ctx) throw std::runtime_error(rsr_last_error());
-        std::vector<uint8_t> out((size_t)in.w * FACTOR * in.h * FACTOR * 4);
+        // the output image lives in page-locked memory: the result's copy back then runs at PCIe speed and overlaps the computation
+        const size_t out_bytes = (size_t)in.w * FACTOR * in.h * FACTOR * 4;
+        uint8_t* out = static_cast<uint8_t*>(rsr_host_alloc(out_bytes));
+        if (!out) { const std::string e = rsr_last_error(); rsr_destroy(ctx); throw std::runtime_error(e); }
         // img_to_data -> graph.forward -> data_to_img(..).to_rgba()   (main.rs:170-175), fused on the device
-        const int rc = rsr_upscale_u8(ctx, in.rgba.data(), in.w, in.h, 4, out.data());
+        const int rc = rsr_upscale_u8(ctx, in.rgba.data(), in.w, in.h, 4, out);
         const std::string err = rc ? rsr_last_error() : "";
         rsr_destroy(ctx);
-        if (rc) throw std::runtime_error(err);
+        if (rc) { rsr_host_free(out); throw std::runtime_error(err); }
         printf(" Writing file...");
         fflush(stdout);
-        rsr_host::write_png_rgba(pos[1], out.data(), in.w * FACTOR, in.h * FACTOR);
+        try {
+            rsr_host::write_png_rgba(pos[1], out, in.w * FACTOR, in.h * FACTOR);
+        } catch (...) {
+            rsr_host_free(out);
+            throw;
+        }
+        rsr_host_free(out);
         printf(" Done\n");
     } catch (const std::exception& e) {
         fprintf(stderr, "\nrusty_sr: %s\n", e.what());  // the reference panics here

@@ -226,6 +226,26 @@ def test_1080p_properties(ups, weights):
     assert np.abs(crop[:99, :879] - out[:99, :879]).max() < 1e-5
 
 
+def test_pinned_host_buffers_from_the_library(R, ups):
+    """rsr_host_alloc / rsr_host_free: page-locked image buffers for hosts that do not link CUDA themselves."""
+    import ctypes
+    L = R._lib.load()
+    u = ups["anime"]
+    img = np.random.default_rng(3).integers(0, 256, size=(33, 45, 3), dtype=np.uint8)
+    n_in, n_out = img.size, 99 * 135 * 4
+    p_in, p_out = L.rsr_host_alloc(n_in), L.rsr_host_alloc(n_out)
+    assert p_in and p_out
+    try:
+        ctypes.memmove(p_in, img.ctypes.data, n_in)
+        R._lib.check(L.rsr_upscale_u8(u._h, ctypes.c_void_p(p_in), 45, 33, 3, ctypes.c_void_p(p_out)))
+        got = np.ctypeslib.as_array(ctypes.cast(p_out, ctypes.POINTER(ctypes.c_uint8)), shape=(99, 135, 4)).copy()
+    finally:
+        L.rsr_host_free(p_in)
+        L.rsr_host_free(p_out)
+    assert np.array_equal(got, u.forward_u8(img))
+    L.rsr_host_free(None)
+
+
 def test_error_paths(R, ups):
     u = ups["anime"]
     with pytest.raises(R.RsrError):
