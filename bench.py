@@ -435,7 +435,7 @@ def bench_config5(R, peaks):
         roof = max(fl / (peaks["bf16_tflops"] * 1e12), by / (peaks["hbm_gbs"] * 1e9)) * 1e3
         rows.append({"C": C, "HW": S, "ms": ms, "tflops_useful": fl / (ms * 1e-3) / 1e12, "gbs_fp32_algorithmic": by / (ms * 1e-3) / 1e9,
                      "roofline_ms": roof, "frac": roof / ms})
-    return {"workload": "3x3 conv, stride 1, zero pad, Cin = Cout = C, fp32 in/out (rsr_conv2d_3x3_f32: fp16 + mxfp8 operands; output blocks of <= 64 channels with row-folded MMAs, wider outputs as blocks of 128)", "rows": rows}
+    return {"workload": "3x3 conv, stride 1, zero pad, Cin = Cout = C, fp32 in/out (rsr_conv2d_3x3_f32: fp16 + mxfp8 operands; output blocks of <= 64 channels with row-folded MMAs, wider outputs as blocks of 128 on CTA pairs)", "rows": rows}
 
 
 def run_ours(args):

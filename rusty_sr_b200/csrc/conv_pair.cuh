@@ -10,6 +10,9 @@
 // pixel tiles (M = 2 x 128) with the weights gathered from both halves, and each CTA's accumulator lands in its
 // own tensor memory.
 //
+// The generic 3x3 convolution (rsr_conv2d_3x3_f32, 128 output channels per launch) runs here too: several input-channel
+// blocks (ConvParams::n_cb) are accumulated per pass, each from its own window of rows, as in conv_strip.cuh.
+//
 // Work split: a cluster owns a (strip, row range) work item like a single CTA does in conv_strip.cuh; the leader
 // takes the upper half of the rows and the peer the lower half, so both walk down the same strip in lock step —
 // same number of passes, same ring slots at every step (the A and B descriptors of a cta_group::2 MMA are
@@ -121,16 +124,22 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(C::NTHREADS, 1) conv
         const uint32_t a_full0 = map_to_cta(smem_u32(a_full), 0);
         uint32_t slot = 0, par = 1;
         while (pair_item_next<C>(p, it, rank, w)) {
-            const int nrows = w.npass * C::R + 2 * C::PH;
-            const int y0 = w.y_b - C::PH;
-            for (int i = 0; i < nrows; ++i) {
-                mbar_wait(&a_empty[slot], par, p.fault, 1);
-                if (elect_one()) {
-                    if (leader) mbar_arrive_expect_tx(&a_full[slot], 2 * C::ROW_BYTES);
-                    tma2_load_4d(smem_u32(sA + slot * C::SLOT), &p.tmA, a_full0 + slot * 8, 0, w.x0 - C::PW, y0 + i, w.img);
+            // n_cb == 1: one sliding window over the item's rows.  n_cb > 1 (generic conv): every (pass, channel block)
+            // segment loads its own window of R + 2*PH rows from plane img * n_cb + cb, as in conv_strip.cuh.
+            const int nseg = p.n_cb == 1 ? 1 : w.npass * p.n_cb;
+            const int nrows = p.n_cb == 1 ? w.npass * C::R + 2 * C::PH : C::R + 2 * C::PH;
+            for (int sg = 0; sg < nseg; ++sg) {
+                const int cb = p.n_cb == 1 ? 0 : sg % p.n_cb;
+                const int y0 = w.y_b - C::PH + (p.n_cb == 1 ? 0 : (sg / p.n_cb) * C::R);
+                for (int i = 0; i < nrows; ++i) {
+                    mbar_wait(&a_empty[slot], par, p.fault, 1);
+                    if (elect_one()) {
+                        if (leader) mbar_arrive_expect_tx(&a_full[slot], 2 * C::ROW_BYTES);
+                        tma2_load_4d(smem_u32(sA + slot * C::SLOT), &p.tmA, a_full0 + slot * 8, 0, w.x0 - C::PW, y0 + i, w.img * p.n_cb + cb);
+                    }
+                    __syncwarp();
+                    if (++slot == C::NR) { slot = 0; par ^= 1; }
                 }
-                __syncwarp();
-                if (++slot == C::NR) { slot = 0; par ^= 1; }
             }
         }
     } else if (warp == 3) {
@@ -139,6 +148,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(C::NTHREADS, 1) conv
         uint32_t st = 0, par = 1;
         while (pair_item_next<C>(p, it, rank, w)) {
             for (int j = 0; j < w.npass; ++j)
+                for (int cb = 0; cb < p.n_cb; ++cb)
                 for (int sp = 0; sp < C::NSTG; ++sp) {
                     mbar_wait(&b_empty[st], par, p.fault, 2);
                     if (elect_one()) {
@@ -147,7 +157,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(C::NTHREADS, 1) conv
                         if (leader) mbar_arrive_expect_tx(&b_full[st], 2 * nt * P::TAP_BYTES);
                         for (int tt = 0; tt < nt; ++tt)
                             tma2_load_2d(smem_u32(sB + st * P::BST + tt * P::TAP_BYTES), &p.tmB, b_full0 + st * 8, 0,
-                                         (t0 + tt) * C::NCOL + (int)rank * P::HB);
+                                         (cb * C::TAPS + t0 + tt) * C::NCOL + (int)rank * P::HB);
                     }
                     __syncwarp();
                     if (++st == C::NBS) { st = 0; par ^= 1; }
@@ -188,7 +198,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(C::NTHREADS, 1) conv
             while (pair_item_next<C>(p, it, rank, w)) {
                 for (int j = 0; j < w.npass; ++j) {
                     mbar_wait_cluster(&t_empty[buf], tpar, p.fault, 3);
-                    const int nnew = j == 0 ? WIN : C::R;
+                    for (int cb = 0; cb < p.n_cb; ++cb) {
+                    // rows this segment adds to the window: all of it for the first pass of an item and for every channel
+                    // block of the generic conv, else R
+                    const int nnew = (j == 0 || p.n_cb > 1) ? WIN : C::R;
                     for (int i = 0; i < nnew; ++i) {
                         mbar_wait(&a_full[wslot], wpar, p.fault, 4);
                         if (++wslot == C::NR) { wslot = 0; wpar ^= 1; }
@@ -223,7 +236,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(C::NTHREADS, 1) conv
                                         #pragma unroll
                                         for (int c = 0; c < C::KC; ++c) {
                                             if (ABL_NO_MMA) continue;
-                                            MM::chunk(d, a_e, b_e, c, 256, C::NCOL, sf, (t | c) != 0 ? 1u : 0u);
+                                            MM::chunk(d, a_e, b_e, c, 256, C::NCOL, sf, (t | c) != 0 ? 1u : (uint32_t)(cb != 0));
                                         }
                                     }
                                     if (tb == C::KW - 1 && ta < NEARLY) {
@@ -238,10 +251,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(C::NTHREADS, 1) conv
                         __syncwarp();
                         if (++bst == C::NBS) { bst = 0; bpar ^= 1; }
                     }
-                    const bool last = j == w.npass - 1;
+                    const bool last = j == w.npass - 1 || p.n_cb > 1;
                     const int n_retire = last ? WIN : C::R;
                     if (elect_one()) {
-                        umma2_commit(&t_full[buf]);
+                        if (cb == p.n_cb - 1) umma2_commit(&t_full[buf]);
                         uint32_t sl = slot0 + NEARLY;
                         if (sl >= C::NR) sl -= C::NR;
                         for (int i = NEARLY; i < n_retire; ++i) {
@@ -253,6 +266,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(C::NTHREADS, 1) conv
                     slot0 += n_retire;
                     if (slot0 >= C::NR) slot0 -= C::NR;
                     if (slot0 >= C::NR) slot0 -= C::NR;
+                    }  // channel blocks
                     buf ^= 1;
                     if (buf == 0) tpar ^= 1;
                 }

@@ -1349,6 +1349,13 @@ extern "C" int rsr_downsample_u8(int device, const uint8_t* in, int w, int h, in
 using CvN32  = ConvCfg<3, 3, 128, 1, 2, 6, 3, 3, 0, 2, 0, 4, false, true, PREC_F16MX>;
 using CvN64  = ConvCfg<3, 3, 128, 2, 2, 8, 3, 2, 0, 2, 0, 4, false, true, PREC_F16MX>;
 using CvN128 = ConvCfg<3, 3, 128, 4, 1, 6, 1, 4, 0, 2, 0, 4, false, false, PREC_F16MX>;
+// the same on CTA pairs (conv_pair.cuh): each CTA holds half of every tap, so an N = 128 MMA reads 4 + 2 KB of operands per
+// 64 tensor cycles instead of 4 + 4 (the shared-memory port's 128 B/cycle) and becomes tensor-bound
+using CvP128 = ConvCfg<3, 3, 128, 4, 1, 6, 1, 4, 0, 2, 0, 4, true, false, PREC_F16MX>;
+
+#ifndef RSR_CONV_N128
+#define RSR_CONV_N128 CvP128   // blocks of 128 output channels on CTA pairs (CvN128: single CTAs)
+#endif
 
 template <int PREC>
 __global__ void __launch_bounds__(256) pack_planes_kernel(const float* __restrict__ x, int W, int H, int Ci,
@@ -1386,6 +1393,7 @@ static int encode_map(PFN_cuTensorMapEncodeTiled_v12000 enc, CUtensorMap* m, CUt
 template <class C>
 static int conv2d_block(PFN_cuTensorMapEncodeTiled_v12000 enc, int num_sms, cudaStream_t st, const uint8_t* planes,
                         const uint8_t* wpack, float* d_out, int W, int H, int Ci, int Co, int co0, int* fault) {
+    constexpr bool PAIR = C::PAIR;
     ConvParams p{};
     p.W = W; p.H = H; p.NIMG = 1; p.row_begin = 0; p.row_end = H; p.fault = fault;
     p.n_cb = Ci / 32;
@@ -1398,7 +1406,7 @@ static int conv2d_block(PFN_cuTensorMapEncodeTiled_v12000 enc, int num_sms, cuda
     {
         cuuint64_t dims[2] = {64, (cuuint64_t)p.n_cb * 9 * C::NCOL};
         cuuint64_t strides[1] = {128};
-        cuuint32_t box[2] = {64, (cuuint32_t)(C::TPS * C::NCOL)};
+        cuuint32_t box[2] = {64, (cuuint32_t)(PAIR ? C::HB : C::TPS * C::NCOL)};   // (pairs load their half of a tap at a time)
         if (int rc = encode_map(enc, &p.tmB, CU_TENSOR_MAP_DATA_TYPE_UINT16, 2, wpack, dims, strides, box)) return rc;
     }
     for (int g = 0; g < C::NG; ++g) {
@@ -1410,9 +1418,15 @@ static int conv2d_block(PFN_cuTensorMapEncodeTiled_v12000 enc, int num_sms, cuda
     }
     p.n_strips = (W + 127) / 128;
     p.total_rowtiles = (long long)p.n_strips * H;
-    const int grid = (int)std::min<long long>(p.total_rowtiles, num_sms);
-    CUDA_TRY(cudaFuncSetAttribute(conv_strip_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
-    conv_strip_kernel<C><<<grid, C::NTHREADS, C::SMEM_BYTES, st>>>(p);
+    if constexpr (PAIR) {
+        const int ncl = (int)std::min<long long>(p.total_rowtiles, num_sms / 2);
+        CUDA_TRY(cudaFuncSetAttribute(conv_pair_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+        if (int rc = launch_kernel(conv_pair_kernel<C>, 2 * ncl, C::NTHREADS, C::SMEM_BYTES, st, true, false, p)) return rc;
+    } else {
+        const int grid = (int)std::min<long long>(p.total_rowtiles, num_sms);
+        CUDA_TRY(cudaFuncSetAttribute(conv_strip_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+        conv_strip_kernel<C><<<grid, C::NTHREADS, C::SMEM_BYTES, st>>>(p);
+    }
     CUDA_TRY(cudaGetLastError());
     return 0;
 }
@@ -1500,7 +1514,7 @@ extern "C" int rsr_conv2d_3x3_f32(int device, const float* x, const float* weigh
         if (it == 1) CV_TRY(cudaEventRecord(e0, st));
         for (size_t b = 0; b < blocks.size(); ++b) {
             const int n = blocks[b].n, co0 = blocks[b].co0;
-            if (n == 128)     rc = conv2d_block<CvN128>(enc, prop.multiProcessorCount, st, d_planes, d_w[b], d_out, w, h, cin, cout, co0, d_fault);
+            if (n == 128)     rc = conv2d_block<RSR_CONV_N128>(enc, prop.multiProcessorCount, st, d_planes, d_w[b], d_out, w, h, cin, cout, co0, d_fault);
             else if (n == 64) rc = conv2d_block<CvN64>(enc, prop.multiProcessorCount, st, d_planes, d_w[b], d_out, w, h, cin, cout, co0, d_fault);
             else              rc = conv2d_block<CvN32>(enc, prop.multiProcessorCount, st, d_planes, d_w[b], d_out, w, h, cin, cout, co0, d_fault);
             if (rc) { cleanup(); return rc; }
