@@ -75,6 +75,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(C::NTHREADS, 1) conv
     const int lane = threadIdx.x & 31;
     const uint32_t rank = cluster_ctarank();
     const bool leader = rank == 0;
+    const int n_cb = C::MCB ? p.n_cb : 1;   // (a compile-time 1 for the sr_net launch: its loops stay as they were)
 
     int pin_g[3], npg = 0;
     #pragma unroll
@@ -126,16 +127,16 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(C::NTHREADS, 1) conv
         while (pair_item_next<C>(p, it, rank, w)) {
             // n_cb == 1: one sliding window over the item's rows.  n_cb > 1 (generic conv): every (pass, channel block)
             // segment loads its own window of R + 2*PH rows from plane img * n_cb + cb, as in conv_strip.cuh.
-            const int nseg = p.n_cb == 1 ? 1 : w.npass * p.n_cb;
-            const int nrows = p.n_cb == 1 ? w.npass * C::R + 2 * C::PH : C::R + 2 * C::PH;
+            const int nseg = n_cb == 1 ? 1 : w.npass * n_cb;
+            const int nrows = n_cb == 1 ? w.npass * C::R + 2 * C::PH : C::R + 2 * C::PH;
             for (int sg = 0; sg < nseg; ++sg) {
-                const int cb = p.n_cb == 1 ? 0 : sg % p.n_cb;
-                const int y0 = w.y_b - C::PH + (p.n_cb == 1 ? 0 : (sg / p.n_cb) * C::R);
+                const int cb = n_cb == 1 ? 0 : sg % n_cb;
+                const int y0 = w.y_b - C::PH + (n_cb == 1 ? 0 : (sg / n_cb) * C::R);
                 for (int i = 0; i < nrows; ++i) {
                     mbar_wait(&a_empty[slot], par, p.fault, 1);
                     if (elect_one()) {
                         if (leader) mbar_arrive_expect_tx(&a_full[slot], 2 * C::ROW_BYTES);
-                        tma2_load_4d(smem_u32(sA + slot * C::SLOT), &p.tmA, a_full0 + slot * 8, 0, w.x0 - C::PW, y0 + i, w.img * p.n_cb + cb);
+                        tma2_load_4d(smem_u32(sA + slot * C::SLOT), &p.tmA, a_full0 + slot * 8, 0, w.x0 - C::PW, y0 + i, w.img * n_cb + cb);
                     }
                     __syncwarp();
                     if (++slot == C::NR) { slot = 0; par ^= 1; }
@@ -148,7 +149,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(C::NTHREADS, 1) conv
         uint32_t st = 0, par = 1;
         while (pair_item_next<C>(p, it, rank, w)) {
             for (int j = 0; j < w.npass; ++j)
-                for (int cb = 0; cb < p.n_cb; ++cb)
+                for (int cb = 0; cb < n_cb; ++cb)
                 for (int sp = 0; sp < C::NSTG; ++sp) {
                     mbar_wait(&b_empty[st], par, p.fault, 2);
                     if (elect_one()) {
@@ -198,10 +199,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(C::NTHREADS, 1) conv
             while (pair_item_next<C>(p, it, rank, w)) {
                 for (int j = 0; j < w.npass; ++j) {
                     mbar_wait_cluster(&t_empty[buf], tpar, p.fault, 3);
-                    for (int cb = 0; cb < p.n_cb; ++cb) {
+                    for (int cb = 0; cb < n_cb; ++cb) {
                     // rows this segment adds to the window: all of it for the first pass of an item and for every channel
                     // block of the generic conv, else R
-                    const int nnew = (j == 0 || p.n_cb > 1) ? WIN : C::R;
+                    const int nnew = (j == 0 || n_cb > 1) ? WIN : C::R;
                     for (int i = 0; i < nnew; ++i) {
                         mbar_wait(&a_full[wslot], wpar, p.fault, 4);
                         if (++wslot == C::NR) { wslot = 0; wpar ^= 1; }
@@ -251,10 +252,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(C::NTHREADS, 1) conv
                         __syncwarp();
                         if (++bst == C::NBS) { bst = 0; bpar ^= 1; }
                     }
-                    const bool last = j == w.npass - 1 || p.n_cb > 1;
+                    const bool last = j == w.npass - 1 || n_cb > 1;
                     const int n_retire = last ? WIN : C::R;
                     if (elect_one()) {
-                        if (cb == p.n_cb - 1) umma2_commit(&t_full[buf]);
+                        if (cb == n_cb - 1) umma2_commit(&t_full[buf]);
                         uint32_t sl = slot0 + NEARLY;
                         if (sl >= C::NR) sl -= C::NR;
                         for (int i = NEARLY; i < n_retire; ++i) {

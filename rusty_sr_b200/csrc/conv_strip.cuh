@@ -140,9 +140,10 @@ struct ConvParams {
 // RAWIN_: the input node is the IMAGE (conv0): four extra warps read the raw pixels and build the x-im2col'd, split rows
 // straight into the shared-memory row ring (no TMA, no intermediate tensor in HBM).
 template <int KH_, int KW_, int RB_, int NG_, int R_, int NR_, int TPS_, int NBS_, int NPIN_, int NOUT_, int SHUF_, int NEPI_ = 4,
-          bool PAIR_ = false, bool FOLD_ = false, int PREC_ = PREC_BF16X3, int OFMT_ = PREC_, bool RAWIN_ = false>
+          bool PAIR_ = false, bool FOLD_ = false, int PREC_ = PREC_BF16X3, int OFMT_ = PREC_, bool RAWIN_ = false, bool MCB_ = false>
 struct ConvCfg {
     static constexpr bool RAWIN = RAWIN_;
+    static constexpr bool MCB = MCB_;                                  // conv_pair_kernel: several input-channel blocks per pass (ConvParams::n_cb)
     static constexpr int NPROD = RAWIN ? 4 : 0;                        // raw-image producer warps (each builds every 4th row of the ring)
     static constexpr bool PAIR = PAIR_;                                // CTA-pair kernel (conv_pair.cuh): half a weight tap per CTA
     // Row-folded MMAs (see the MMA role): the KH vertical taps of one tap column become ONE MMA per input row whose N spans

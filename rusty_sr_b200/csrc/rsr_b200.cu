@@ -1351,7 +1351,7 @@ using CvN64  = ConvCfg<3, 3, 128, 2, 2, 8, 3, 2, 0, 2, 0, 4, false, true, PREC_F
 using CvN128 = ConvCfg<3, 3, 128, 4, 1, 6, 1, 4, 0, 2, 0, 4, false, false, PREC_F16MX>;
 // the same on CTA pairs (conv_pair.cuh): each CTA holds half of every tap, so an N = 128 MMA reads 4 + 2 KB of operands per
 // 64 tensor cycles instead of 4 + 4 (the shared-memory port's 128 B/cycle) and becomes tensor-bound
-using CvP128 = ConvCfg<3, 3, 128, 4, 1, 6, 1, 4, 0, 2, 0, 4, true, false, PREC_F16MX>;
+using CvP128 = ConvCfg<3, 3, 128, 4, 1, 6, 1, 4, 0, 2, 0, 4, true, false, PREC_F16MX, PREC_F16MX, false, true>;
 
 #ifndef RSR_CONV_N128
 #define RSR_CONV_N128 CvP128   // blocks of 128 output channels on CTA pairs (CvN128: single CTAs)
