@@ -655,7 +655,9 @@ def run_ours(args):
                     "unpipelined_call": "rsr_upscale_u8, one synchronous call per frame",
                     "copy_probe": {"d2h_gbs_this_rank": d2h_gbs, "h2d_gbs_this_rank": h2d_gbs,
                                    "d2h_gbs_aggregate": sum(v[0] for v in d2h_all) / 1000.0,
-                                   "note": "pinned 74.6 MB buffers, every rank copying at once; the e2e floor per frame is d2h_bytes / this bandwidth"}},
+                                   "d2h_floor_ms_per_step": (H_LR * W_LR * 9 * 3 / (d2h_gbs * 1e9) * 1e3) if d2h_gbs else None,
+                                   "note": "pinned 74.6 MB buffers, every rank copying at once; d2h_floor = d2h_bytes_per_step / this rank's "
+                                           "bandwidth: the result's way over PCIe bounds the e2e step once the forward pass is as fast as the copy"}},
             "config3": cfg3, "config4": cfg4, "config5": cfg5,
             "gpu_launches": launches[0],
             "clocks": clocks,
