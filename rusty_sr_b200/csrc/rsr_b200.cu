@@ -681,7 +681,7 @@ struct OutSpec {
 // images can pay for a nearly empty extra strip; per strip the fused launch costs FUSED_STRIP_COST of the two split launches
 // (same-box measurements, profiles/README.md).
 #ifndef RSR_FUSED_STRIP_COST
-#define RSR_FUSED_STRIP_COST 0.75
+#define RSR_FUSED_STRIP_COST 0.62   // (0.75 before the fused launch's epilogues were rebuilt; tools/plan_by_width.py, profiles/r03p_*)
 #endif
 static bool use_fused(const rsr_ctx* c, int w) {
     if (c->plan == 1) return true;

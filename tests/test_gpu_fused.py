@@ -40,10 +40,11 @@ def test_launch_plans(pair):
     assert f["anime"].last_launch_count() == 4 and s["anime"].last_launch_count() == 5
 
 
-@pytest.mark.parametrize("width,launches", [(100, 4), (124, 4), (125, 5), (128, 5), (248, 4), (256, 5), (260, 4), (372, 4), (384, 4), (1000, 4)])
+@pytest.mark.parametrize("width,launches", [(100, 4), (124, 4), (125, 5), (128, 5), (248, 4), (256, 4), (260, 4), (372, 4), (384, 4), (1000, 4)])
 def test_default_plan_is_chosen_by_width(R, weights, width, launches):
     """Without a plan flag the middle levels run fused unless the 124-pixel strips of the fused launch waste too much against
-    the 128-pixel strips of the split launches (e.g. BASELINE config 3's 256-wide patches: 3 strips vs 2)."""
+    the 128-pixel strips of the split launches: only W = 125..128 (2 strips vs 1) runs split; BASELINE config 3's 256-wide patches
+    (3 strips vs 2) run fused (tools/plan_by_width.py)."""
     x = noise_image(6, width, width)
     with R.Upscaler(weights["anime"]) as u, R.Upscaler(weights["anime"], flags=R.RSR_FLAG_SPLIT_MID) as s:
         out = u.forward(x)
